@@ -353,9 +353,13 @@ static void edge_row(const Ctx *k, SRow *r, int c, int i, int j, int pt, const d
   point_map(k, c, j, pt, ax, &xc, ay, &yc);
   double dx = e[2] - e[0], dy = e[3] - e[1];
   /* cross = dx*(Y - y1) - (X - x1)*dy */
+  /* scaled by the edge length only: the row value is the signed distance (in metres) of
+   * the point from the edge line, for the rear point and the front corners alike */
+  double len = sqrt(dx * dx + dy * dy);
+  if (len > 0.0) { dx /= len; dy /= len; }
+  double ec = dx * e[1] - e[0] * dy;
   for (int t = 0; t < 8; ++t) r->a[t] = sign * (dx * ay[t] - dy * ax[t]);
-  r->rhs = -sign * (dx * (yc - e[1]) - (xc - e[0]) * dy);
-  srow_normalize(r);
+  r->rhs = -sign * (dx * yc - dy * xc - ec);
 }
 
 /* rows of a rho=0 mode (j,h) that go beyond simple bounds: wedge (2), curvature (2), half-plane (1) */

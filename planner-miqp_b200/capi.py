@@ -1,0 +1,334 @@
+"""ctypes binding of the C ABI in include/miqp_b200.h.
+
+A problem is any object with the attributes of the reference's ModelParameters in flat
+form (N, R, C, O, L, E, scal, safety, safety_slack, car, x0, ref, lim, initial_region,
+possible_region, obs_edges, obs_nedges, obs_soft, env_edges, env_off, frac, poly) -- the
+same field names the OPL data files use (src/model_input_data_source.cpp:180-275).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+DECLARED_SYMBOLS = [
+    "miqp_b200_version", "miqp_b200_default_options", "miqp_b200_create", "miqp_b200_destroy",
+    "miqp_b200_last_error", "miqp_b200_layout", "miqp_b200_sizes", "miqp_b200_assemble",
+    "miqp_b200_evaluate", "miqp_b200_solve_batch", "miqp_b200_batch_upload", "miqp_b200_batch_run",
+    "miqp_b200_batch_fetch", "miqp_b200_run_stats",
+]
+
+
+class MiqpB200Error(RuntimeError):
+    pass
+
+
+class CProblem(C.Structure):
+    _fields_ = (
+        [(n, C.c_int) for n in ("N", "R", "C", "O", "L", "E")]
+        + [(n, C.c_double) for n in (
+            "ts", "min_vel", "max_vel", "total_min_acc", "total_max_acc", "total_min_jerk",
+            "total_max_jerk", "maximum_slack", "w_slack", "w_slack_obs",
+            "min_region_change_speed", "gap_tol", "time_limit")]
+        + [("safety", _dp), ("safety_slack", _dp)]
+        + [(n, _dp) for n in ("w_pos_x", "w_vel_x", "w_acc_x", "w_pos_y", "w_vel_y", "w_acc_y",
+                              "w_jerk_x", "w_jerk_y", "wheelbase", "radius", "x0",
+                              "x_ref", "vx_ref", "y_ref", "vy_ref",
+                              "min_acc_x", "max_acc_x", "min_acc_y", "max_acc_y",
+                              "min_jerk_x", "max_jerk_x", "min_jerk_y", "max_jerk_y")]
+        + [("initial_region", _ip), ("possible_region", _ip), ("obs_edges", _dp),
+           ("obs_nedges", _ip), ("obs_soft", _ip), ("env_edges", _dp), ("env_off", _ip),
+           ("frac", _dp)]
+        + [(n, _dp) for n in ("poly_sint_ub", "poly_sint_lb", "poly_coss_ub", "poly_coss_lb",
+                              "poly_kappa_max", "poly_kappa_min")]
+    )
+
+
+class CLayout(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "C", "N", "R", "O", "L", "E", "K", "base_nwe", "base_ar", "base_rcna", "base_dcc",
+        "base_dcf", "base_so", "base_sof", "base_c2c", "base_sv", "ncols")]
+
+
+class CSizes(C.Structure):
+    _fields_ = [("ncols", C.c_int), ("ncont", C.c_int), ("nbin", C.c_int),
+                ("nrows", C.c_long), ("nnz_struct", C.c_long), ("nnz", C.c_long)]
+
+
+class CSolveInfo(C.Structure):
+    _fields_ = [("status", C.c_int), ("proven", C.c_int), ("objective", C.c_double),
+                ("best_bound", C.c_double), ("gap", C.c_double), ("seconds", C.c_double),
+                ("max_violation", C.c_double), ("nodes", C.c_long), ("qp_iters", C.c_long),
+                ("rounds", C.c_long)]
+
+
+class COptions(C.Structure):
+    _fields_ = [("device", C.c_int), ("nodes_per_round", C.c_int), ("pool_capacity", C.c_int),
+                ("max_rounds", C.c_int), ("verbose", C.c_int)]
+
+
+class CRunStats(C.Structure):
+    _fields_ = [("launches", C.c_long), ("node_kernel_launches", C.c_long), ("nodes", C.c_long),
+                ("qp_iters", C.c_long), ("rounds", C.c_long), ("node_kernel_ms", C.c_double),
+                ("total_ms", C.c_double), ("h2d_bytes", C.c_long), ("d2h_bytes", C.c_long),
+                ("rows_visited", C.c_long)]
+
+
+@dataclass
+class SolveInfo:
+    status: int
+    proven: bool
+    objective: float
+    best_bound: float
+    gap: float
+    seconds: float
+    max_violation: float
+    nodes: int
+    qp_iters: int
+    rounds: int
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "libmiqp_b200.so")
+
+
+_lib = None
+
+
+def load_library():
+    """Loads libmiqp_b200.so; raises if it has not been built (no fallback of any kind)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise MiqpB200Error(f"{path} is missing: run __graft_entry__.build() / planner-miqp_b200/build.py")
+    lib = C.CDLL(path)
+    lib.miqp_b200_version.restype = C.c_char_p
+    lib.miqp_b200_last_error.restype = C.c_char_p
+    lib.miqp_b200_last_error.argtypes = [C.c_void_p]
+    lib.miqp_b200_create.argtypes = [C.POINTER(COptions), C.POINTER(C.c_void_p)]
+    lib.miqp_b200_destroy.argtypes = [C.c_void_p]
+    lib.miqp_b200_layout.argtypes = [C.POINTER(CProblem), C.POINTER(CLayout)]
+    lib.miqp_b200_sizes.argtypes = [C.c_void_p, C.POINTER(CProblem), C.POINTER(CSizes)]
+    lib.miqp_b200_assemble.argtypes = [C.c_void_p, C.POINTER(CProblem), C.POINTER(C.c_long), _ip, _dp, _dp, _dp]
+    lib.miqp_b200_evaluate.argtypes = [C.c_void_p, C.POINTER(CProblem), _dp, _dp, _dp]
+    lib.miqp_b200_solve_batch.argtypes = [C.c_void_p, C.POINTER(CProblem), C.c_int, C.POINTER(_dp),
+                                          C.POINTER(_dp), C.POINTER(CSolveInfo)]
+    lib.miqp_b200_batch_upload.argtypes = [C.c_void_p, C.POINTER(CProblem), C.c_int, C.POINTER(_dp)]
+    lib.miqp_b200_batch_run.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    lib.miqp_b200_batch_fetch.argtypes = [C.c_void_p, C.POINTER(_dp), C.POINTER(CSolveInfo)]
+    lib.miqp_b200_run_stats.argtypes = [C.c_void_p, C.POINTER(CRunStats)]
+    _lib = lib
+    return lib
+
+
+def exported_symbols() -> list[str]:
+    lib = load_library()
+    return [s for s in DECLARED_SYMBOLS if hasattr(lib, s)]
+
+
+def _d(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a, a.ctypes.data_as(_ip)
+
+
+def to_c(p, gap_tol=None, time_limit=None, keep=None) -> CProblem:
+    """Flat problem -> C struct.  Arrays are kept alive in `keep`."""
+    s = CProblem()
+    keep = keep if keep is not None else []
+    s.N, s.R, s.C, s.O, s.L, s.E = p.N, p.R, p.C, p.O, p.L, p.E
+    sc = p.scal
+    s.ts = sc["ts"]
+    s.min_vel, s.max_vel = sc["min_vel_x_y"], sc["max_vel_x_y"]
+    s.total_min_acc, s.total_max_acc = sc["total_min_acc"], sc["total_max_acc"]
+    s.total_min_jerk, s.total_max_jerk = sc["total_min_jerk"], sc["total_max_jerk"]
+    s.maximum_slack = sc["maximum_slack"]
+    s.w_slack, s.w_slack_obs = sc["WEIGHTS_SLACK"], sc["WEIGHTS_SLACK_OBSTACLE"]
+    s.min_region_change_speed = sc["minimum_region_change_speed"]
+    s.gap_tol = sc["relative_mip_gap_tolerance"] if gap_tol is None else gap_tol
+    s.time_limit = sc["max_solution_time"] if time_limit is None else time_limit
+
+    def setd(name, arr):
+        a, ptr = _d(arr)
+        keep.append(a)
+        setattr(s, name, ptr)
+
+    def seti(name, arr):
+        a, ptr = _i(arr)
+        keep.append(a)
+        setattr(s, name, ptr)
+
+    setd("safety", p.safety)
+    setd("safety_slack", p.safety_slack)
+    for cn, key in (("w_pos_x", "WEIGHTS_POS_X"), ("w_vel_x", "WEIGHTS_VEL_X"), ("w_acc_x", "WEIGHTS_ACC_X"),
+                    ("w_pos_y", "WEIGHTS_POS_Y"), ("w_vel_y", "WEIGHTS_VEL_Y"), ("w_acc_y", "WEIGHTS_ACC_Y"),
+                    ("w_jerk_x", "WEIGHTS_JERK_X"), ("w_jerk_y", "WEIGHTS_JERK_Y"),
+                    ("wheelbase", "WheelBase"), ("radius", "CollisionRadius")):
+        setd(cn, p.car[key])
+    setd("x0", p.x0)
+    for k in ("x_ref", "vx_ref", "y_ref", "vy_ref"):
+        setd(k, p.ref[k])
+    for k in ("min_acc_x", "max_acc_x", "min_acc_y", "max_acc_y",
+              "min_jerk_x", "max_jerk_x", "min_jerk_y", "max_jerk_y"):
+        setd(k, p.lim[k])
+    seti("initial_region", p.initial_region)
+    seti("possible_region", p.possible_region)
+    setd("obs_edges", p.obs_edges if np.size(p.obs_edges) else np.zeros(4))
+    seti("obs_nedges", p.obs_nedges if np.size(p.obs_nedges) else np.zeros(1, dtype=np.int32))
+    seti("obs_soft", p.obs_soft if np.size(p.obs_soft) else np.zeros(1, dtype=np.int32))
+    setd("env_edges", p.env_edges if np.size(p.env_edges) else np.zeros(4))
+    seti("env_off", p.env_off)
+    setd("frac", p.frac)
+    for cn, key in (("poly_sint_ub", "POLY_SINT_UB"), ("poly_sint_lb", "POLY_SINT_LB"),
+                    ("poly_coss_ub", "POLY_COSS_UB"), ("poly_coss_lb", "POLY_COSS_LB"),
+                    ("poly_kappa_max", "POLY_KAPPA_AX_MAX"), ("poly_kappa_min", "POLY_KAPPA_AX_MIN")):
+        setd(cn, p.poly[key])
+    return s
+
+
+def layout(p) -> CLayout:
+    keep = []
+    cp = to_c(p, keep=keep)
+    out = CLayout()
+    rc = load_library().miqp_b200_layout(C.byref(cp), C.byref(out))
+    if rc != 0:
+        raise MiqpB200Error(f"miqp_b200_layout failed ({rc})")
+    return out
+
+
+class Solver:
+    """Owns one MiqpB200Solver handle (one CUDA device, one stream)."""
+
+    def __init__(self, device: int = 0, nodes_per_round: int = 0, pool_capacity: int = 0,
+                 max_rounds: int = 0, verbose: int = 0):
+        self._lib = load_library()
+        opt = COptions(device, nodes_per_round, pool_capacity, max_rounds, verbose)
+        h = C.c_void_p()
+        rc = self._lib.miqp_b200_create(C.byref(opt), C.byref(h))
+        if rc != 0 or not h:
+            raise MiqpB200Error("miqp_b200_create failed: no usable CUDA device "
+                                "(this backend has no CPU fallback)")
+        self._h = h
+        self._batch = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.miqp_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self._lib.miqp_b200_last_error(self._h)
+            raise MiqpB200Error(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    # ---- formulation ---------------------------------------------------------------
+    def sizes(self, p) -> CSizes:
+        keep = []
+        cp = to_c(p, keep=keep)
+        out = CSizes()
+        self._check(self._lib.miqp_b200_sizes(self._h, C.byref(cp), C.byref(out)), "miqp_b200_sizes")
+        return out
+
+    def assemble(self, p):
+        """Big-M model rows in OPL order: (rowptr, cols, vals, lo, hi), structural zeros kept."""
+        sz = self.sizes(p)
+        keep = []
+        cp = to_c(p, keep=keep)
+        rowptr = np.zeros(sz.nrows + 1, dtype=np.int64)
+        cols = np.zeros(sz.nnz_struct, dtype=np.int32)
+        vals = np.zeros(sz.nnz_struct)
+        lo = np.zeros(sz.nrows)
+        hi = np.zeros(sz.nrows)
+        self._check(self._lib.miqp_b200_assemble(
+            self._h, C.byref(cp), rowptr.ctypes.data_as(C.POINTER(C.c_long)), cols.ctypes.data_as(_ip),
+            vals.ctypes.data_as(_dp), lo.ctypes.data_as(_dp), hi.ctypes.data_as(_dp)), "miqp_b200_assemble")
+        return rowptr, cols, vals, lo, hi
+
+    def evaluate(self, p, x):
+        keep = []
+        cp = to_c(p, keep=keep)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        obj = C.c_double()
+        viol = C.c_double()
+        self._check(self._lib.miqp_b200_evaluate(self._h, C.byref(cp), x.ctypes.data_as(_dp),
+                                                 C.byref(obj), C.byref(viol)), "miqp_b200_evaluate")
+        return obj.value, viol.value
+
+    # ---- solve ---------------------------------------------------------------------
+    def _pack(self, problems, gap_tol, time_limit, warm):
+        n = len(problems)
+        keep = []
+        arr = (CProblem * n)()
+        for k, p in enumerate(problems):
+            arr[k] = to_c(p, gap_tol, time_limit, keep)
+        warm_arr = None
+        if warm is not None:
+            warm_arr = (_dp * n)()
+            for k, w in enumerate(warm):
+                if w is not None:
+                    a, ptr = _d(w)
+                    keep.append(a)
+                    warm_arr[k] = ptr
+        ncols = [layout(p).ncols for p in problems]
+        return arr, warm_arr, ncols, keep
+
+    def solve_batch(self, problems, gap_tol=None, time_limit=None, warm=None):
+        """Host buffers in, host buffers out (H2D + solve + D2H).  Returns (xs, infos)."""
+        n = len(problems)
+        arr, warm_arr, ncols, keep = self._pack(problems, gap_tol, time_limit, warm)
+        xs = [np.zeros(c) for c in ncols]
+        xptr = (_dp * n)(*[x.ctypes.data_as(_dp) for x in xs])
+        infos = (CSolveInfo * n)()
+        self._check(self._lib.miqp_b200_solve_batch(self._h, arr, n, warm_arr, xptr, infos), "miqp_b200_solve_batch")
+        return xs, [self._info(i) for i in infos]
+
+    def solve(self, p, gap_tol=None, time_limit=None, warm=None):
+        xs, infos = self.solve_batch([p], gap_tol, time_limit, None if warm is None else [warm])
+        return xs[0], infos[0]
+
+    def upload(self, problems, gap_tol=None, time_limit=None, warm=None):
+        n = len(problems)
+        arr, warm_arr, ncols, keep = self._pack(problems, gap_tol, time_limit, warm)
+        self._check(self._lib.miqp_b200_batch_upload(self._h, arr, n, warm_arr), "miqp_b200_batch_upload")
+        self._batch = (n, ncols)
+
+    def run(self) -> float:
+        ms = C.c_float()
+        self._check(self._lib.miqp_b200_batch_run(self._h, C.byref(ms)), "miqp_b200_batch_run")
+        return ms.value
+
+    def fetch(self):
+        n, ncols = self._batch
+        xs = [np.zeros(c) for c in ncols]
+        xptr = (_dp * n)(*[x.ctypes.data_as(_dp) for x in xs])
+        infos = (CSolveInfo * n)()
+        self._check(self._lib.miqp_b200_batch_fetch(self._h, xptr, infos), "miqp_b200_batch_fetch")
+        return xs, [self._info(i) for i in infos]
+
+    def run_stats(self) -> dict:
+        st = CRunStats()
+        self._check(self._lib.miqp_b200_run_stats(self._h, C.byref(st)), "miqp_b200_run_stats")
+        return {n: getattr(st, n) for n, _ in CRunStats._fields_}
+
+    @staticmethod
+    def _info(i: CSolveInfo) -> SolveInfo:
+        return SolveInfo(i.status, bool(i.proven), i.objective, i.best_bound, i.gap, i.seconds,
+                         i.max_violation, i.nodes, i.qp_iters, i.rounds)

@@ -1,0 +1,713 @@
+// bnb.cu -- device-resident branch and bound over a batch of plans.
+//
+// What the reference delegates to cplex.solve() (src/cplex_wrapper.cpp:158-185): a search over
+// the binaries of cplexmodel/*.mod that stops at the CPLEX relative gap
+// |best_bound - incumbent| / (1e-10 + |incumbent|) <= epgap (cplexmodel.mod:8-10).
+//
+// Every plan owns a pool of open nodes in HBM (structure of arrays, fixed capacity, free-slot
+// stack).  One round of the search is two kernels:
+//
+//   bnb_select_kernel  one CTA per plan: releases the slots handed out in the last round,
+//                      snapshots the cutoff from the incumbent, prunes the open list by
+//                      bound, picks the K best nodes (radix select on 64-bit priority keys:
+//                      depth first until an incumbent exists, best bound first afterwards)
+//                      and appends them to the global work list.
+//   bnb_nodes_kernel   persistent warps pull (plan, node) items from the work list; each warp
+//                      solves its node relaxation (node_qp.cuh), scans the relaxed optimum for
+//                      violated disjunctions, and either records an incumbent, or pushes the
+//                      children (one per alternative of the most violated disjunction) onto
+//                      the plan's pool.
+//
+// The host only launches rounds and polls one integer (number of unfinished plans).
+#include "kernels.cuh"
+#include "node_qp.cuh"
+
+namespace miqp {
+
+// ---------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_min_double(double *addr, double v) {
+  unsigned long long *a = reinterpret_cast<unsigned long long *>(addr);
+  unsigned long long old = *a;
+  while (__longlong_as_double((long long)old) > v) {
+    unsigned long long assumed = old;
+    old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+    if (old == assumed) break;
+  }
+}
+
+__device__ __forceinline__ unsigned long long ordered_bits(double v) {
+  long long b = __double_as_longlong(v);
+  unsigned long long u = (unsigned long long)b;
+  return (b < 0) ? ~u : (u | 0x8000000000000000ULL);
+}
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+  return x;
+}
+
+// priority key, smaller = earlier.  Without incumbent: depth first (deepest, then the least
+// violated alternative, then bound); with incumbent: best bound first, then deepest.
+__device__ __forceinline__ unsigned long long node_key(double bound, int depth, int rank, unsigned long long uid, bool have_inc) {
+  unsigned long long d = 1023 - (unsigned long long)(depth > 1023 ? 1023 : depth);  // 10 bits
+  unsigned long long r = (unsigned long long)(rank + 1 > 127 ? 127 : rank + 1);      // 7 bits
+  unsigned long long b = ordered_bits(bound) >> 24;                                   // 40 bits
+  unsigned long long u = uid & 127ULL;                                                // 7 bits
+  if (have_inc) return (b << 24) | (d << 14) | (r << 7) | u;
+  return (d << 54) | (r << 47) | (b << 7) | u;
+}
+
+// ---------------------------------------------------------------------------------------
+// init
+// ---------------------------------------------------------------------------------------
+__global__ void bnb_init_kernel(BnbState st, const DevProb *probs, const unsigned char *warm_dec, const int *has_warm) {
+  const int s = blockIdx.x;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const long pb = (long)s * st.cap;
+  const int nroot = (has_warm && has_warm[s]) ? 2 : 1;
+  // free stack: slots cap-1 .. nroot (top of stack = lowest index first out)
+  for (int k = tid; k < st.cap - nroot; k += nt) st.free_stack[pb + k] = st.cap - 1 - k;
+  unsigned char *d0 = st.dec + (pb + 0) * st.ndec_stride;
+  for (int k = tid; k < st.ndec_stride; k += nt) d0[k] = UNDEC;
+  if (nroot == 2) {
+    unsigned char *d1 = st.dec + (pb + 1) * st.ndec_stride;
+    const unsigned char *wd = warm_dec + (long)s * st.ndec_stride;
+    for (int k = tid; k < st.ndec_stride; k += nt) d1[k] = wd[k];
+  }
+  if (tid == 0) {
+    st.free_cnt[s] = st.cap - nroot;
+    st.bound[pb] = -MQ_INF; st.meta[pb] = make_int2(0, 0); st.uid[pb] = 1ULL;
+    st.open_idx[pb] = 0;
+    if (nroot == 2) {  // MIP start: the fully decided node is evaluated first (cplex_wrapper.cpp:494-639)
+      st.bound[pb + 1] = -MQ_INF; st.meta[pb + 1] = make_int2(1 << 20, 0); st.uid[pb + 1] = 2ULL;
+      st.open_idx[pb + 1] = 1;
+    }
+    st.open_cnt[s] = nroot;
+    st.sel_cnt[s] = 0;
+    st.ub[s] = MQ_INF; st.cutoff[s] = MQ_INF; st.pruned_lb[s] = MQ_INF;
+    st.done[s] = 0; st.lock[s] = 0;
+    st.stat_nodes[s] = 0; st.stat_iters[s] = 0; st.stat_rows[s] = 0;
+    st.inc_uid[s] = ~0ULL;
+    if (s == 0) { *st.work_cnt = 0; *st.work_next = 0; *st.active = 0; *st.err = 0; }
+  }
+}
+
+void launch_bnb_init(const BnbState &st, const DevProb *probs, const unsigned char *warm_dec, const int *has_warm, cudaStream_t s) {
+  bnb_init_kernel<<<st.count, 128, 0, s>>>(st, probs, warm_dec, has_warm);
+}
+
+// ---------------------------------------------------------------------------------------
+// select
+// ---------------------------------------------------------------------------------------
+constexpr int SEL_THREADS = 256;
+
+__device__ __forceinline__ int block_excl_scan(int flag, int *warp_tot /*[8]*/, int &total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned bal = __ballot_sync(FULL, flag);
+  int pre = __popc(bal & ((1u << lane) - 1));
+  if (lane == 0) warp_tot[wid] = __popc(bal);
+  __syncthreads();
+  int off = 0; total = 0;
+  for (int k = 0; k < SEL_THREADS / 32; ++k) { int t = warp_tot[k]; if (k < wid) off += t; total += t; }
+  __syncthreads();
+  return off + pre;
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) bnb_select_kernel(BnbState st, const DevProb *probs, int round_reset) {
+  const int s = blockIdx.x;
+  const int tid = threadIdx.x;
+  __shared__ int warp_tot[SEL_THREADS / 32];
+  __shared__ int s_out, s_free, s_tie, s_wbase;
+  __shared__ int hist[256];
+  __shared__ double s_pruned[SEL_THREADS / 32];
+  __shared__ unsigned long long s_prefix; __shared__ int s_remaining;
+  if (st.done[s]) return;
+  const DevProb &p = probs[s];
+  const long pb = (long)s * st.cap;
+  const int K = st.sel_per_plan;
+  // 1. release the slots processed in the last round
+  const int nsel_prev = st.sel_cnt[s];
+  const int free0 = st.free_cnt[s];
+  for (int k = tid; k < nsel_prev; k += SEL_THREADS) st.free_stack[pb + free0 + k] = st.sel_idx[(long)s * K + k];
+  if (tid == 0) { s_free = free0 + nsel_prev; s_out = 0; s_tie = 0; }
+  // 2. cutoff snapshot
+  const double ub = st.ub[s];
+  const bool have_inc = ub < MQ_INF;
+  const double cutoff = have_inc ? ub - p.gap_tol * fabs(ub) : MQ_INF;
+  __syncthreads();
+  // 3. prune by bound, compute keys, compact in place
+  const int n0 = st.open_cnt[s];
+  double pruned = MQ_INF;
+  for (int base = 0; base < n0; base += SEL_THREADS) {
+    const int idx = base + tid;
+    int slot = -1, keep = 0; unsigned long long key = 0;
+    if (idx < n0) {
+      slot = st.open_idx[pb + idx];
+      const double b = st.bound[pb + slot];
+      keep = (b < cutoff);
+      if (keep) { int2 m = st.meta[pb + slot]; key = node_key(b, m.x, m.y, st.uid[pb + slot], have_inc); }
+      else { pruned = fmin(pruned, b); int pos = atomicAdd(&s_free, 1); st.free_stack[pb + pos] = slot; }
+    }
+    int total; const int rank = block_excl_scan(keep, warp_tot, total);
+    const int out0 = s_out;
+    if (keep) { st.open_idx[pb + out0 + rank] = slot; st.keybuf[pb + out0 + rank] = key; }
+    __syncthreads();
+    if (tid == 0) s_out = out0 + total;
+    __syncthreads();
+  }
+  pruned = warp_min(pruned);
+  if ((tid & 31) == 0) s_pruned[tid >> 5] = pruned;
+  __syncthreads();
+  const int n1 = s_out;
+  if (tid == 0) {
+    double pm = st.pruned_lb[s];
+    for (int k = 0; k < SEL_THREADS / 32; ++k) pm = fmin(pm, s_pruned[k]);
+    st.pruned_lb[s] = pm;
+  }
+  // 4. threshold key of the K best
+  unsigned long long T = ~0ULL; int remaining = n1;  // take everything
+  if (n1 > K) {
+    if (tid == 0) { s_prefix = 0ULL; s_remaining = K; }
+    __syncthreads();
+    for (int pass = 0; pass < 8; ++pass) {
+      const int shift = 56 - 8 * pass;
+      hist[tid] = 0;
+      __syncthreads();
+      const unsigned long long prefix = s_prefix;
+      const unsigned long long himask = (pass == 0) ? 0ULL : (~0ULL << (shift + 8));
+      for (int idx = tid; idx < n1; idx += SEL_THREADS) {
+        const unsigned long long key = st.keybuf[pb + idx];
+        if ((key & himask) == prefix) atomicAdd(&hist[(int)((key >> shift) & 255ULL)], 1);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int rem = s_remaining, b = 0;
+        while (b < 255 && hist[b] < rem) { rem -= hist[b]; ++b; }
+        s_remaining = rem;  // how many to take from bucket b at this digit
+        s_prefix = prefix | ((unsigned long long)b << shift);
+      }
+      __syncthreads();
+    }
+    T = s_prefix; remaining = s_remaining;
+  }
+  // 5. hand the selected nodes to the work list, keep the rest
+  if (tid == 0) s_out = 0;
+  __syncthreads();
+  int nsel_total = 0;
+  for (int base = 0; base < n1; base += SEL_THREADS) {
+    const int idx = base + tid;
+    int slot = -1, sel = 0, keep = 0; unsigned long long key = 0;
+    if (idx < n1) {
+      slot = st.open_idx[pb + idx]; key = st.keybuf[pb + idx];
+      if (key < T) sel = 1;
+      else if (key == T) sel = (atomicAdd(&s_tie, 1) < remaining);
+      keep = !sel;
+    }
+    int tsel; const int rsel = block_excl_scan(sel, warp_tot, tsel);
+    int tkeep; const int rkeep = block_excl_scan(keep, warp_tot, tkeep);
+    const int out0 = s_out;
+    if (sel) st.sel_idx[(long)s * K + nsel_total + rsel] = slot;
+    if (keep) { st.open_idx[pb + out0 + rkeep] = slot; st.keybuf[pb + out0 + rkeep] = key; }
+    nsel_total += tsel;
+    __syncthreads();
+    if (tid == 0) s_out = out0 + tkeep;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    st.open_cnt[s] = s_out;
+    st.sel_cnt[s] = nsel_total;
+    st.free_cnt[s] = s_free;
+    st.cutoff[s] = cutoff;
+    if (nsel_total == 0) st.done[s] = 1;  // frontier exhausted (everything pruned or solved)
+    else { atomicAdd(st.active, 1); s_wbase = atomicAdd(st.work_cnt, nsel_total); }
+  }
+  __syncthreads();
+  if (nsel_total > 0) {
+    const int wb = s_wbase;
+    for (int k = tid; k < nsel_total; k += SEL_THREADS) st.work[wb + k] = make_int2(s, st.sel_idx[(long)s * K + k]);
+  }
+}
+
+__global__ void bnb_round_reset_kernel(BnbState st) { *st.work_cnt = 0; *st.work_next = 0; *st.active = 0; }
+
+void launch_bnb_select(const BnbState &st, const DevProb *probs, cudaStream_t s) {
+  bnb_round_reset_kernel<<<1, 1, 0, s>>>(st);
+  bnb_select_kernel<<<st.count, SEL_THREADS, 0, s>>>(st, probs, 0);
+}
+
+// ---------------------------------------------------------------------------------------
+// scan of a relaxed optimum: implied alternatives and the most violated disjunction
+// ---------------------------------------------------------------------------------------
+struct Branch { int kind, i, o, pt; double viol; int ord; };  // kind: 0 none, 1 mode, 2 env, 3 obs
+
+__device__ __forceinline__ void branch_offer(Branch &b, double viol, int ord, int kind, int i, int o, int pt) {
+  if (viol > b.viol || (viol == b.viol && ord < b.ord)) { b.viol = viol; b.ord = ord; b.kind = kind; b.i = i; b.o = o; b.pt = pt; }
+}
+
+// worst violation of the bounds (and for rho=0 modes the five mode rows) of alternative alt
+__device__ __forceinline__ double mode_alt_violation(const WarpCtx &w, int i, int alt, int jprev, const double y[8]) {
+  const DevProb &p = *w.p;
+  double lo[8], hi[8];
+  const int j = (alt == MODE_FROZEN) ? jprev : (alt >> 2);
+  stage_bounds(w, i, j, alt == MODE_FROZEN, lo, hi);
+  double v = -MQ_INF;
+#pragma unroll
+  for (int t = 1; t < 8; ++t) {
+    if (t == Y_PY) continue;
+    if (t >= 6 && i == w.N - 1) { if (lo[t] > 0.0) v = fmax(v, lo[t]); if (hi[t] < 0.0) v = fmax(v, -hi[t]); continue; }
+    v = fmax(v, y[t] - hi[t]); v = fmax(v, lo[t] - y[t]);
+  }
+  if (alt != MODE_FROZEN) {
+    double a[6], rhs;
+#pragma unroll 1
+    for (int k = 0; k < 5; ++k) {
+      mode_row(w, alt >> 2, alt & 3, k, a, rhs);
+      double gz = -rhs;
+#pragma unroll
+      for (int t = 0; t < 6; ++t) gz += a[t] * y[t];
+      v = fmax(v, gz);
+    }
+  }
+  return v;
+}
+
+__device__ __forceinline__ double edge_violation(const double *et, const double *ft, int pt, double sign, const double y[8]) {
+  double a[6], rhs;
+  edge_row(et, ft, pt, sign, a, rhs);
+  double gz = -rhs;
+#pragma unroll
+  for (int t = 0; t < 6; ++t) gz += a[t] * y[t];
+  return gz;
+}
+
+// returns number of undecided disjunctions; fills w.imp and br
+__device__ __forceinline__ int scan_node(const WarpCtx &w, Branch &br) {
+  const DevProb &p = *w.p;
+  const int lane = w.lane, N = w.N, O = p.O, E = p.E, L = p.L;
+  const double tol = 1e-6;
+  const int ord_stride = 6 + 5 * O;
+  int *bestalt = w.aux, *rdec = w.aux + N, *blame = w.aux + 2 * N;
+  double *bestv = w.auxd;
+  const int nalt = w.I[p.o_nalt];
+  const int *alts = w.I + p.o_alt;
+  for (int k = lane; k < p.ndec_pad; k += 32) w.imp[k] = w.dec[k];
+  // phase 1: best rho=0 alternative per undecided stage (independent of the previous region)
+  for (int i = lane; i < N; i += 32) {
+    if (i == 0 || w.dec[p.off_mode + i] != UNDEC) continue;
+    double y[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) y[t] = w.V[i * V_STRIDE + V_Z + t];
+    int best = -1; double bv = MQ_INF;
+    for (int a = 0; a < nalt; ++a) {
+      const int alt = alts[a];
+      const double v = mode_alt_violation(w, i, alt, 0, y);
+      if (v < bv - 1e-12) { bv = v; best = alt; }
+    }
+    bestalt[i] = best; bestv[i] = bv;
+  }
+  __syncwarp();
+  // phase 2: region chain (all lanes redundantly; the frozen alternative inherits the region)
+  br.kind = 0; br.viol = tol; br.ord = 0x7fffffff; br.i = 0; br.o = 0; br.pt = 0;
+  int und = 0;
+  {
+    int jp = w.I[p.o_initreg] - 1;
+    int root_undec = -1;
+    for (int i = 1; i < N; ++i) {
+      const unsigned char m = w.dec[p.off_mode + i];
+      int j;
+      if (m == UNDEC || (m == MODE_FROZEN && root_undec >= 0)) {
+        double y[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) y[t] = w.V[i * V_STRIDE + V_Z + t];
+        const double vfz = mode_alt_violation(w, i, MODE_FROZEN, jp, y);
+        if (m == UNDEC) {
+          ++und;
+          int best = MODE_FROZEN; double bv = vfz;
+          if (bestalt[i] >= 0 && bestv[i] < vfz - 1e-12) { best = bestalt[i]; bv = bestv[i]; }
+          if (lane == 0) w.imp[p.off_mode + i] = (unsigned char)best;
+          j = (best == MODE_FROZEN) ? jp : (best >> 2);
+          root_undec = (best == MODE_FROZEN && root_undec >= 0) ? root_undec : i;
+          branch_offer(br, bv, i * ord_stride, 1, i, 0, 0);
+        } else {
+          j = jp;  // decided frozen, but its region is only implied: blame the chain root
+          branch_offer(br, vfz, i * ord_stride, 1, root_undec, 0, 0);
+        }
+      } else if (m == MODE_FROZEN) {
+        j = jp;
+      } else { j = m >> 2; root_undec = -1; }
+      if (lane == 0) { w.jeff[i] = j; rdec[i] = (root_undec < 0); blame[i] = root_undec; }
+      jp = j;
+    }
+  }
+  __syncwarp();
+  // phase 3: environment polygons and obstacle edges per point (lane = stage)
+  Branch mine = br;  // every lane starts from the (identical) mode result
+  int und3 = 0;
+  for (int i = lane; i < N; i += 32) {
+    if (i == 0) continue;
+    double y[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) y[t] = w.V[i * V_STRIDE + V_Z + t];
+    const int j = w.jeff[i];
+    const bool region_decided = rdec[i] != 0;
+    const int mode_blame = blame[i];
+    const double *ft = w.D + p.o_fronttab + 12 * j;
+    if (E > 0)
+      for (int pt = 0; pt < 5; ++pt) {
+        const unsigned char d = (E == 1) ? (unsigned char)0 : w.dec[p.off_env + i * 5 + pt];
+        if (d == UNDEC) ++und3;
+        if (d != UNDEC && (pt == 0 || region_decided)) continue;
+        int best = -1; double bv = MQ_INF;
+        for (int e = 0; e < E; ++e) {
+          if (d != UNDEC && e != d) continue;
+          double v = -MQ_INF;
+          for (int ed = w.I[p.o_env_off + e]; ed < w.I[p.o_env_off + e + 1]; ++ed)
+            v = fmax(v, edge_violation(w.D + p.o_envtab + 3 * ed, ft, pt, -1.0, y));
+          if (v < bv) { bv = v; best = e; }
+        }
+        if (E > 1) w.imp[p.off_env + i * 5 + pt] = (unsigned char)best;
+        if (pt > 0 && !region_decided) branch_offer(mine, bv, i * ord_stride + 1 + pt, 1, mode_blame, 0, 0);
+        else branch_offer(mine, bv, i * ord_stride + 1 + pt, 2, i, 0, pt);
+      }
+    for (int o = 0; o < O; ++o)
+      for (int pt = 0; pt < 5; ++pt) {
+        const unsigned char d = w.dec[p.off_obs + (o * N + i) * 5 + pt];
+        if (d == OBS_SOFT) continue;
+        if (d == UNDEC) ++und3;
+        if (d != UNDEC && (pt == 0 || region_decided)) continue;
+        const int ne = w.I[p.o_obs_nedges + o * N + i];
+        int best = -1; double bv = MQ_INF;
+        for (int ed = 0; ed < ne; ++ed) {
+          if (d != UNDEC && ed != d) continue;
+          const double v = edge_violation(w.D + p.o_obstab + 3 * ((o * N + i) * L + ed), ft, pt, 1.0, y);
+          if (v < bv) { bv = v; best = ed; }
+        }
+        if (ne == 0) { bv = -1.0; best = 0; }
+        w.imp[p.off_obs + (o * N + i) * 5 + pt] = (unsigned char)best;
+        if (pt > 0 && !region_decided) branch_offer(mine, bv, i * ord_stride + 6 + o * 5 + pt, 1, mode_blame, 0, 0);
+        else branch_offer(mine, bv, i * ord_stride + 6 + o * 5 + pt, 3, i, o, pt);
+      }
+  }
+  // phase 4: most violated, first in scan order among equals
+  for (int off = 16; off > 0; off >>= 1) {
+    Branch o;
+    o.viol = __shfl_xor_sync(FULL, mine.viol, off); o.ord = __shfl_xor_sync(FULL, mine.ord, off);
+    o.kind = __shfl_xor_sync(FULL, mine.kind, off); o.i = __shfl_xor_sync(FULL, mine.i, off);
+    o.o = __shfl_xor_sync(FULL, mine.o, off); o.pt = __shfl_xor_sync(FULL, mine.pt, off);
+    branch_offer(mine, o.viol, o.ord, o.kind, o.i, o.o, o.pt);
+  }
+  br = mine;
+  und += warp_sum_i(und3);
+  __syncwarp();
+  return und;
+}
+
+// ---------------------------------------------------------------------------------------
+// node kernel
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void copy_bytes16(unsigned char *dst, const unsigned char *src, int nbytes, int lane) {
+  const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+  uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+  for (int k = lane; k < nbytes / 16; k += 32) d4[k] = s4[k];
+}
+
+__device__ __forceinline__ void effective_regions(const WarpCtx &w) {
+  const DevProb &p = *w.p;
+  if (w.lane == 0) {
+    int jp = w.I[p.o_initreg] - 1;
+    w.jeff[0] = jp;
+    for (int i = 1; i < w.N; ++i) {
+      const unsigned char m = w.dec[p.off_mode + i];
+      int j = (m == UNDEC) ? -1 : (m == MODE_FROZEN) ? jp : (m >> 2);
+      w.jeff[i] = j; jp = j;
+    }
+  }
+  __syncwarp();
+}
+
+__host__ __device__ inline int node_smem_dec_offset(int maxN) {
+  int b = maxN * (S_STRIDE + V_STRIDE + 1) * 8;  // S, V, auxd
+  b += maxN * 4 * 4;                             // jeff + aux[3N]
+  return (b + 15) & ~15;
+}
+int node_kernel_smem_per_warp(int maxN, int ndec_stride) {
+  int b = node_smem_dec_offset(maxN) + 2 * ndec_stride + 272;  // dec, imp, alternatives
+  return (b + 15) & ~15;
+}
+
+__global__ void __launch_bounds__(128) bnb_nodes_kernel(BnbState st, const DevProb *probs, const double *dblob,
+                                                        const int *iblob, int smem_per_warp, int maxN) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * (blockDim.x >> 5) + warp;
+  unsigned char *base = smem_raw + (size_t)warp * smem_per_warp;
+  WarpCtx w;
+  w.D = dblob; w.I = iblob; w.lane = lane;
+  w.S = reinterpret_cast<double *>(base);
+  w.V = w.S + maxN * S_STRIDE;
+  w.auxd = w.V + maxN * V_STRIDE;
+  w.jeff = reinterpret_cast<int *>(w.auxd + maxN);
+  w.aux = w.jeff + maxN;
+  w.dec = base + node_smem_dec_offset(maxN);
+  w.imp = w.dec + st.ndec_stride;
+  unsigned char *alts = w.imp + st.ndec_stride;
+  w.npad = st.npad;
+  w.arr_stride = (long)st.kmax * st.npad;
+  w.rs = st.rowscratch + (long)gw * 4 * w.arr_stride;
+  const int nwork = *reinterpret_cast<volatile int *>(st.work_cnt);
+
+  for (;;) {
+    int wi = 0;
+    if (lane == 0) wi = atomicAdd(st.work_next, 1);
+    wi = __shfl_sync(FULL, wi, 0);
+    if (wi >= nwork) break;
+    const int2 item = st.work[wi];
+    const int s = item.x, slot = item.y;
+    const DevProb &p = probs[s];
+    const long pb = (long)s * st.cap;
+    w.p = &p; w.N = p.N;
+    copy_bytes16(w.dec, st.dec + (pb + slot) * st.ndec_stride, st.ndec_stride, lane);
+    const double nbound = st.bound[pb + slot];
+    const int2 nmeta = st.meta[pb + slot];
+    const unsigned long long nuid = st.uid[pb + slot];
+    const double cutoff = st.cutoff[s];
+    __syncwarp();
+    effective_regions(w);
+    // constant cost of SOFT obstacle decisions
+    int nsoft = 0;
+    for (int k = lane; k < 5 * p.O * p.N; k += 32) nsoft += (w.dec[p.off_obs + k] == OBS_SOFT);
+    nsoft = warp_sum_i(nsoft);
+    const double pen = nsoft * p.w_slack_obs;
+
+    PhiEntry e1, e2;
+    e1.setup(p, lane);
+    e2.setup(p, (lane >= 21 && lane < 25) ? lane + 11 : 35);
+    QpResult r = solve_node_qp(w, e1, e2);
+    if (lane == 0) {
+      atomicAdd(&st.stat_nodes[s], 1ULL);
+      atomicAdd(&st.stat_iters[s], (unsigned long long)r.iters);
+      atomicAdd(&st.stat_rows[s], (unsigned long long)r.rows);
+    }
+    if (r.status != 0) continue;  // infeasible: the node dies
+    double obj = r.obj + pen;
+    if (obj < nbound) obj = nbound;  // numerical monotonicity
+    if (obj >= cutoff) { if (lane == 0) atomic_min_double(&st.pruned_lb[s], obj); continue; }
+
+    Branch br;
+    const int und = scan_node(w, br);
+    if (br.kind == 0 && und == 0) {
+      // every disjunction decided and satisfied: incumbent candidate
+      if (lane == 0) { while (atomicCAS(&st.lock[s], 0, 1) != 0) {} }
+      __syncwarp();
+      __threadfence();
+      const double cur = *reinterpret_cast<volatile double *>(&st.ub[s]);
+      const unsigned long long cuid = *reinterpret_cast<volatile unsigned long long *>(&st.inc_uid[s]);
+      if (obj < cur || (obj == cur && nuid < cuid)) {
+        double *iz = st.inc_z + (long)s * st.zstride;
+        for (int i = lane; i < p.N; i += 32)
+          for (int t = 0; t < 8; ++t) iz[i * 8 + t] = w.V[i * V_STRIDE + V_Z + t];
+        copy_bytes16(st.inc_dec + (long)s * st.ndec_stride, w.dec, st.ndec_stride, lane);
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) { st.ub[s] = obj; st.inc_uid[s] = nuid; }
+      }
+      __syncwarp();
+      if (lane == 0) { __threadfence(); atomicExch(&st.lock[s], 0); }
+      continue;
+    }
+    // children
+    int nalt = 0, soff = 0;
+    const unsigned char *src = w.dec;
+    if (br.kind == 0) { nalt = 1; src = w.imp; soff = -1; }
+    else if (br.kind == 1) {
+      soff = p.off_mode + br.i;
+      const int na = w.I[p.o_nalt];
+      nalt = na + 1;
+      if (lane == 0) { alts[0] = MODE_FROZEN; for (int a = 0; a < na; ++a) alts[1 + a] = (unsigned char)w.I[p.o_alt + a]; }
+    } else if (br.kind == 2) {
+      soff = p.off_env + br.i * 5 + br.pt;
+      nalt = p.E;
+      if (lane == 0) for (int e = 0; e < p.E; ++e) alts[e] = (unsigned char)e;
+    } else {
+      soff = p.off_obs + (br.o * p.N + br.i) * 5 + br.pt;
+      const int ne = w.I[p.o_obs_nedges + br.o * p.N + br.i];
+      nalt = ne;
+      if (lane == 0) { for (int e = 0; e < ne; ++e) alts[e] = (unsigned char)e; }
+      if (w.I[p.o_obs_soft + br.o] == 1) { if (lane == 0) alts[ne] = OBS_SOFT; nalt = ne + 1; }
+    }
+    __syncwarp();
+    int fbase = 0, opos = 0, ok = 1;
+    if (lane == 0) {
+      const int old = atomicSub(&st.free_cnt[s], nalt);
+      if (old < nalt) { atomicAdd(&st.free_cnt[s], nalt); atomicExch(st.err, 1); ok = 0; }
+      else { fbase = old - nalt; opos = atomicAdd(&st.open_cnt[s], nalt); }
+    }
+    ok = __shfl_sync(FULL, ok, 0); fbase = __shfl_sync(FULL, fbase, 0); opos = __shfl_sync(FULL, opos, 0);
+    if (!ok) continue;
+    for (int a = 0; a < nalt; ++a) {
+      const int cs = st.free_stack[pb + fbase + a];
+      unsigned char *dst = st.dec + (pb + cs) * st.ndec_stride;
+      copy_bytes16(dst, src, st.ndec_stride, lane);
+      __syncwarp();
+      if (lane == 0) {
+        int rank = 0;
+        if (soff >= 0) { dst[soff] = alts[a]; rank = (alts[a] == w.imp[soff]) ? -1 : a; }
+        st.bound[pb + cs] = obj;
+        st.meta[pb + cs] = make_int2(nmeta.x >= (1 << 20) ? nmeta.x : nmeta.x + 1, rank);
+        st.uid[pb + cs] = mix64(nuid * 0x9e3779b97f4a7c15ULL + (unsigned long long)(a + 1));
+        st.open_idx[pb + opos + a] = cs;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+int node_kernel_max_ctas(int smem_per_cta, int threads) {
+  int nb = 0;
+  cudaFuncSetAttribute(bnb_nodes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_per_cta);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bnb_nodes_kernel, threads, smem_per_cta) != cudaSuccess) return 0;
+  return nb;
+}
+
+int launch_bnb_nodes(const BnbState &st, const DevProb *probs, const double *dblob, const int *iblob,
+                     int smem_per_warp, int warps_per_cta, int ctas, int maxN, cudaStream_t s) {
+  bnb_nodes_kernel<<<ctas, warps_per_cta * 32, (size_t)smem_per_warp * warps_per_cta, s>>>(st, probs, dblob, iblob,
+                                                                                             smem_per_warp, maxN);
+  return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
+// finish: best bound, full column vector of the incumbent (collectRawResults,
+// src/cplex_wrapper.cpp:311-448)
+// ---------------------------------------------------------------------------------------
+__global__ void bnb_finish_kernel(BnbState st, const DevProb *probs, const double *dblob, const int *iblob,
+                                  double *xall, double *best_bound) {
+  const int s = blockIdx.x;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const DevProb &p = probs[s];
+  const double *D = dblob; const int *I = iblob;
+  const long pb = (long)s * st.cap;
+  __shared__ double red[128];
+  __shared__ int jeff_s[8 * 64];
+  // best bound: smallest bound still open or pruned by the gap rule
+  double lb = MQ_INF;
+  const int nopen = st.open_cnt[s];
+  for (int k = tid; k < nopen; k += nt) lb = fmin(lb, st.bound[pb + st.open_idx[pb + k]]);
+  red[tid] = lb;
+  __syncthreads();
+  if (tid == 0) {
+    for (int k = 0; k < nt; ++k) lb = fmin(lb, red[k]);
+    lb = fmin(lb, st.pruned_lb[s]);
+    const double ub = st.ub[s];
+    if (st.done[s] && lb == MQ_INF) lb = ub;  // tree exhausted
+    if (ub < MQ_INF && lb > ub) lb = ub;
+    best_bound[s] = lb;
+  }
+  const double ub = st.ub[s];
+  double *x = xall + p.x_base;
+  for (int k = tid; k < p.ncols; k += nt) x[k] = 0.0;
+  __syncthreads();
+  if (!(ub < MQ_INF)) return;
+  const int C = p.C, N = p.N, R = p.R, E = p.E, O = p.O, L = p.L;
+  const unsigned char *dec = st.inc_dec + (long)s * st.ndec_stride;
+  double *z = st.inc_z + (long)s * st.zstride;
+  // exact trajectory from the jerks (model_region_constraints.mod:11-19)
+  if (tid < C) {
+    const int c = tid;
+    double *zc = z + (long)c * N * 8;
+    for (int t = 0; t < 6; ++t) zc[t] = D[p.o_x0 + 6 * c + t];
+    zc[(N - 1) * 8 + 6] = 0.0; zc[(N - 1) * 8 + 7] = 0.0;
+    for (int i = 0; i + 1 < N; ++i)
+      for (int ax = 0; ax < 2; ++ax) {
+        const double P = zc[i * 8 + 3 * ax], V = zc[i * 8 + 3 * ax + 1], A = zc[i * 8 + 3 * ax + 2], U = zc[i * 8 + 6 + ax];
+        zc[(i + 1) * 8 + 3 * ax] = P + p.ts * V + p.c2 * A + p.c3 * U;
+        zc[(i + 1) * 8 + 3 * ax + 1] = V + p.ts * A + p.c2 * U;
+        zc[(i + 1) * 8 + 3 * ax + 2] = A + p.ts * U;
+      }
+    int jp = I[p.o_initreg + c] - 1;
+    jeff_s[c * 64] = jp;
+    for (int i = 1; i < N; ++i) {
+      const unsigned char m = dec[p.off_mode + c * N + i];
+      int j = (m == UNDEC) ? jp : (m == MODE_FROZEN) ? jp : (m >> 2);
+      jeff_s[c * 64 + i] = j; jp = j;
+    }
+  }
+  __syncthreads();
+  const double vm = p.vm;
+  for (int q = tid; q < C * N; q += nt) {
+    const int c = q / N, i = q % N;
+    const double *y = z + ((long)c * N + i) * 8;
+    const int blk[8] = {B_PX, B_VX, B_AX, B_PY, B_VY, B_AY, B_UX, B_UY};
+    for (int t = 0; t < 8; ++t) x[col_core(p, blk[t], c, i)] = y[t];
+    const int j = jeff_s[c * 64 + i];
+    double fxu, fxl, fyu, fyl;
+    if (i == 0) {
+      fxu = fxl = D[p.o_front0 + 2 * c]; fyu = fyl = D[p.o_front0 + 2 * c + 1];
+    } else {
+      const double *ft = D + p.o_fronttab + 12 * (c * R + j);
+      fxu = y[Y_PX] + (ft[0] + ft[1] * y[Y_VX] + ft[2] * y[Y_VY]);
+      fxl = y[Y_PX] + (ft[3] + ft[4] * y[Y_VX] + ft[5] * y[Y_VY]);
+      fyu = y[Y_PY] + (ft[6] + ft[7] * y[Y_VX] + ft[8] * y[Y_VY]);
+      fyl = y[Y_PY] + (ft[9] + ft[10] * y[Y_VX] + ft[11] * y[Y_VY]);
+    }
+    x[col_core(p, B_XFU, c, i)] = fxu; x[col_core(p, B_XFL, c, i)] = fxl;
+    x[col_core(p, B_YFU, c, i)] = fyu; x[col_core(p, B_YFL, c, i)] = fyl;
+    x[col_ar(p, c, i, j)] = 1.0;
+    if (i > 0) {
+      const unsigned char m = dec[p.off_mode + c * N + i];
+      double b[4] = {(y[Y_VX] <= vm) ? 1.0 : 0.0, (y[Y_VY] <= vm) ? 1.0 : 0.0, (y[Y_VX] >= -vm) ? 1.0 : 0.0, (y[Y_VY] >= -vm) ? 1.0 : 0.0};
+      double rho = 0.0;
+      if (m == MODE_FROZEN) { b[0] = b[1] = b[2] = b[3] = 1.0; rho = 1.0; }
+      else b[m & 3] = 0.0;
+      for (int t = 0; t < 4; ++t) x[col_rcna(p, t, c, i)] = b[t];
+      x[col_rcna(p, 4, c, i)] = rho;
+    }
+    for (int pt = 0; pt < 5; ++pt) {
+      const double PX = (pt == 0) ? y[Y_PX] : ((pt == 1 || pt == 3) ? fxu : fxl);
+      const double PY = (pt == 0) ? y[Y_PY] : ((pt == 1 || pt == 2) ? fyu : fyl);
+      if (E > 0) {
+        int e = (E == 1) ? 0 : dec[p.off_env + (c * N + i) * 5 + pt];
+        if (i == 0 && E > 1) {  // nothing is decided at the fixed initial state: pick the containing polygon
+          double bestv = -MQ_INF; e = 0;
+          for (int ee = 0; ee < E; ++ee) {
+            double mn = MQ_INF;
+            for (int ed = I[p.o_env_off + ee]; ed < I[p.o_env_off + ee + 1]; ++ed) {
+              const double *g = D + p.o_env_edges + 4 * ed;
+              mn = fmin(mn, (g[2] - g[0]) * (PY - g[1]) - (PX - g[0]) * (g[3] - g[1]));
+            }
+            if (mn > bestv) { bestv = mn; e = ee; }
+          }
+        }
+        for (int ee = 0; ee < E; ++ee) x[col_nwe(p, pt, c, ee, i)] = (ee == e) ? 0.0 : 1.0;
+      }
+      for (int o = 0; o < O; ++o) {
+        unsigned char d = dec[p.off_obs + ((c * O + o) * N + i) * 5 + pt];
+        const int ne = I[p.o_obs_nedges + o * N + i];
+        if (i == 0) {
+          double bestv = MQ_INF; d = 0;
+          for (int ed = 0; ed < ne; ++ed) {
+            const double *g = D + p.o_obs_edges + 4 * ((o * N + i) * L + ed);
+            const double cr = (g[2] - g[0]) * (PY - g[1]) - (PX - g[0]) * (g[3] - g[1]);
+            if (cr < bestv) { bestv = cr; d = (unsigned char)ed; }
+          }
+          if (bestv > 1e-9 && I[p.o_obs_soft + o] == 1) d = OBS_SOFT;
+        }
+        // env point order (UU,LU,UL,LL) -> obstacle front index 4-pt (LL,UL,LU,UU)
+        for (int ed = 0; ed < ne; ++ed) {
+          const double v = (d == OBS_SOFT || ed != d) ? 1.0 : 0.0;
+          if (pt == 0) x[col_dcc(p, c, o, i, ed)] = v; else x[col_dcf(p, c, o, i, ed, 4 - pt)] = v;
+        }
+        if (d == OBS_SOFT) { if (pt == 0) x[col_so(p, c, o, i)] = 1.0; else x[col_sof(p, c, o, i, 4 - pt)] = 1.0; }
+      }
+    }
+  }
+}
+
+void launch_bnb_finish(const BnbState &st, const DevProb *probs, const double *dblob, const int *iblob,
+                       double *xall, double *best_bound, cudaStream_t s) {
+  bnb_finish_kernel<<<st.count, 128, 0, s>>>(st, probs, dblob, iblob, xall, best_bound);
+}
+
+}  // namespace miqp

@@ -1,0 +1,62 @@
+// kernels.cuh -- launcher declarations shared by the host driver (solver.cu).
+#pragma once
+#include "dev_problem.cuh"
+
+namespace miqp {
+
+// ---- formulation.cu -------------------------------------------------------------------
+void launch_prepare_tables(DevProb *probs, double *dblob, int *iblob, int count, cudaStream_t st);
+void launch_assemble_rows(const DevProb *probs, const double *dblob, const int *iblob, int count, long max_rows,
+                          long *rowptr, int *cols, double *vals, double *lo, double *hi,
+                          unsigned long long *nnz_count, cudaStream_t st);
+void launch_evaluate(const DevProb *probs, const double *dblob, const int *iblob, int count, long max_rows,
+                     const double *xall, double *max_viol, double *objective, cudaStream_t st);
+
+// ---- bnb.cu ---------------------------------------------------------------------------
+// Device-resident branch and bound state of a batch of plans.
+struct BnbState {
+  int count;            // plans
+  int cap;              // node slots per plan
+  int ndec_stride;      // bytes per node decision vector (max over plans, multiple of 16)
+  int zstride;          // doubles per incumbent trajectory (max C*N*8 + 4*P*N)
+  int kmax;             // row slots per stage (max over plans)
+  int npad;             // stages padded to a multiple of 32 (max over plans)
+  int nwarps;           // resident warps of the node kernel (row scratch slots)
+  int sel_per_plan;     // K: node relaxations taken per plan per round
+  int work_cap;
+  // node pools [count][cap]
+  unsigned char *dec;
+  double *bound;
+  int2 *meta;           // depth, rank
+  unsigned long long *uid;
+  int *open_idx; int *open_cnt;
+  int *free_stack; int *free_cnt;
+  int *sel_idx; int *sel_cnt;      // slots handed to the node kernel in the last round [count][sel_per_plan]
+  unsigned long long *keybuf;      // [count][cap]
+  // per plan
+  double *ub;           // incumbent objective (inf if none)
+  double *cutoff;       // snapshot used by the node kernel in the current round
+  double *pruned_lb;
+  int *done;
+  int *lock;
+  double *inc_z;        // [count][zstride]
+  unsigned char *inc_dec;  // [count][ndec_stride]
+  unsigned long long *inc_uid;  // tie break between equal incumbents (deterministic result)
+  unsigned long long *stat_nodes, *stat_iters, *stat_rows;
+  // round control
+  int2 *work; int *work_cnt; int *work_next; int *active; int *err;
+  double *rowscratch;   // [nwarps][4][kmax][npad]
+};
+
+void launch_bnb_init(const BnbState &st, const DevProb *probs, const unsigned char *warm_dec /* [count][ndec_stride] or null */,
+                     const int *has_warm, cudaStream_t s);
+void launch_bnb_select(const BnbState &st, const DevProb *probs, cudaStream_t s);
+// returns 0 or a cudaError
+int launch_bnb_nodes(const BnbState &st, const DevProb *probs, const double *dblob, const int *iblob,
+                     int smem_per_warp, int warps_per_cta, int ctas, int maxN, cudaStream_t s);
+void launch_bnb_finish(const BnbState &st, const DevProb *probs, const double *dblob, const int *iblob,
+                       double *xall, double *best_bound, cudaStream_t s);
+int node_kernel_smem_per_warp(int maxN, int ndec_stride);
+int node_kernel_max_ctas(int smem_per_cta, int threads);
+
+}  // namespace miqp

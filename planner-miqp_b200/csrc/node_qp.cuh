@@ -1,0 +1,695 @@
+// node_qp.cuh -- one warp solves one node relaxation of the branch and bound.
+//
+// A node fixes a subset of the disjunctions of the cplexmodel .mod files (region + low-speed
+// mode per car-step, model_region_constraints.mod:43-113 / minimum_speed_constraints.mod;
+// environment polygon per point, separating obstacle edge per point,
+// obstacle_environment_constraints.mod; collision side per pair quadruple,
+// agent_collision_constraints.mod).  The decided alternatives contribute their rows without
+// big-M, undecided ones contribute nothing, so the relaxation is a convex QP over the
+// trajectory with the triple-integrator dynamics (model_region_constraints.mod:11-19):
+//
+//     min  sum_i 1/2 z_i' Q_i z_i + c_i' z_i      z_i = (px,vx,ax,py,vy,ay | ux,uy)
+//     s.t. x_{i+1} = A x_i + B u_i,  x_0 given,  u_{N-1} = 0
+//          G_i z_i <= h_i                          (stage-local rows)
+//
+// Solver: Mehrotra predictor-corrector interior point in STAGE space.  Every Newton step is
+// a Riccati sweep over the banded KKT system: lane = stage for everything that is local to
+// a stage (row generation, residuals, Hessian accumulation, step lengths), lanes = matrix
+// entries for the backward Riccati factorisation, and the cheap vector sweeps are done
+// redundantly by all lanes without any synchronisation.  Inequality rows are never stored:
+// their coefficients are regenerated from the small per-plan tables in every pass; only
+// (s, lambda, rp, ds*dl) per row live in a warp-private, L2-resident global scratch laid
+// out [array][slot][stage] so that lanes (stages) access it coalesced.
+//
+// This file handles one car per plan (C == 1); the multi-car kernel couples the cars of a
+// stage through the pair rows and is a separate instantiation.
+#pragma once
+#include "dev_problem.cuh"
+
+namespace miqp {
+
+#define MQ_INF (__longlong_as_double(0x7ff0000000000000LL))
+constexpr unsigned FULL = 0xffffffffu;
+
+// per-stage shared-memory records (strides are odd so that lane = stage accesses are
+// bank-conflict free for 64-bit words)
+constexpr int S_STRIDE = 41;  // [0..20] Pxx packed lower, [21..32] G = Phi_ux (2x6), [33..35] Phi_uu, [36..37] Muu diag, [38..40] Finv
+constexpr int S_G = 21, S_PUU = 33, S_MUU = 36, S_FINV = 38;
+constexpr int V_STRIDE = 41;  // z[8] g[8] dz[8] p[6] nu[6] phiu[2] k[2]
+constexpr int V_Z = 0, V_G = 8, V_DZ = 16, V_P = 24, V_NU = 30, V_PHIU = 36, V_K = 38;
+
+__device__ __forceinline__ int pidx(int a, int b) { return a >= b ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a; }
+
+struct WarpCtx {
+  const DevProb *p;
+  const double *D;
+  const int *I;
+  double *S;            // [N][S_STRIDE]
+  double *V;            // [N][V_STRIDE]
+  unsigned char *dec;   // node decisions
+  unsigned char *imp;   // implied completion (scan)
+  int *jeff;            // effective region per stage (-1 unknown)
+  int *aux;             // [3N] scan tables: best alt, region_decided, blame
+  double *auxd;         // [N] scan: best non-frozen violation
+  double *rs;           // row scratch of this warp
+  long arr_stride;      // kmax * npad
+  int npad;
+  int lane, N;
+};
+
+__device__ __forceinline__ double warp_max(double v) {
+  for (int o = 16; o > 0; o >>= 1) { double t = __shfl_xor_sync(FULL, v, o); v = t > v ? t : v; }
+  return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+  for (int o = 16; o > 0; o >>= 1) { double t = __shfl_xor_sync(FULL, v, o); v = t < v ? t : v; }
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+// bounds of a stage (model_region_constraints.mod:22-39 and the per-region boxes :73-94
+// of the effective region; low-speed box of minimum_speed_constraints.mod when frozen)
+__device__ __forceinline__ void stage_bounds(const WarpCtx &w, int i, int je, bool frozen, double lo[8], double hi[8]) {
+  const DevProb &p = *w.p;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) { lo[t] = -MQ_INF; hi[t] = MQ_INF; }
+  lo[Y_VX] = p.min_vel; hi[Y_VX] = p.max_vel; lo[Y_VY] = p.min_vel;  // vel_y has no upper bound
+  lo[Y_AX] = p.total_min_acc; hi[Y_AX] = p.total_max_acc; lo[Y_AY] = p.total_min_acc; hi[Y_AY] = p.total_max_acc;
+  lo[Y_UX] = p.total_min_jerk; hi[Y_UX] = p.total_max_jerk; lo[Y_UY] = p.total_min_jerk; hi[Y_UY] = p.total_max_jerk;
+  if (je >= 0) {
+    const double *D = w.D;
+    const int q = je;  // car 0
+    lo[Y_UX] = fmax(lo[Y_UX], D[p.o_lim[4] + q]); hi[Y_UX] = fmin(hi[Y_UX], D[p.o_lim[5] + q]);
+    lo[Y_UY] = fmax(lo[Y_UY], D[p.o_lim[6] + q]); hi[Y_UY] = fmin(hi[Y_UY], D[p.o_lim[7] + q]);
+    if (i > 0) {
+      lo[Y_AX] = fmax(lo[Y_AX], D[p.o_lim[0] + q]); hi[Y_AX] = fmin(hi[Y_AX], D[p.o_lim[1] + q]);
+      lo[Y_AY] = fmax(lo[Y_AY], D[p.o_lim[2] + q]); hi[Y_AY] = fmin(hi[Y_AY], D[p.o_lim[3] + q]);
+    }
+  }
+  if (frozen) {
+    const double vm = p.vm;
+    lo[Y_VX] = fmax(lo[Y_VX], -vm); hi[Y_VX] = fmin(hi[Y_VX], vm);
+    lo[Y_VY] = fmax(lo[Y_VY], -vm); hi[Y_VY] = fmin(hi[Y_VY], vm);
+  }
+}
+
+// row of one polygon edge for point pt of the car in region j:
+// sign=+1: cross(P)/len <= 0 (obstacle, chosen edge); sign=-1: cross(P)/len >= 0 (environment)
+// points: 0 rear, 1 (xU,yU), 2 (xL,yU), 3 (xU,yL), 4 (xL,yL)
+__device__ __forceinline__ void edge_row(const double *et, const double *ft, int pt, double sign, double a[6], double &rhs) {
+  const double ex = et[0], ey = et[1], ec = et[2];
+  double xc = 0.0, fx1 = 0.0, fx2 = 0.0, yc = 0.0, fy1 = 0.0, fy2 = 0.0;
+  if (pt > 0) {
+    const double *fx = (pt == 1 || pt == 3) ? ft : ft + 3;
+    const double *fy = (pt == 1 || pt == 2) ? ft + 6 : ft + 9;
+    xc = fx[0]; fx1 = fx[1]; fx2 = fx[2];
+    yc = fy[0]; fy1 = fy[1]; fy2 = fy[2];
+  }
+  a[Y_PX] = -sign * ey; a[Y_VX] = sign * (ex * fy1 - ey * fx1); a[Y_AX] = 0.0;
+  a[Y_PY] = sign * ex;  a[Y_VY] = sign * (ex * fy2 - ey * fx2); a[Y_AY] = 0.0;
+  rhs = -sign * (ex * yc - ey * xc - ec);
+}
+
+// the five rows of a decided rho=0 mode (j,h): wedge (2), curvature (2), speed half plane (1)
+__device__ __forceinline__ void mode_row(const WarpCtx &w, int j, int h, int k, double a[6], double &rhs) {
+  const DevProb &p = *w.p;
+  if (k < 4) {
+    const double *t = w.D + p.o_modetab + 20 * j + 5 * k;
+    a[Y_PX] = 0.0; a[Y_VX] = t[0]; a[Y_AX] = t[1]; a[Y_PY] = 0.0; a[Y_VY] = t[2]; a[Y_AY] = t[3];
+    rhs = t[4];
+  } else {
+    a[Y_PX] = 0.0; a[Y_AX] = 0.0; a[Y_PY] = 0.0; a[Y_AY] = 0.0;
+    a[Y_VX] = (h == 0) ? -1.0 : (h == 2) ? 1.0 : 0.0;   // h: 0 vx>=vm, 1 vy>=vm, 2 vx<=-vm, 3 vy<=-vm
+    a[Y_VY] = (h == 1) ? -1.0 : (h == 3) ? 1.0 : 0.0;
+    rhs = -p.vm;
+  }
+}
+
+// Enumerates the inequality rows of stage i of the node in a fixed slot order.
+// Vis::bound<T>(slot, sgn, rhs):  sgn * y[T] <= rhs ;  Vis::general(slot, a[6], rhs):  a.x <= rhs
+template <class Vis>
+__device__ __forceinline__ void visit_rows(const WarpCtx &w, int i, Vis &v) {
+  const DevProb &p = *w.p;
+  const int N = w.N;
+  const unsigned char m = (i > 0) ? w.dec[p.off_mode + i] : (unsigned char)0;
+  const int je = w.jeff[i];
+  double lo[8], hi[8];
+  stage_bounds(w, i, je, i > 0 && m == MODE_FROZEN, lo, hi);
+  const bool st = (i > 0), ut = (i < N - 1);
+  int slot = 0;
+#define MQ_BND(T, act)                                                        \
+  {                                                                           \
+    if ((act) && hi[T] < MQ_INF) v.template bound<T>(slot, 1.0, hi[T]);       \
+    ++slot;                                                                   \
+    if ((act) && lo[T] > -MQ_INF) v.template bound<T>(slot, -1.0, -lo[T]);    \
+    ++slot;                                                                   \
+  }
+  MQ_BND(Y_VX, st) MQ_BND(Y_AX, st) MQ_BND(Y_VY, st) MQ_BND(Y_AY, st) MQ_BND(Y_UX, ut) MQ_BND(Y_UY, ut)
+#undef MQ_BND
+  if (i == 0) return;
+  double a[6], rhs;
+  if (m != UNDEC && m != MODE_FROZEN) {
+    const int j = m >> 2, h = m & 3;
+#pragma unroll 1
+    for (int k = 0; k < 5; ++k) { mode_row(w, j, h, k, a, rhs); v.general(slot + k, a, rhs); }
+  }
+  slot += 5;
+  const double *ft = w.D + p.o_fronttab + 12 * (je >= 0 ? je : 0);
+  if (p.E > 0) {
+#pragma unroll 1
+    for (int pt = 0; pt < 5; ++pt) {
+      const int e = (p.E == 1) ? 0 : w.dec[p.off_env + i * 5 + pt];
+      const bool act = (e != UNDEC) && (pt == 0 || je >= 0);
+      const int e0 = act ? w.I[p.o_env_off + e] : 0;
+      const int ne = act ? w.I[p.o_env_off + e + 1] - e0 : 0;
+#pragma unroll 1
+      for (int ed = 0; ed < p.maxEnvEdges; ++ed) {
+        if (ed < ne) { edge_row(w.D + p.o_envtab + 3 * (e0 + ed), ft, pt, -1.0, a, rhs); v.general(slot, a, rhs); }
+        ++slot;
+      }
+    }
+  }
+#pragma unroll 1
+  for (int o = 0; o < p.O; ++o)
+#pragma unroll 1
+    for (int pt = 0; pt < 5; ++pt) {
+      const unsigned char d = w.dec[p.off_obs + (o * N + i) * 5 + pt];
+      if (d != UNDEC && d != OBS_SOFT && (pt == 0 || je >= 0)) {
+        edge_row(w.D + p.o_obstab + 3 * ((o * N + i) * p.L + d), ft, pt, 1.0, a, rhs);
+        v.general(slot, a, rhs);
+      }
+      ++slot;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// row passes
+// ---------------------------------------------------------------------------------------
+struct RowIO {
+  double *base;       // rs + i
+  long arr; int npad;
+  __device__ __forceinline__ double &at(int arrk, int slot) const { return base[arrk * arr + (long)slot * npad]; }
+};
+enum { R_S = 0, R_LAM = 1, R_RP = 2, R_DD = 3 };
+
+struct PassInit {  // s = max(h - g.z, 1), lambda = 1
+  RowIO io; double y[8]; int m;
+  template <int T> __device__ __forceinline__ void bound(int slot, double sgn, double rhs) {
+    double sl = rhs - sgn * y[T];
+    io.at(R_S, slot) = sl > 1.0 ? sl : 1.0; io.at(R_LAM, slot) = 1.0; ++m;
+  }
+  __device__ __forceinline__ void general(int slot, const double a[6], double rhs) {
+    double gz = 0.0;
+#pragma unroll
+    for (int t = 0; t < 6; ++t) gz += a[t] * y[t];
+    double sl = rhs - gz;
+    io.at(R_S, slot) = sl > 1.0 ? sl : 1.0; io.at(R_LAM, slot) = 1.0; ++m;
+  }
+};
+
+struct PassA {  // apply pending step, residuals, Hessian and predictor gradient
+  RowIO io; double y[8];
+  double alpha; bool pending;
+  double H[21], Huu[2], gx[8], gl[8];
+  double rpn, musum, lmax; int m;
+  __device__ __forceinline__ void load(int slot, double &s, double &lam) {
+    s = io.at(R_S, slot); lam = io.at(R_LAM, slot);
+    if (pending) { s += alpha * io.at(R_RP, slot); lam += alpha * io.at(R_DD, slot); }
+  }
+  __device__ __forceinline__ void stats(int slot, double s, double lam, double rp) {
+    io.at(R_S, slot) = s; io.at(R_LAM, slot) = lam; io.at(R_RP, slot) = rp;
+    rpn = fmax(rpn, fabs(rp)); musum += s * lam; lmax = fmax(lmax, lam); ++m;
+  }
+  template <int T> __device__ __forceinline__ void bound(int slot, double sgn, double rhs) {
+    double s, lam; load(slot, s, lam);
+    double rp = sgn * y[T] + s - rhs;
+    double wgt = lam / s;
+    if (T < 6) H[T * (T + 1) / 2 + T] += wgt; else Huu[T - 6] += wgt;
+    gx[T] += sgn * (wgt * rp); gl[T] += sgn * lam;
+    stats(slot, s, lam, rp);
+  }
+  __device__ __forceinline__ void general(int slot, const double a[6], double rhs) {
+    double s, lam; load(slot, s, lam);
+    double gz = 0.0;
+#pragma unroll
+    for (int t = 0; t < 6; ++t) gz += a[t] * y[t];
+    double rp = gz + s - rhs;
+    double wgt = lam / s;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      double wa = wgt * a[r];
+#pragma unroll
+      for (int c = 0; c <= r; ++c) H[r * (r + 1) / 2 + c] += wa * a[c];
+    }
+    double wr = wgt * rp;
+#pragma unroll
+    for (int t = 0; t < 6; ++t) { gx[t] += a[t] * wr; gl[t] += a[t] * lam; }
+    stats(slot, s, lam, rp);
+  }
+};
+
+struct PassD {  // affine step: ratios and the three sums that give mu_aff for any step length
+  RowIO io; double d[8];
+  double amin, s1, s2;
+  __device__ __forceinline__ void row(int slot, double gd) {
+    double s = io.at(R_S, slot), lam = io.at(R_LAM, slot), rp = io.at(R_RP, slot);
+    double wgt = lam / s;
+    double dsa = -rp - gd;
+    double dla = -lam - wgt * dsa;
+    if (dsa < 0.0) amin = fmin(amin, -s / dsa);
+    if (dla < 0.0) amin = fmin(amin, -lam / dla);
+    s1 += s * dla + lam * dsa; s2 += dsa * dla;
+    io.at(R_DD, slot) = dsa * dla;
+  }
+  template <int T> __device__ __forceinline__ void bound(int slot, double sgn, double) { row(slot, sgn * d[T]); }
+  __device__ __forceinline__ void general(int slot, const double a[6], double) {
+    double gd = 0.0;
+#pragma unroll
+    for (int t = 0; t < 6; ++t) gd += a[t] * d[t];
+    row(slot, gd);
+  }
+};
+
+struct PassE {  // corrector gradient
+  RowIO io; double sigmu; double gx[8];
+  __device__ __forceinline__ double coef(int slot) {
+    double s = io.at(R_S, slot), lam = io.at(R_LAM, slot), rp = io.at(R_RP, slot), dd = io.at(R_DD, slot);
+    return (lam * rp - (dd - sigmu)) / s;
+  }
+  template <int T> __device__ __forceinline__ void bound(int slot, double sgn, double) { gx[T] += sgn * coef(slot); }
+  __device__ __forceinline__ void general(int slot, const double a[6], double) {
+    double cf = coef(slot);
+#pragma unroll
+    for (int t = 0; t < 6; ++t) gx[t] += a[t] * cf;
+  }
+};
+
+struct PassG {  // final step: ds, dl (stored in the rp / dd slots) and the step length
+  RowIO io; double d[8]; double sigmu; double amin;
+  __device__ __forceinline__ void row(int slot, double gd) {
+    double s = io.at(R_S, slot), lam = io.at(R_LAM, slot), rp = io.at(R_RP, slot), dd = io.at(R_DD, slot);
+    double ds = -rp - gd;
+    double rc = s * lam + dd - sigmu;
+    double dl = -(rc + lam * ds) / s;
+    if (ds < 0.0) amin = fmin(amin, -s / ds);
+    if (dl < 0.0) amin = fmin(amin, -lam / dl);
+    io.at(R_RP, slot) = ds; io.at(R_DD, slot) = dl;
+  }
+  template <int T> __device__ __forceinline__ void bound(int slot, double sgn, double) { row(slot, sgn * d[T]); }
+  __device__ __forceinline__ void general(int slot, const double a[6], double) {
+    double gd = 0.0;
+#pragma unroll
+    for (int t = 0; t < 6; ++t) gd += a[t] * d[t];
+    row(slot, gd);
+  }
+};
+
+struct PassViol {  // worst primal violation of the current point
+  double y[8]; double worst;
+  template <int T> __device__ __forceinline__ void bound(int, double sgn, double rhs) { worst = fmax(worst, sgn * y[T] - rhs); }
+  __device__ __forceinline__ void general(int, const double a[6], double rhs) {
+    double gz = 0.0;
+#pragma unroll
+    for (int t = 0; t < 6; ++t) gz += a[t] * y[t];
+    worst = fmax(worst, gz - rhs);
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// Riccati sweeps
+// ---------------------------------------------------------------------------------------
+// column a of [A B] (6x8): rows 3*axis .. 3*axis+cnt-1 with coefficients cf[]
+__device__ __forceinline__ void ab_column(const DevProb &p, int a, int &row0, int &cnt, double cf[3]) {
+  if (a < 6) {
+    const int o = a % 3;
+    row0 = (a / 3) * 3; cnt = o + 1;
+    // T = [[1,ts,c2],[0,1,ts],[0,0,1]]: column o = (T[0][o], .., T[o][o])
+    cf[0] = (o == 0) ? 1.0 : (o == 1) ? p.ts : p.c2;
+    cf[1] = (o == 1) ? 1.0 : p.ts;
+    cf[2] = 1.0;
+  } else {
+    row0 = (a - 6) * 3; cnt = 3;
+    cf[0] = p.c3; cf[1] = p.c2; cf[2] = p.ts;
+  }
+}
+
+struct PhiEntry {  // one entry (a,b) of Phi = M + [A B]' P [A B]
+  int a, b, n;
+  int pi[9]; double cf[9];
+  __device__ __forceinline__ void setup(const DevProb &p, int e) {
+    if (e < 21) { a = 0; while ((a + 1) * (a + 2) / 2 <= e) ++a; b = e - a * (a + 1) / 2; }
+    else if (e < 33) { a = 6 + (e - 21) / 6; b = (e - 21) % 6; }
+    else { a = (e == 33) ? 6 : 7; b = (e == 35) ? 7 : 6; }
+    int ra, ca, rb, cb; double fa[3], fb[3];
+    ab_column(p, a, ra, ca, fa); ab_column(p, b, rb, cb, fb);
+    n = ca * cb;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int l = 0; l < 3; ++l) {
+        const bool on = (k < ca && l < cb);
+        pi[k * 3 + l] = on ? pidx(ra + k, rb + l) : 0;
+        cf[k * 3 + l] = on ? fa[k] * fb[l] : 0.0;
+      }
+  }
+  __device__ __forceinline__ double eval(const double *P) const {
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) v += cf[k] * P[pi[k]];
+    return v;
+  }
+};
+
+// Backward factorisation + predictor vector.  On return S_i holds P_i, G_i, Finv_i and V_i
+// holds p_i, k_i for every stage.
+__device__ __forceinline__ void riccati_factor(const WarpCtx &w, const PhiEntry &e1, const PhiEntry &e2) {
+  const DevProb &p = *w.p;
+  const int lane = w.lane, N = w.N;
+  // terminal stage: P = Mxx (in place), p = g_x
+  if (lane < 6) w.V[(N - 1) * V_STRIDE + V_P + lane] = w.V[(N - 1) * V_STRIDE + V_G + lane];
+  __syncwarp();
+  int prow0 = 0, pcnt = 0; double pcf[3] = {0, 0, 0};
+  if (lane < 8) ab_column(p, lane, prow0, pcnt, pcf);
+  for (int i = N - 2; i >= 0; --i) {
+    double *Si = w.S + i * S_STRIDE, *Vi = w.V + i * V_STRIDE;
+    const double *Pn = w.S + (i + 1) * S_STRIDE, *pn = w.V + (i + 1) * V_STRIDE + V_P;
+    // phase 1: Phi entries
+    double phi1 = e1.eval(Pn);
+    if (lane < 21) phi1 += Si[lane];                       // Mxx
+    else {                                                 // lanes 21..31: entries 21..31 of G
+      Si[lane] = phi1;                                     // M_ux = 0
+    }
+    double phix = 0.0;
+    if (lane < 8) {                                        // phi = g + [A B]' p_next
+      double v = Vi[V_G + lane];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) if (k < pcnt) v += pcf[k] * pn[prow0 + k];
+      if (lane < 6) phix = v; else Vi[V_PHIU + lane - 6] = v;
+    }
+    if (lane >= 21 && lane < 25) {                         // entries 32..35
+      double phi2 = e2.eval(Pn);
+      const int e = lane + 11;
+      if (e == 33) phi2 += Si[S_MUU]; else if (e == 35) phi2 += Si[S_MUU + 1];
+      Si[e] = phi2;
+    }
+    __syncwarp();
+    // phase 2: Finv, P_i, p_i, k_i
+    const double f00 = Si[S_PUU], f10 = Si[S_PUU + 1], f11 = Si[S_PUU + 2];
+    const double idet = 1.0 / (f00 * f11 - f10 * f10);
+    const double i00 = f11 * idet, i10 = -f10 * idet, i11 = f00 * idet;
+    const double pu0 = Vi[V_PHIU], pu1 = Vi[V_PHIU + 1];
+    const double k0 = -(i00 * pu0 + i10 * pu1), k1 = -(i10 * pu0 + i11 * pu1);
+    if (lane < 21) {
+      const double g0a = Si[S_G + e1.a], g1a = Si[S_G + 6 + e1.a], g0b = Si[S_G + e1.b], g1b = Si[S_G + 6 + e1.b];
+      const double w0 = i00 * g0b + i10 * g1b, w1 = i10 * g0b + i11 * g1b;
+      Si[lane] = phi1 - (g0a * w0 + g1a * w1);
+    }
+    if (lane < 6) Vi[V_P + lane] = phix + Si[S_G + lane] * k0 + Si[S_G + 6 + lane] * k1;
+    if (lane == 31) { Si[S_FINV] = i00; Si[S_FINV + 1] = i10; Si[S_FINV + 2] = i11; Vi[V_K] = k0; Vi[V_K + 1] = k1; }
+    __syncwarp();
+  }
+}
+
+// vector-only backward sweep with a new gradient (V_G), all lanes redundantly
+__device__ __forceinline__ void riccati_vector(const WarpCtx &w) {
+  const DevProb &p = *w.p;
+  const int N = w.N;
+  const double ts = p.ts, c2 = p.c2, c3 = p.c3;
+  double pn[6];
+#pragma unroll
+  for (int t = 0; t < 6; ++t) pn[t] = w.V[(N - 1) * V_STRIDE + V_G + t];
+  if (w.lane < 6) w.V[(N - 1) * V_STRIDE + V_P + w.lane] = w.V[(N - 1) * V_STRIDE + V_G + w.lane];
+  for (int i = N - 2; i >= 0; --i) {
+    const double *Si = w.S + i * S_STRIDE;
+    double *Vi = w.V + i * V_STRIDE;
+    double phi[8];
+#pragma unroll
+    for (int ax = 0; ax < 2; ++ax) {
+      const double pp = pn[3 * ax], pv = pn[3 * ax + 1], pa = pn[3 * ax + 2];
+      phi[3 * ax] = Vi[V_G + 3 * ax] + pp;
+      phi[3 * ax + 1] = Vi[V_G + 3 * ax + 1] + ts * pp + pv;
+      phi[3 * ax + 2] = Vi[V_G + 3 * ax + 2] + c2 * pp + ts * pv + pa;
+      phi[6 + ax] = Vi[V_G + 6 + ax] + c3 * pp + c2 * pv + ts * pa;
+    }
+    const double i00 = Si[S_FINV], i10 = Si[S_FINV + 1], i11 = Si[S_FINV + 2];
+    const double k0 = -(i00 * phi[6] + i10 * phi[7]), k1 = -(i10 * phi[6] + i11 * phi[7]);
+#pragma unroll
+    for (int t = 0; t < 6; ++t) pn[t] = phi[t] + Si[S_G + t] * k0 + Si[S_G + 6 + t] * k1;
+#pragma unroll
+    for (int t = 0; t < 6; ++t) if (w.lane == t) Vi[V_P + t] = pn[t];
+    if (w.lane == 6) { Vi[V_K] = k0; Vi[V_K + 1] = k1; }
+  }
+  __syncwarp();
+}
+
+// forward sweep, all lanes redundantly; writes dz_i (V_DZ)
+__device__ __forceinline__ void riccati_forward(const WarpCtx &w) {
+  const DevProb &p = *w.p;
+  const int N = w.N;
+  const double ts = p.ts, c2 = p.c2, c3 = p.c3;
+  double dx[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < N; ++i) {
+    double *Vi = w.V + i * V_STRIDE;
+    double du0 = 0.0, du1 = 0.0;
+    if (i < N - 1) {
+      const double *Si = w.S + i * S_STRIDE;
+      double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+      for (int t = 0; t < 6; ++t) { t0 += Si[S_G + t] * dx[t]; t1 += Si[S_G + 6 + t] * dx[t]; }
+      const double i00 = Si[S_FINV], i10 = Si[S_FINV + 1], i11 = Si[S_FINV + 2];
+      du0 = Vi[V_K] - (i00 * t0 + i10 * t1);
+      du1 = Vi[V_K + 1] - (i10 * t0 + i11 * t1);
+    }
+#pragma unroll
+    for (int t = 0; t < 6; ++t) if (w.lane == t) Vi[V_DZ + t] = dx[t];
+    if (w.lane == 6) Vi[V_DZ + 6] = du0;
+    if (w.lane == 7) Vi[V_DZ + 7] = du1;
+#pragma unroll
+    for (int ax = 0; ax < 2; ++ax) {
+      const double P = dx[3 * ax], Vv = dx[3 * ax + 1], A = dx[3 * ax + 2], U = ax ? du1 : du0;
+      dx[3 * ax] = P + ts * Vv + c2 * A + c3 * U;
+      dx[3 * ax + 1] = Vv + ts * A + c2 * U;
+      dx[3 * ax + 2] = A + ts * U;
+    }
+  }
+  __syncwarp();
+}
+
+struct QpResult {
+  int status;     // 0 optimal, 1 infeasible
+  int iters;
+  double obj;     // without soft-decision penalties
+  long rows;      // active rows x iterations (work counter)
+};
+
+// Solves the node QP of w.dec.  On success V_Z holds the optimal stage vectors.
+__device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEntry &e1, const PhiEntry &e2) {
+  const DevProb &p = *w.p;
+  const double *D = w.D;
+  const int lane = w.lane, N = w.N;
+  QpResult res; res.status = 1; res.iters = 0; res.obj = 0.0; res.rows = 0;
+
+  // trivially infeasible boxes (build_node_qp of the oracle)
+  int bad = 0;
+  for (int i = lane; i < N; i += 32) {
+    const unsigned char m = (i > 0) ? w.dec[p.off_mode + i] : (unsigned char)0;
+    double lo[8], hi[8];
+    stage_bounds(w, i, w.jeff[i], i > 0 && m == MODE_FROZEN, lo, hi);
+#pragma unroll
+    for (int t = 1; t < 8; ++t) {
+      if (t == Y_PY) continue;
+      if (i == 0 && t < 6) continue;
+      if (lo[t] > hi[t] + 1e-12) bad = 1;
+      if (i == N - 1 && t >= 6 && (lo[t] > 1e-9 || hi[t] < -1e-9)) bad = 1;
+    }
+  }
+  if (__any_sync(FULL, bad)) return res;
+
+  // start: zero jerk (free response), s = max(h - g.z, 1), lambda = 1, nu = 0
+  const double x0[6] = {D[p.o_x0], D[p.o_x0 + 1], D[p.o_x0 + 2], D[p.o_x0 + 3], D[p.o_x0 + 4], D[p.o_x0 + 5]};
+  double cn = 0.0;
+  for (int i = lane; i < N; i += 32) {
+    double *Vi = w.V + i * V_STRIDE;
+    const double t = i * p.ts;
+#pragma unroll
+    for (int ax = 0; ax < 2; ++ax) {
+      const double P = x0[3 * ax], Vv = x0[3 * ax + 1], A = x0[3 * ax + 2];
+      Vi[V_Z + 3 * ax] = P + t * Vv + 0.5 * t * t * A;
+      Vi[V_Z + 3 * ax + 1] = Vv + t * A;
+      Vi[V_Z + 3 * ax + 2] = A;
+    }
+    Vi[V_Z + 6] = 0.0; Vi[V_Z + 7] = 0.0;
+#pragma unroll
+    for (int t6 = 0; t6 < 6; ++t6) Vi[V_NU + t6] = 0.0;
+    const double *cst = D + p.o_cost + 16 * i;
+#pragma unroll
+    for (int t8 = 0; t8 < 8; ++t8) cn = fmax(cn, fabs(cst[8 + t8]));
+  }
+  cn = warp_max(cn);
+  __syncwarp();
+  for (int i = lane; i < N; i += 32) {
+    PassInit v; v.io = RowIO{w.rs + i, w.arr_stride, w.npad}; v.m = 0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) v.y[t] = w.V[i * V_STRIDE + V_Z + t];
+    visit_rows(w, i, v);
+  }
+
+  double alpha = 0.0; bool pending = false;
+  int status = 2, stall = 0, it = 0;
+  for (it = 0; it < 100; ++it) {
+    // ---- pass A ----
+    double rpn = 0.0, musum = 0.0, lmax = 0.0, rdn = 0.0; int m = 0;
+    for (int i = lane; i < N; i += 32) {
+      double *Vi = w.V + i * V_STRIDE, *Si = w.S + i * S_STRIDE;
+      PassA v; v.io = RowIO{w.rs + i, w.arr_stride, w.npad}; v.alpha = alpha; v.pending = pending;
+      v.rpn = 0.0; v.musum = 0.0; v.lmax = 0.0; v.m = 0;
+#pragma unroll
+      for (int t = 0; t < 21; ++t) v.H[t] = 0.0;
+      v.Huu[0] = v.Huu[1] = 0.0;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) { v.y[t] = Vi[V_Z + t]; v.gx[t] = 0.0; v.gl[t] = 0.0; }
+      visit_rows(w, i, v);
+      const double *cst = D + p.o_cost + 16 * i;
+      // stage Hessian and predictor gradient
+#pragma unroll
+      for (int t = 0; t < 6; ++t) v.H[t * (t + 1) / 2 + t] += cst[t];
+#pragma unroll
+      for (int t = 0; t < 21; ++t) Si[t] = v.H[t];
+      Si[S_MUU] = v.Huu[0] + cst[6] + 1e-10; Si[S_MUU + 1] = v.Huu[1] + cst[7] + 1e-10;
+      double q[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) { q[t] = cst[t] * v.y[t] + cst[8 + t]; Vi[V_G + t] = q[t] + v.gx[t]; }
+      // dual residual: q + G'lambda + [A' nu_{i+1} - nu_i ; B' nu_{i+1}]
+      double nn[6] = {0, 0, 0, 0, 0, 0};
+      if (i + 1 < N) {
+#pragma unroll
+        for (int t = 0; t < 6; ++t) nn[t] = w.V[(i + 1) * V_STRIDE + V_NU + t];
+      }
+      if (i > 0) {
+#pragma unroll
+        for (int ax = 0; ax < 2; ++ax) {
+          const double np_ = nn[3 * ax], nv = nn[3 * ax + 1], na = nn[3 * ax + 2];
+          rdn = fmax(rdn, fabs(q[3 * ax] + v.gl[3 * ax] + np_ - Vi[V_NU + 3 * ax]));
+          rdn = fmax(rdn, fabs(q[3 * ax + 1] + v.gl[3 * ax + 1] + p.ts * np_ + nv - Vi[V_NU + 3 * ax + 1]));
+          rdn = fmax(rdn, fabs(q[3 * ax + 2] + v.gl[3 * ax + 2] + p.c2 * np_ + p.ts * nv + na - Vi[V_NU + 3 * ax + 2]));
+        }
+      }
+      if (i < N - 1) {
+#pragma unroll
+        for (int ax = 0; ax < 2; ++ax)
+          rdn = fmax(rdn, fabs(q[6 + ax] + v.gl[6 + ax] + p.c3 * nn[3 * ax] + p.c2 * nn[3 * ax + 1] + p.ts * nn[3 * ax + 2]));
+      }
+      rpn = fmax(rpn, v.rpn); musum += v.musum; lmax = fmax(lmax, v.lmax); m += v.m;
+    }
+    pending = false;
+    rpn = warp_max(rpn); rdn = warp_max(rdn); lmax = warp_max(lmax); musum = warp_sum(musum); m = warp_sum_i(m);
+    res.rows += m;
+    const double mu = (m > 0) ? musum / m : 0.0;
+    __syncwarp();
+    if (rpn <= 1e-9 && rdn <= 1e-8 * (1.0 + cn) && mu <= 1e-10) { status = 0; break; }
+    if (lmax > 1e13) { status = 1; break; }
+    // ---- predictor ----
+    riccati_factor(w, e1, e2);
+    riccati_forward(w);
+    double amin = 1.0, s1 = 0.0, s2 = 0.0;
+    for (int i = lane; i < N; i += 32) {
+      PassD v; v.io = RowIO{w.rs + i, w.arr_stride, w.npad}; v.amin = 1.0; v.s1 = 0.0; v.s2 = 0.0;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) v.d[t] = w.V[i * V_STRIDE + V_DZ + t];
+      visit_rows(w, i, v);
+      amin = fmin(amin, v.amin); s1 += v.s1; s2 += v.s2;
+    }
+    amin = warp_min(amin); s1 = warp_sum(s1); s2 = warp_sum(s2);
+    double sigma = 0.0;
+    if (m > 0 && mu > 0.0) {
+      const double mu_aff = (musum + amin * s1 + amin * amin * s2) / m;
+      const double r = mu_aff / mu;
+      sigma = r * r * r;
+      if (sigma > 1.0) sigma = 1.0;
+      if (sigma < 0.0) sigma = 0.0;
+    }
+    const double sigmu = sigma * mu;
+    // ---- corrector ----
+    for (int i = lane; i < N; i += 32) {
+      double *Vi = w.V + i * V_STRIDE;
+      PassE v; v.io = RowIO{w.rs + i, w.arr_stride, w.npad}; v.sigmu = sigmu;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) v.gx[t] = 0.0;
+      visit_rows(w, i, v);
+      const double *cst = D + p.o_cost + 16 * i;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) Vi[V_G + t] = cst[t] * Vi[V_Z + t] + cst[8 + t] + v.gx[t];
+    }
+    __syncwarp();
+    riccati_vector(w);
+    riccati_forward(w);
+    amin = 1e300;
+    for (int i = lane; i < N; i += 32) {
+      PassG v; v.io = RowIO{w.rs + i, w.arr_stride, w.npad}; v.sigmu = sigmu; v.amin = 1e300;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) v.d[t] = w.V[i * V_STRIDE + V_DZ + t];
+      visit_rows(w, i, v);
+      amin = fmin(amin, v.amin);
+    }
+    amin = warp_min(amin);
+    alpha = 0.995 * amin;
+    if (alpha > 1.0) alpha = 1.0;
+    if (!(alpha >= 0.0)) { status = 2; break; }  // NaN: singular stage system
+    pending = true;
+    // z += alpha dz ; nu += alpha (nu~ - nu) with nu~_i = P_i dx_i + p_i
+    for (int i = lane; i < N; i += 32) {
+      double *Vi = w.V + i * V_STRIDE;
+      const double *Si = w.S + i * S_STRIDE;
+      double dz[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) { dz[t] = Vi[V_DZ + t]; Vi[V_Z + t] += alpha * dz[t]; }
+      if (i > 0) {
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          double nt = Vi[V_P + r];
+#pragma unroll
+          for (int c = 0; c < 6; ++c) nt += Si[pidx(r, c)] * dz[c];
+          Vi[V_NU + r] += alpha * (nt - Vi[V_NU + r]);
+        }
+      }
+    }
+    __syncwarp();
+    if (alpha < 1e-6) { if (++stall >= 5) { status = 2; break; } } else stall = 0;
+  }
+  res.iters = it;
+  if (status != 0) {
+    // not converged: infeasible only if the primal point violates its rows
+    double worst = 0.0;
+    for (int i = lane; i < N; i += 32) {
+      PassViol v; v.worst = 0.0;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) v.y[t] = w.V[i * V_STRIDE + V_Z + t];
+      visit_rows(w, i, v);
+      worst = fmax(worst, v.worst);
+    }
+    worst = warp_max(worst);
+    status = (worst > 1e-7 || !(worst == worst)) ? 1 : 0;
+  }
+  res.status = status;
+  if (status == 0) {
+    double o = 0.0;
+    for (int i = lane; i < N; i += 32) {
+      const double *cst = D + p.o_cost + 16 * i;
+      const double *z = w.V + i * V_STRIDE + V_Z;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) o += (0.5 * cst[t] * z[t] + cst[8 + t]) * z[t];
+    }
+    o = warp_sum(o);
+    res.obj = o + p.cost_const;
+  }
+  return res;
+}
+
+}  // namespace miqp

@@ -1,0 +1,729 @@
+// solver.cu -- host driver and C ABI (include/miqp_b200.h) of the B200 MIQP backend.
+//
+// Host responsibilities (everything else runs on the device):
+//   * flatten a batch of plans (ModelParameters, reference src/miqp_planner_data.hpp:99-185)
+//     into one double blob + one int blob and upload them with one copy each;
+//   * the two scalar pre-computations OPL does in its `execute` blocks
+//     (cplexmodel/initialization.mod:16-29: front axle point at step 1 from atan2/cos/sin)
+//     and the list of mode alternatives per car;
+//   * MIP start: decisions of a full column vector (src/cplex_wrapper.cpp:494-639);
+//   * the round loop: launch select + node kernels, poll the number of unfinished plans,
+//     enforce the time limit (tilim, cplexmodel.mod:8-10).
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <algorithm>
+#include <vector>
+
+#include "../../include/miqp_b200.h"
+#include "kernels.cuh"
+
+using namespace miqp;
+
+namespace {
+
+#define CK(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      char buf_[512];                                                                    \
+      snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      throw std::runtime_error(buf_);                                                    \
+    }                                                                                    \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  void ensure(size_t count) {
+    if (count <= n) return;
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+    CK(cudaMalloc(&p, count * sizeof(T)));
+    n = count;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct Packed {
+  std::vector<DevProb> probs;
+  std::vector<double> dblob;
+  std::vector<int> iblob;
+  long total_rows = 0, total_nnz = 0, total_cols = 0, max_rows = 0;
+  int maxN = 0, max_ndec = 0, max_kmax = 0, max_z = 0, maxC = 0;
+};
+
+long push_d(std::vector<double> &b, const double *src, size_t n) {
+  long off = (long)b.size();
+  if (src) b.insert(b.end(), src, src + n); else b.resize(b.size() + n, 0.0);
+  return off;
+}
+long push_i(std::vector<int> &b, const int *src, size_t n) {
+  long off = (long)b.size();
+  if (src) b.insert(b.end(), src, src + n); else b.resize(b.size() + n, 0);
+  return off;
+}
+
+void layout_of(const MiqpB200Problem &q, MiqpB200Layout &l) {
+  l.C = q.C; l.N = q.N; l.R = q.R; l.O = q.O; l.L = q.L; l.E = q.E; l.K = q.C - 1;
+  const int C = q.C, N = q.N, R = q.R, O = q.O, L = q.L, E = q.E, K = l.K;
+  int b = 12 * C * N;
+  l.base_nwe = b;  b += 5 * C * E * N;
+  l.base_ar = b;   b += C * N * R;
+  l.base_rcna = b; b += 5 * C * N;
+  l.base_dcc = b;  b += C * O * N * L;
+  l.base_dcf = b;  b += 4 * C * O * N * L;
+  l.base_so = b;   b += C * O * N;
+  l.base_sof = b;  b += 4 * C * O * N;
+  l.base_c2c = b;  b += 16 * K * K * N;
+  l.base_sv = b;   b += 4 * K * K * N;
+  l.ncols = b;
+}
+
+// closed-form sizes of the big-M model (same arithmetic as prepare_tables_kernel)
+void model_sizes(const MiqpB200Problem &q, long &rows, long &nnz) {
+  const long C = q.C, N = q.N, R = q.R, O = q.O, E = q.E;
+  long nE = q.E > 0 ? q.env_off[q.E] : 0;
+  long rr = 0, nn = 0;
+  for (int c = 0; c < C; ++c) {
+    long rp = 0;
+    for (int j = 0; j < R; ++j) rp += (q.possible_region[c * R + j] == 1);
+    rr += 20 * rp + (R - rp) + 1;
+    nn += 76 * rp + (R - rp) + R;
+  }
+  rows = 12 * C + 5 * R * C + 5 * C + 6 * C * (N - 1) + 12 * C * N + rr * (N - 1) + 15 * R * C * (N - 1);
+  nnz = 12 * C + 9 * R * C + 5 * C + 24 * C * (N - 1) + 12 * C * N + nn * (N - 1) + 35 * R * C * (N - 1);
+  if (E > 0) { rows += C * N * (5 * nE + 5); nnz += C * N * (15 * nE + 5 * E); }
+  if (O > 0)
+    for (int i = 0; i < N; ++i)
+      for (int o = 0; o < O; ++o) {
+        long ne = q.obs_nedges[o * N + i], soft = (q.obs_soft[o] == 1);
+        rows += C * (5 * ne + 5); nnz += C * (15 * ne + 5 * (ne + soft));
+      }
+  if (C > 1) {
+    long K = C - 1, Z = K * (K - 1) / 2, P = C * (C - 1) / 2;
+    rows += 20 * Z * N + 24 * P * N; nnz += 20 * Z * N + 76 * P * N;
+  }
+}
+
+std::string validate(const MiqpB200Problem &q) {
+  if (q.N < 2 || q.N > 64) return "NumSteps must be in [2,64]";
+  if (q.R < 1 || q.R > 64) return "nr_regions must be in [1,64]";
+  if (q.C < 1 || q.C > 8) return "NumCars must be in [1,8]";
+  if (q.O < 0 || q.E < 0 || q.L < 0) return "negative dimension";
+  if (q.O > 0 && q.L > 16) return "max_lines_obstacles must be <= 16";
+  if (q.E > 250 || q.L > 250) return "too many polygons";
+  if (!q.x0 || !q.frac || !q.possible_region || !q.initial_region) return "null array";
+  for (int c = 0; c < q.C; ++c)
+    if (q.initial_region[c] < 1 || q.initial_region[c] > q.R) return "initial_region out of range";
+  if (q.O > 0)
+    for (int k = 0; k < q.O * q.N; ++k)
+      if (q.obs_nedges[k] < 0 || q.obs_nedges[k] > q.L) return "obstacle polygon with more edges than max_lines_obstacles";
+  return "";
+}
+
+// mode alternatives of a car: every possible region with its non-dominated low-speed half planes
+void mode_alternatives(const MiqpB200Problem &q, int c, std::vector<int> &out) {
+  out.clear();
+  for (int j = 0; j < q.R; ++j) {
+    if (q.possible_region[c * q.R + j] != 1) continue;
+    const double *f = q.frac + 4 * j;
+    const double d1x = f[0], d1y = f[1], d2x = f[2], d2y = f[3];
+    int useful[4];
+    useful[0] = (d1x > 1e-9 || d2x > 1e-9); useful[1] = (d1y > 1e-9 || d2y > 1e-9);
+    useful[2] = (d1x < -1e-9 || d2x < -1e-9); useful[3] = (d1y < -1e-9 || d2y < -1e-9);
+    const bool x_dom = (std::fabs(d1x) >= std::fabs(d1y) - 1e-9) && (std::fabs(d2x) >= std::fabs(d2y) - 1e-9);
+    const bool y_dom = (std::fabs(d1y) >= std::fabs(d1x) - 1e-9) && (std::fabs(d2y) >= std::fabs(d2x) - 1e-9);
+    if (x_dom && (useful[0] || useful[2])) { useful[1] = 0; useful[3] = 0; }
+    else if (y_dom && (useful[1] || useful[3])) { useful[0] = 0; useful[2] = 0; }
+    for (int h = 0; h < 4; ++h) if (useful[h]) out.push_back(j * 4 + h);
+  }
+}
+
+void pack_one(const MiqpB200Problem &q, Packed &pk) {
+  DevProb p;
+  std::memset(&p, 0, sizeof p);
+  const int N = q.N, R = q.R, C = q.C, O = q.O, L = q.L, E = q.E;
+  p.N = N; p.R = R; p.C = C; p.O = O; p.L = L; p.E = E; p.K = C - 1; p.P = C * (C - 1) / 2;
+  p.nEnvEdges = (E > 0) ? q.env_off[E] : 0;
+  p.maxEnvEdges = 0;
+  for (int e = 0; e < E; ++e) p.maxEnvEdges = std::max(p.maxEnvEdges, q.env_off[e + 1] - q.env_off[e]);
+  p.ts = q.ts;
+  p.c2 = 0.5 * (q.ts * q.ts);
+  p.c3 = (1.0 / 6.0) * ((q.ts * q.ts) * q.ts);
+  p.min_vel = q.min_vel; p.max_vel = q.max_vel;
+  p.total_min_acc = q.total_min_acc; p.total_max_acc = q.total_max_acc;
+  p.total_min_jerk = q.total_min_jerk; p.total_max_jerk = q.total_max_jerk;
+  p.maximum_slack = q.maximum_slack; p.w_slack = q.w_slack; p.w_slack_obs = q.w_slack_obs;
+  p.vm = q.min_region_change_speed; p.gap_tol = q.gap_tol;
+  auto &d = pk.dblob; auto &ib = pk.iblob;
+  p.o_safety = push_d(d, q.safety, N);
+  p.o_safety_slack = push_d(d, q.safety_slack, N);
+  const double *w[8] = {q.w_pos_x, q.w_vel_x, q.w_acc_x, q.w_pos_y, q.w_vel_y, q.w_acc_y, q.w_jerk_x, q.w_jerk_y};
+  for (int k = 0; k < 8; ++k) p.o_w[k] = push_d(d, w[k], C);
+  p.o_wb = push_d(d, q.wheelbase, C);
+  p.o_radius = push_d(d, q.radius, C);
+  p.o_x0 = push_d(d, q.x0, 6 * C);
+  p.o_front0 = push_d(d, nullptr, 2 * C);
+  for (int c = 0; c < C; ++c) {  // initialization.mod:25-29, initial_conditions.mod:20-23
+    const double *x0 = q.x0 + 6 * c;
+    const double th = std::atan2(x0[4], x0[1]);
+    const double ct = std::cos(th), st = std::sin(th), wb = q.wheelbase[c];
+    d[p.o_front0 + 2 * c] = x0[0] + ct * wb;
+    d[p.o_front0 + 2 * c + 1] = x0[3] + st * wb;
+  }
+  const double *ref[4] = {q.x_ref, q.vx_ref, q.y_ref, q.vy_ref};
+  for (int k = 0; k < 4; ++k) p.o_ref[k] = push_d(d, ref[k], (size_t)C * N);
+  const double *lim[8] = {q.min_acc_x, q.max_acc_x, q.min_acc_y, q.max_acc_y, q.min_jerk_x, q.max_jerk_x, q.min_jerk_y, q.max_jerk_y};
+  for (int k = 0; k < 8; ++k) p.o_lim[k] = push_d(d, lim[k], (size_t)C * R);
+  p.o_obs_edges = push_d(d, O > 0 ? q.obs_edges : nullptr, (size_t)O * N * L * 4);
+  p.o_env_edges = push_d(d, p.nEnvEdges > 0 ? q.env_edges : nullptr, (size_t)p.nEnvEdges * 4);
+  p.o_frac = push_d(d, q.frac, (size_t)R * 4);
+  const double *poly[6] = {q.poly_sint_ub, q.poly_sint_lb, q.poly_coss_ub, q.poly_coss_lb, q.poly_kappa_max, q.poly_kappa_min};
+  for (int k = 0; k < 6; ++k) p.o_poly[k] = push_d(d, poly[k], (size_t)R * 3);
+  p.o_envtab = push_d(d, nullptr, (size_t)p.nEnvEdges * 3);
+  p.o_obstab = push_d(d, nullptr, (size_t)O * N * L * 3);
+  p.o_modetab = push_d(d, nullptr, (size_t)R * 20);
+  p.o_fronttab = push_d(d, nullptr, (size_t)C * R * 12);
+  p.o_cost = push_d(d, nullptr, (size_t)C * N * 16);
+
+  p.o_initreg = push_i(ib, q.initial_region, C);
+  p.o_possible = push_i(ib, q.possible_region, (size_t)C * R);
+  p.o_obs_nedges = push_i(ib, O > 0 ? q.obs_nedges : nullptr, (size_t)O * N);
+  p.o_obs_soft = push_i(ib, O > 0 ? q.obs_soft : nullptr, O);
+  p.o_env_off = push_i(ib, q.env_off, E + 1);
+  p.o_alt = push_i(ib, nullptr, (size_t)C * 4 * R);
+  p.o_nalt = push_i(ib, nullptr, C);
+  std::vector<int> alts;
+  for (int c = 0; c < C; ++c) {
+    mode_alternatives(q, c, alts);
+    ib[p.o_nalt + c] = (int)alts.size();
+    for (size_t a = 0; a < alts.size(); ++a) ib[p.o_alt + c * 4 * R + a] = alts[a];
+  }
+  p.o_posspre = push_i(ib, nullptr, (size_t)C * (R + 1));
+  p.o_obsrowpre = push_i(ib, nullptr, (size_t)N * (O + 1));
+  p.o_obsnnzpre = push_i(ib, nullptr, (size_t)N * (O + 1));
+  p.o_obsstep_rows = push_i(ib, nullptr, N + 1);
+  p.o_obsstep_nnz = push_i(ib, nullptr, N + 1);
+
+  MiqpB200Layout l; layout_of(q, l);
+  p.base_nwe = l.base_nwe; p.base_ar = l.base_ar; p.base_rcna = l.base_rcna; p.base_dcc = l.base_dcc;
+  p.base_dcf = l.base_dcf; p.base_so = l.base_so; p.base_sof = l.base_sof; p.base_c2c = l.base_c2c;
+  p.base_sv = l.base_sv; p.ncols = l.ncols;
+
+  long rows, nnz; model_sizes(q, rows, nnz);
+  p.row_base = pk.total_rows; p.nnz_base = pk.total_nnz; p.x_base = pk.total_cols;
+  pk.total_rows += rows; pk.total_nnz += nnz; pk.total_cols += l.ncols;
+  pk.max_rows = std::max(pk.max_rows, rows);
+
+  p.off_mode = 0; p.off_env = p.off_mode + C * N; p.off_obs = p.off_env + 5 * C * N;
+  p.off_pair = p.off_obs + 5 * C * O * N; p.ndec = p.off_pair + 4 * p.P * N;
+  p.ndec_pad = (p.ndec + 15) & ~15;
+  p.kmax = 12 + 5 + (E > 0 ? 5 * p.maxEnvEdges : 0) + 5 * O;
+  pk.maxN = std::max(pk.maxN, N); pk.max_ndec = std::max(pk.max_ndec, p.ndec_pad);
+  pk.max_kmax = std::max(pk.max_kmax, p.kmax); pk.maxC = std::max(pk.maxC, C);
+  pk.max_z = std::max(pk.max_z, C * N * 8 + 4 * p.P * N);
+  pk.probs.push_back(p);
+}
+
+// decisions of a full column vector (MIP start / warm start)
+void decisions_from_solution(const MiqpB200Problem &q, const DevProb &p, const std::vector<int> &alts_all,
+                             const double *x, unsigned char *dec) {
+  const int C = p.C, N = p.N, R = p.R, E = p.E, O = p.O, L = p.L, K = p.K;
+  std::memset(dec, UNDEC, (size_t)p.ndec_pad);
+  std::vector<int> alts;
+  for (int c = 0; c < C; ++c) {
+    mode_alternatives(q, c, alts);
+    for (int i = 0; i < N; ++i) {
+      int j = 0;
+      for (int jj = 0; jj < R; ++jj) if (x[col_ar(p, c, i, jj)] > 0.5) j = jj;
+      if (i > 0) {
+        const double rho = x[col_rcna(p, 4, c, i)];
+        if (rho > 0.5) dec[p.off_mode + c * N + i] = MODE_FROZEN;
+        else {
+          int h = -1;
+          for (int t = 0; t < 4; ++t) if (x[col_rcna(p, t, c, i)] < 0.5) { h = t; break; }
+          if (h < 0) h = 0;
+          bool found = false; int firsth = -1;
+          for (int alt : alts) if ((alt >> 2) == j) { if (firsth < 0) firsth = alt & 3; if ((alt & 3) == h) found = true; }
+          if (!found && firsth >= 0) h = firsth;
+          dec[p.off_mode + c * N + i] = (unsigned char)(j * 4 + h);
+        }
+      }
+      for (int pt = 0; pt < 5; ++pt) {
+        if (E > 1) {
+          int e = 0;
+          for (int ee = 0; ee < E; ++ee) if (x[col_nwe(p, pt, c, ee, i)] < 0.5) { e = ee; break; }
+          dec[p.off_env + (c * N + i) * 5 + pt] = (unsigned char)e;
+        }
+        for (int o = 0; o < O; ++o) {
+          const int ne = q.obs_nedges[o * N + i];
+          int dd = OBS_SOFT;
+          for (int ed = 0; ed < ne; ++ed) {
+            const double v = (pt == 0) ? x[col_dcc(p, c, o, i, ed)] : x[col_dcf(p, c, o, i, ed, 4 - pt)];
+            if (v < 0.5) { dd = ed; break; }
+          }
+          dec[p.off_obs + ((c * O + o) * N + i) * 5 + pt] = (unsigned char)dd;
+        }
+      }
+    }
+  }
+  int pr = 0;
+  for (int a = 0; a < C - 1; ++a)
+    for (int b = a + 1; b < C; ++b, ++pr)
+      for (int i = 0; i < N; ++i)
+        for (int qd = 0; qd < 4; ++qd) {
+          int dd = 0;
+          for (int side = 0; side < 4; ++side) if (x[col_c2c(p, a, b - 1, i, qd * 4 + side)] < 0.5) { dd = side; break; }
+          dec[p.off_pair + (pr * N + i) * 4 + qd] = (unsigned char)dd;
+        }
+  (void)alts_all; (void)L; (void)K;
+}
+
+}  // namespace
+
+struct MiqpB200Solver {
+  MiqpB200Options opt;
+  std::string err;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evr0 = nullptr, evr1 = nullptr;
+  int num_sms = 0;
+  // batch
+  Packed pk;
+  std::vector<double> time_limits;
+  DevBuf<DevProb> d_probs;
+  DevBuf<double> d_dblob;
+  DevBuf<int> d_iblob;
+  DevBuf<double> d_x, d_viol, d_obj, d_bb;
+  DevBuf<unsigned char> d_warm;
+  DevBuf<int> d_haswarm;
+  std::vector<unsigned char> h_warm;
+  std::vector<int> h_haswarm;
+  bool any_warm = false;
+  // bnb state buffers
+  BnbState st;
+  DevBuf<unsigned char> b_dec, b_incdec;
+  DevBuf<double> b_bound, b_ub, b_cutoff, b_pruned, b_incz, b_rowscratch;
+  DevBuf<int2> b_meta, b_work;
+  DevBuf<unsigned long long> b_uid, b_keybuf, b_incuid, b_stats;
+  DevBuf<int> b_open, b_opencnt, b_free, b_freecnt, b_sel, b_selcnt, b_done, b_lock, b_ctrl;
+  int smem_per_warp = 0, warps_per_cta = 4, ctas = 0;
+  bool uploaded = false, ran = false;
+  double last_seconds = 0.0;
+  bool timed_out = false;
+  MiqpB200RunStats stats;
+  std::vector<double> h_x, h_viol, h_obj, h_bb, h_ub;
+  std::vector<unsigned long long> h_stats;
+  std::vector<int> h_done;
+};
+
+namespace {
+
+int fail(MiqpB200Solver *s, int code, const std::string &msg) {
+  if (s) s->err = msg;
+  return code;
+}
+
+void upload_packed(MiqpB200Solver *s) {
+  Packed &pk = s->pk;
+  const int count = (int)pk.probs.size();
+  s->d_probs.ensure(count);
+  s->d_dblob.ensure(std::max<size_t>(pk.dblob.size(), 1));
+  s->d_iblob.ensure(std::max<size_t>(pk.iblob.size(), 1));
+  CK(cudaMemcpyAsync(s->d_probs.p, pk.probs.data(), sizeof(DevProb) * count, cudaMemcpyHostToDevice, s->stream));
+  CK(cudaMemcpyAsync(s->d_dblob.p, pk.dblob.data(), sizeof(double) * pk.dblob.size(), cudaMemcpyHostToDevice, s->stream));
+  CK(cudaMemcpyAsync(s->d_iblob.p, pk.iblob.data(), sizeof(int) * pk.iblob.size(), cudaMemcpyHostToDevice, s->stream));
+  s->stats.h2d_bytes = (long)(sizeof(DevProb) * count + sizeof(double) * pk.dblob.size() + sizeof(int) * pk.iblob.size());
+  launch_prepare_tables(s->d_probs.p, s->d_dblob.p, s->d_iblob.p, count, s->stream);
+  CK(cudaGetLastError());
+}
+
+void pack_batch(MiqpB200Solver *s, const MiqpB200Problem *problems, int count) {
+  s->pk = Packed();
+  s->time_limits.clear();
+  for (int k = 0; k < count; ++k) {
+    std::string v = validate(problems[k]);
+    if (!v.empty()) throw std::invalid_argument("plan " + std::to_string(k) + ": " + v);
+    pack_one(problems[k], s->pk);
+    s->time_limits.push_back(problems[k].time_limit);
+  }
+}
+
+void setup_bnb(MiqpB200Solver *s) {
+  Packed &pk = s->pk;
+  const int count = (int)pk.probs.size();
+  BnbState &st = s->st;
+  st.count = count;
+  st.ndec_stride = pk.max_ndec;
+  st.zstride = pk.max_z;
+  st.kmax = pk.max_kmax;
+  st.npad = ((pk.maxN + 31) / 32) * 32;
+  // node kernel geometry
+  s->smem_per_warp = node_kernel_smem_per_warp(pk.maxN, st.ndec_stride);
+  s->warps_per_cta = 4;
+  int per_sm = 0;
+  while (s->warps_per_cta >= 1) {
+    per_sm = node_kernel_max_ctas(s->smem_per_warp * s->warps_per_cta, s->warps_per_cta * 32);
+    if (per_sm > 0) break;
+    s->warps_per_cta /= 2;
+  }
+  if (per_sm <= 0) throw std::runtime_error("node kernel does not fit in shared memory for this horizon");
+  s->ctas = per_sm * s->num_sms;
+  st.nwarps = s->ctas * s->warps_per_cta;
+  // nodes per plan per round: fill the resident warps about twice
+  int K = s->opt.nodes_per_round;
+  if (K <= 0) { K = (2 * st.nwarps + count - 1) / count; if (K < 1) K = 1; if (K > 1024) K = 1024; }
+  st.sel_per_plan = K;
+  // pool capacity per plan
+  int cap = s->opt.pool_capacity;
+  if (cap <= 0) {
+    const size_t node_bytes = (size_t)st.ndec_stride + 48;
+    size_t budget = (size_t)8 << 30;  // 8 GiB of pool by default
+    size_t c = budget / (node_bytes * (size_t)count);
+    if (c > (1u << 20)) c = 1u << 20;
+    if (c < 256) c = 256;
+    cap = (int)c;
+  }
+  if (cap < 4 * K + 64) cap = 4 * K + 64;
+  st.cap = cap;
+  st.work_cap = count * K;
+  const size_t nodes = (size_t)count * cap;
+  s->b_dec.ensure(nodes * st.ndec_stride); st.dec = s->b_dec.p;
+  s->b_bound.ensure(nodes); st.bound = s->b_bound.p;
+  s->b_meta.ensure(nodes); st.meta = s->b_meta.p;
+  s->b_uid.ensure(nodes); st.uid = s->b_uid.p;
+  s->b_open.ensure(nodes); st.open_idx = s->b_open.p;
+  s->b_free.ensure(nodes); st.free_stack = s->b_free.p;
+  s->b_keybuf.ensure(nodes); st.keybuf = s->b_keybuf.p;
+  s->b_opencnt.ensure(count); st.open_cnt = s->b_opencnt.p;
+  s->b_freecnt.ensure(count); st.free_cnt = s->b_freecnt.p;
+  s->b_sel.ensure((size_t)count * K); st.sel_idx = s->b_sel.p;
+  s->b_selcnt.ensure(count); st.sel_cnt = s->b_selcnt.p;
+  s->b_ub.ensure(count); st.ub = s->b_ub.p;
+  s->b_cutoff.ensure(count); st.cutoff = s->b_cutoff.p;
+  s->b_pruned.ensure(count); st.pruned_lb = s->b_pruned.p;
+  s->b_done.ensure(count); st.done = s->b_done.p;
+  s->b_lock.ensure(count); st.lock = s->b_lock.p;
+  s->b_incz.ensure((size_t)count * st.zstride); st.inc_z = s->b_incz.p;
+  s->b_incdec.ensure((size_t)count * st.ndec_stride); st.inc_dec = s->b_incdec.p;
+  s->b_incuid.ensure(count); st.inc_uid = s->b_incuid.p;
+  s->b_stats.ensure((size_t)3 * count);
+  st.stat_nodes = s->b_stats.p; st.stat_iters = s->b_stats.p + count; st.stat_rows = s->b_stats.p + 2 * count;
+  s->b_work.ensure(st.work_cap); st.work = s->b_work.p;
+  s->b_ctrl.ensure(4);
+  st.work_cnt = s->b_ctrl.p; st.work_next = s->b_ctrl.p + 1; st.active = s->b_ctrl.p + 2; st.err = s->b_ctrl.p + 3;
+  s->b_rowscratch.ensure((size_t)st.nwarps * 4 * st.kmax * st.npad); st.rowscratch = s->b_rowscratch.p;
+  s->d_x.ensure(std::max<long>(pk.total_cols, 1));
+  s->d_viol.ensure(count); s->d_obj.ensure(count); s->d_bb.ensure(count);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *miqp_b200_version(void) { return "planner-miqp_b200 0.1 (sm_100a)"; }
+
+void miqp_b200_default_options(MiqpB200Options *opt) {
+  if (!opt) return;
+  opt->device = 0; opt->nodes_per_round = 0; opt->pool_capacity = 0; opt->max_rounds = 0; opt->verbose = 0;
+}
+
+int miqp_b200_create(const MiqpB200Options *opt, MiqpB200Solver **out) {
+  if (!out) return MIQP_B200_ERR_ARG;
+  *out = nullptr;
+  MiqpB200Solver *s = new MiqpB200Solver();
+  if (opt) s->opt = *opt; else miqp_b200_default_options(&s->opt);
+  std::memset(&s->stats, 0, sizeof s->stats);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= s->opt.device) {
+    fprintf(stderr, "miqp_b200: no usable CUDA device (%s); this backend has no CPU fallback\n",
+            e != cudaSuccess ? cudaGetErrorString(e) : "device ordinal out of range");
+    delete s;
+    return MIQP_B200_ERR_CUDA;
+  }
+  try {
+    CK(cudaSetDevice(s->opt.device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, s->opt.device));
+    s->num_sms = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&s->ev0)); CK(cudaEventCreate(&s->ev1));
+    CK(cudaEventCreate(&s->evr0)); CK(cudaEventCreate(&s->evr1));
+  } catch (const std::exception &ex) {
+    fprintf(stderr, "miqp_b200: %s\n", ex.what());
+    delete s;
+    return MIQP_B200_ERR_CUDA;
+  }
+  *out = s;
+  return MIQP_B200_OK;
+}
+
+void miqp_b200_destroy(MiqpB200Solver *s) {
+  if (!s) return;
+  cudaSetDevice(s->opt.device);
+  s->d_probs.release(); s->d_dblob.release(); s->d_iblob.release(); s->d_x.release(); s->d_viol.release();
+  s->d_obj.release(); s->d_bb.release(); s->d_warm.release(); s->d_haswarm.release();
+  s->b_dec.release(); s->b_incdec.release(); s->b_bound.release(); s->b_ub.release(); s->b_cutoff.release();
+  s->b_pruned.release(); s->b_incz.release(); s->b_rowscratch.release(); s->b_meta.release(); s->b_work.release();
+  s->b_uid.release(); s->b_keybuf.release(); s->b_incuid.release(); s->b_stats.release(); s->b_open.release();
+  s->b_opencnt.release(); s->b_free.release(); s->b_freecnt.release(); s->b_sel.release(); s->b_selcnt.release();
+  s->b_done.release(); s->b_lock.release(); s->b_ctrl.release();
+  if (s->ev0) cudaEventDestroy(s->ev0);
+  if (s->ev1) cudaEventDestroy(s->ev1);
+  if (s->evr0) cudaEventDestroy(s->evr0);
+  if (s->evr1) cudaEventDestroy(s->evr1);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+const char *miqp_b200_last_error(const MiqpB200Solver *s) { return s ? s->err.c_str() : "null solver"; }
+
+int miqp_b200_layout(const MiqpB200Problem *p, MiqpB200Layout *out) {
+  if (!p || !out) return MIQP_B200_ERR_ARG;
+  layout_of(*p, *out);
+  return MIQP_B200_OK;
+}
+
+int miqp_b200_assemble(MiqpB200Solver *s, const MiqpB200Problem *p, long *rowptr, int *cols, double *vals,
+                       double *lo, double *hi) {
+  MiqpB200Sizes sz;
+  if (!s || !p) return MIQP_B200_ERR_ARG;
+  try {
+    CK(cudaSetDevice(s->opt.device));
+    pack_batch(s, p, 1);
+    s->uploaded = false;
+    upload_packed(s);
+    const long rows = s->pk.total_rows, nnz = s->pk.total_nnz;
+    DevBuf<long> d_rowptr; DevBuf<int> d_cols; DevBuf<double> d_vals, d_lo, d_hi; DevBuf<unsigned long long> d_cnt;
+    d_rowptr.ensure(rows + 1); d_cols.ensure(std::max<long>(nnz, 1)); d_vals.ensure(std::max<long>(nnz, 1));
+    d_lo.ensure(rows + 1); d_hi.ensure(rows + 1); d_cnt.ensure(1);
+    CK(cudaMemsetAsync(d_cnt.p, 0, sizeof(unsigned long long), s->stream));
+    launch_assemble_rows(s->d_probs.p, s->d_dblob.p, s->d_iblob.p, 1, s->pk.max_rows, d_rowptr.p, d_cols.p, d_vals.p,
+                         d_lo.p, d_hi.p, d_cnt.p, s->stream);
+    CK(cudaGetLastError());
+    if (rowptr) CK(cudaMemcpyAsync(rowptr, d_rowptr.p, sizeof(long) * (rows + 1), cudaMemcpyDeviceToHost, s->stream));
+    if (cols) CK(cudaMemcpyAsync(cols, d_cols.p, sizeof(int) * nnz, cudaMemcpyDeviceToHost, s->stream));
+    if (vals) CK(cudaMemcpyAsync(vals, d_vals.p, sizeof(double) * nnz, cudaMemcpyDeviceToHost, s->stream));
+    if (lo) CK(cudaMemcpyAsync(lo, d_lo.p, sizeof(double) * rows, cudaMemcpyDeviceToHost, s->stream));
+    if (hi) CK(cudaMemcpyAsync(hi, d_hi.p, sizeof(double) * rows, cudaMemcpyDeviceToHost, s->stream));
+    unsigned long long cnt = 0;
+    CK(cudaMemcpyAsync(&cnt, d_cnt.p, sizeof cnt, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    s->stats.launches += 2;
+    sz.nnz = (long)cnt;
+    s->h_stats.assign(1, cnt);
+    d_rowptr.release(); d_cols.release(); d_vals.release(); d_lo.release(); d_hi.release(); d_cnt.release();
+  } catch (const std::invalid_argument &ex) {
+    return fail(s, MIQP_B200_ERR_ARG, ex.what());
+  } catch (const std::exception &ex) {
+    return fail(s, MIQP_B200_ERR_CUDA, ex.what());
+  }
+  return MIQP_B200_OK;
+}
+
+int miqp_b200_sizes(MiqpB200Solver *s, const MiqpB200Problem *p, MiqpB200Sizes *out) {
+  if (!s || !p || !out) return MIQP_B200_ERR_ARG;
+  int rc = miqp_b200_assemble(s, p, nullptr, nullptr, nullptr, nullptr, nullptr);
+  if (rc != MIQP_B200_OK) return rc;
+  MiqpB200Layout l; layout_of(*p, l);
+  out->ncols = l.ncols;
+  out->nbin = (l.base_so - l.base_nwe) + (l.base_sv - l.base_c2c);
+  out->ncont = l.ncols - out->nbin;
+  out->nrows = s->pk.total_rows; out->nnz_struct = s->pk.total_nnz;
+  out->nnz = (long)s->h_stats[0];
+  return MIQP_B200_OK;
+}
+
+int miqp_b200_evaluate(MiqpB200Solver *s, const MiqpB200Problem *p, const double *x, double *objective,
+                       double *max_violation) {
+  if (!s || !p || !x) return MIQP_B200_ERR_ARG;
+  try {
+    CK(cudaSetDevice(s->opt.device));
+    pack_batch(s, p, 1);
+    s->uploaded = false;
+    upload_packed(s);
+    s->d_x.ensure(s->pk.total_cols); s->d_viol.ensure(1); s->d_obj.ensure(1);
+    CK(cudaMemcpyAsync(s->d_x.p, x, sizeof(double) * s->pk.total_cols, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaMemsetAsync(s->d_viol.p, 0, sizeof(double), s->stream));
+    launch_evaluate(s->d_probs.p, s->d_dblob.p, s->d_iblob.p, 1, s->pk.max_rows, s->d_x.p, s->d_viol.p, s->d_obj.p, s->stream);
+    CK(cudaGetLastError());
+    double v = 0, o = 0;
+    CK(cudaMemcpyAsync(&v, s->d_viol.p, sizeof v, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(&o, s->d_obj.p, sizeof o, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    s->stats.launches += 2;
+    if (objective) *objective = o;
+    if (max_violation) *max_violation = v;
+  } catch (const std::invalid_argument &ex) {
+    return fail(s, MIQP_B200_ERR_ARG, ex.what());
+  } catch (const std::exception &ex) {
+    return fail(s, MIQP_B200_ERR_CUDA, ex.what());
+  }
+  return MIQP_B200_OK;
+}
+
+int miqp_b200_batch_upload(MiqpB200Solver *s, const MiqpB200Problem *problems, int count, const double *const *warm) {
+  if (!s || !problems || count <= 0) return MIQP_B200_ERR_ARG;
+  try {
+    CK(cudaSetDevice(s->opt.device));
+    s->uploaded = false; s->ran = false;
+    pack_batch(s, problems, count);
+    for (int k = 0; k < count; ++k)
+      if (problems[k].C != 1) return fail(s, MIQP_B200_ERR_UNSUPPORTED, "node kernel is built for NumCars == 1 in this release");
+    upload_packed(s);
+    setup_bnb(s);
+    // MIP starts
+    s->any_warm = false;
+    s->h_haswarm.assign(count, 0);
+    s->h_warm.assign((size_t)count * s->st.ndec_stride, UNDEC);
+    if (warm)
+      for (int k = 0; k < count; ++k)
+        if (warm[k]) {
+          std::vector<int> dummy;
+          decisions_from_solution(problems[k], s->pk.probs[k], dummy, warm[k], s->h_warm.data() + (size_t)k * s->st.ndec_stride);
+          s->h_haswarm[k] = 1; s->any_warm = true;
+        }
+    if (s->any_warm) {
+      s->d_warm.ensure(s->h_warm.size()); s->d_haswarm.ensure(count);
+      CK(cudaMemcpyAsync(s->d_warm.p, s->h_warm.data(), s->h_warm.size(), cudaMemcpyHostToDevice, s->stream));
+      CK(cudaMemcpyAsync(s->d_haswarm.p, s->h_haswarm.data(), sizeof(int) * count, cudaMemcpyHostToDevice, s->stream));
+      s->stats.h2d_bytes += (long)(s->h_warm.size() + sizeof(int) * count);
+    }
+    CK(cudaStreamSynchronize(s->stream));
+    s->uploaded = true;
+  } catch (const std::invalid_argument &ex) {
+    return fail(s, MIQP_B200_ERR_ARG, ex.what());
+  } catch (const std::exception &ex) {
+    return fail(s, MIQP_B200_ERR_CUDA, ex.what());
+  }
+  return MIQP_B200_OK;
+}
+
+int miqp_b200_batch_run(MiqpB200Solver *s, float *device_ms) {
+  if (!s) return MIQP_B200_ERR_ARG;
+  if (!s->uploaded) return fail(s, MIQP_B200_ERR_ARG, "batch_run without batch_upload");
+  try {
+    CK(cudaSetDevice(s->opt.device));
+    const int count = s->st.count;
+    const auto t0 = std::chrono::steady_clock::now();
+    double tlim = 0.0;
+    for (double t : s->time_limits) tlim = std::max(tlim, t);
+    long launches = 0, node_launches = 0, rounds = 0;
+    double node_ms = 0.0;
+    CK(cudaEventRecord(s->ev0, s->stream));
+    launch_bnb_init(s->st, s->d_probs.p, s->any_warm ? s->d_warm.p : nullptr, s->any_warm ? s->d_haswarm.p : nullptr, s->stream);
+    ++launches;
+    s->timed_out = false;
+    int ctrl[4] = {0, 0, 0, 0};
+    for (;;) {
+      launch_bnb_select(s->st, s->d_probs.p, s->stream);
+      launches += 2;
+      CK(cudaEventRecord(s->evr0, s->stream));
+      int rc = launch_bnb_nodes(s->st, s->d_probs.p, s->d_dblob.p, s->d_iblob.p, s->smem_per_warp, s->warps_per_cta,
+                                s->ctas, s->pk.maxN, s->stream);
+      if (rc != 0) throw std::runtime_error(std::string("node kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
+      CK(cudaEventRecord(s->evr1, s->stream));
+      ++launches; ++node_launches; ++rounds;
+      CK(cudaMemcpyAsync(ctrl, s->b_ctrl.p, sizeof ctrl, cudaMemcpyDeviceToHost, s->stream));
+      CK(cudaStreamSynchronize(s->stream));
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, s->evr0, s->evr1));
+      node_ms += ms;
+      if (s->opt.verbose > 1) fprintf(stderr, "[miqp_b200] round %ld: work %d active %d err %d node kernel %.3f ms\n", rounds, ctrl[0], ctrl[2], ctrl[3], ms);
+      if (ctrl[3]) return fail(s, MIQP_B200_ERR_RESOURCE, "node pool exhausted; raise MiqpB200Options.pool_capacity");
+      if (ctrl[2] == 0) break;  // every plan finished
+      const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      if (el > tlim) { s->timed_out = true; break; }
+      if (s->opt.max_rounds > 0 && rounds >= s->opt.max_rounds) { s->timed_out = true; break; }
+    }
+    launch_bnb_finish(s->st, s->d_probs.p, s->d_dblob.p, s->d_iblob.p, s->d_x.p, s->d_bb.p, s->stream);
+    CK(cudaMemsetAsync(s->d_viol.p, 0, sizeof(double) * count, s->stream));
+    launch_evaluate(s->d_probs.p, s->d_dblob.p, s->d_iblob.p, count, s->pk.max_rows, s->d_x.p, s->d_viol.p, s->d_obj.p, s->stream);
+    launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(s->ev1, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    float total_ms = 0.f;
+    CK(cudaEventElapsedTime(&total_ms, s->ev0, s->ev1));
+    if (device_ms) *device_ms = total_ms;
+    s->last_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    s->stats.launches = launches; s->stats.node_kernel_launches = node_launches; s->stats.rounds = rounds;
+    s->stats.node_kernel_ms = node_ms; s->stats.total_ms = total_ms;
+    s->ran = true;
+  } catch (const std::exception &ex) {
+    return fail(s, MIQP_B200_ERR_CUDA, ex.what());
+  }
+  return MIQP_B200_OK;
+}
+
+int miqp_b200_batch_fetch(MiqpB200Solver *s, double *const *x_out, MiqpB200SolveInfo *infos) {
+  if (!s) return MIQP_B200_ERR_ARG;
+  if (!s->ran) return fail(s, MIQP_B200_ERR_ARG, "batch_fetch without batch_run");
+  try {
+    CK(cudaSetDevice(s->opt.device));
+    const int count = s->st.count;
+    const long ncols = s->pk.total_cols;
+    s->h_x.resize(ncols); s->h_viol.resize(count); s->h_obj.resize(count); s->h_bb.resize(count); s->h_ub.resize(count);
+    s->h_stats.resize((size_t)3 * count); s->h_done.resize(count);
+    CK(cudaMemcpyAsync(s->h_x.data(), s->d_x.p, sizeof(double) * ncols, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(s->h_viol.data(), s->d_viol.p, sizeof(double) * count, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(s->h_obj.data(), s->d_obj.p, sizeof(double) * count, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(s->h_bb.data(), s->d_bb.p, sizeof(double) * count, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(s->h_ub.data(), s->st.ub, sizeof(double) * count, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(s->h_stats.data(), s->b_stats.p, sizeof(unsigned long long) * 3 * count, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(s->h_done.data(), s->st.done, sizeof(int) * count, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    s->stats.d2h_bytes = (long)(sizeof(double) * (ncols + 4 * count) + sizeof(unsigned long long) * 3 * count + sizeof(int) * count);
+    long nodes = 0, iters = 0, rows = 0;
+    for (int k = 0; k < count; ++k) {
+      const DevProb &p = s->pk.probs[k];
+      if (x_out && x_out[k]) std::memcpy(x_out[k], s->h_x.data() + p.x_base, sizeof(double) * p.ncols);
+      nodes += (long)s->h_stats[k]; iters += (long)s->h_stats[count + k]; rows += (long)s->h_stats[2 * count + k];
+      if (!infos) continue;
+      MiqpB200SolveInfo &in = infos[k];
+      std::memset(&in, 0, sizeof in);
+      const bool have = std::isfinite(s->h_ub[k]);
+      in.seconds = s->last_seconds;
+      in.nodes = (long)s->h_stats[k]; in.qp_iters = (long)s->h_stats[count + k]; in.rounds = s->stats.rounds;
+      in.best_bound = s->h_bb[k];
+      if (have) {
+        in.status = MIQP_B200_SUCCESS;
+        in.objective = s->h_obj[k];  // re-evaluated on the full vector by evaluate_kernel
+        in.max_violation = s->h_viol[k];
+        const double lb = std::min(s->h_bb[k], s->h_ub[k]);
+        in.gap = std::fabs(lb - s->h_ub[k]) / (1e-10 + std::fabs(s->h_ub[k]));
+        in.proven = (in.gap <= p.gap_tol + 1e-15) ? 1 : 0;
+      } else {
+        // no incumbent: the reference reports FAILED_TIMEOUT only for the time-limit status
+        in.status = (s->timed_out && !s->h_done[k]) ? MIQP_B200_FAILED_TIMEOUT : MIQP_B200_FAILED_NO_SOLUT;
+        in.objective = NAN; in.gap = NAN; in.max_violation = NAN;
+      }
+    }
+    s->stats.nodes = nodes; s->stats.qp_iters = iters; s->stats.rows_visited = rows;
+  } catch (const std::exception &ex) {
+    return fail(s, MIQP_B200_ERR_CUDA, ex.what());
+  }
+  return MIQP_B200_OK;
+}
+
+int miqp_b200_solve_batch(MiqpB200Solver *s, const MiqpB200Problem *problems, int count, const double *const *warm,
+                          double *const *x_out, MiqpB200SolveInfo *infos) {
+  int rc = miqp_b200_batch_upload(s, problems, count, warm);
+  if (rc != MIQP_B200_OK) return rc;
+  rc = miqp_b200_batch_run(s, nullptr);
+  if (rc != MIQP_B200_OK) return rc;
+  return miqp_b200_batch_fetch(s, x_out, infos);
+}
+
+int miqp_b200_run_stats(const MiqpB200Solver *s, MiqpB200RunStats *out) {
+  if (!s || !out) return MIQP_B200_ERR_ARG;
+  *out = s->stats;
+  return MIQP_B200_OK;
+}
+
+}  // extern "C"
