@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py -- MIQP plans/s at 1e-4 relative gap on N B200s (BASELINE.json metric).
+
+Workload (config[1] of BASELINE.json): batch of single-agent plans with one static and one
+dynamic-occupancy obstacle, N=40 steps, 32 fitted regions, reference default settings
+(planner-miqp_b200/scenarios.py:obstacle_scenario, seeds rank*B .. rank*B+B-1).
+
+One step = one pass of the hot path over one batch: every plan is solved to a proven
+relative gap <= 1e-4 by the device branch and bound.
+  value : plans/s, whole job, batch already resident in HBM when the timed region starts
+          (miqp_b200_batch_run; CUDA events on the solver stream, max over ranks)
+  e2e   : plans/s through the C ABI with host buffers (miqp_b200_solve_batch: pack + H2D +
+          solve + D2H of every solution vector inside the timed region)
+Rank layout: one process per GPU, scenario sharding, no data-path collective ("weak").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+GAP = 1e-4
+WORKLOAD = "single agent, static + dynamic-occupancy obstacle, N=40, R=32 (BASELINE.json configs[1])"
+
+
+def make_plans(first_seed: int, count: int):
+    import planner_miqp_b200  # noqa: F401
+    from planner_miqp_b200.scenarios import obstacle_scenario
+    return [obstacle_scenario(first_seed + k).build() for k in range(count)]
+
+
+class ClockSampler:
+    """nvidia-smi clocks during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([t.strip() for t in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks() -> dict:
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d.get("hbm_gbs"), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def algorithmic_flops(stats: dict, N: int) -> float:
+    """Algorithmic FP64 flops of the node kernel: per interior-point
+    iteration 1000 flops per stage for the Riccati factorisation and sweeps, 60 flops per
+    active inequality row for residuals, Hessian update, two gradients and two step lengths."""
+    return 1000.0 * N * stats["qp_iters"] + 60.0 * stats["rows_visited"]
+
+
+def cpu_oracle_rate(plans, threads: int):
+    """plans/s of the CPU oracle (oracle/, the checker) on `plans` with `threads` host threads."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as O
+    O.lib()
+    t0 = time.perf_counter()
+    if threads <= 1:
+        infos = [O.solve(p, gap_tol=GAP, time_limit=60.0)[1] for p in plans]
+    else:
+        with ThreadPoolExecutor(max_workers=threads) as ex:   # ctypes releases the GIL
+            infos = [r[1] for r in ex.map(lambda p: O.solve(p, gap_tol=GAP, time_limit=60.0), plans)]
+    dt = time.perf_counter() - t0
+    ok = sum(1 for i in infos if i.status == 0)
+    return len(plans) / dt, dt, ok
+
+
+def run_reference(args):
+    """Reference arm: the CPU implementation of the path (the oracle port; CPLEX 12.10 is
+    proprietary and absent) on all host cores, same workload/metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    sample = min(args.batch, max(4 * cores, 32))
+    plans = make_plans(0, sample)
+    for _ in range(args.warmup):
+        cpu_oracle_rate(plans[:cores], cores)
+    rates, times = [], []
+    for _ in range(args.steps):
+        r, dt, ok = cpu_oracle_rate(plans, cores)
+        rates.append(r); times.append(dt)
+    value = sample * args.steps / sum(times)
+    line = {
+        "impl": "reference", "metric": "MIQP plans/sec at 1e-4 gap", "value": value, "unit": "plans/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "plans_per_step": sample, "gap": GAP},
+        "cpu_baseline": {"value": value, "unit": "plans/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} plans of the workload per step, one oracle solve per host thread"},
+        "e2e": {"value": value, "unit": "plans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=2048, help="plans per GPU per step")
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--nodes-per-round", type=int, default=0)
+    ap.add_argument("--cpu-sample", type=int, default=48)
+    ap.add_argument("--latency-plans", type=int, default=16)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the MIQP backend has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import planner_miqp_b200 as P
+    B = args.batch
+    plans = make_plans(rank * B, B)
+    N = plans[0].N
+    solver = P.Solver(device=local_rank, nodes_per_round=args.nodes_per_round)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ------------------------------------------------------
+    solver.upload(plans, gap_tol=GAP, time_limit=600.0)
+    for _ in range(args.warmup):
+        flush.fill_(1)
+        solver.run()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    dev_ms, node_ms, launches, stats_acc = [], 0.0, 0, None
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        ms = solver.run()
+        dev_ms.append(ms)
+        st = solver.run_stats()
+        node_ms += st["node_kernel_ms"]; launches += st["launches"]
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    xs, infos = solver.fetch()
+    st = solver.run_stats()
+    n_ok = sum(1 for i in infos if i.status == 0 and i.proven)
+    worst_viol = max((i.max_violation for i in infos if i.status == 0), default=float("nan"))
+    total_ms = sum(dev_ms)
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        ok_t = torch.tensor([n_ok], dtype=torch.int64, device="cuda")
+        dist.all_reduce(ok_t)
+        n_ok_all = int(ok_t.item())
+    else:
+        n_ok_all = n_ok
+    value = world * B * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers ------------------------------------
+    for _ in range(2):
+        solver.solve_batch(plans, gap_tol=GAP, time_limit=600.0)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.fill_(1)
+        xs, infos2 = solver.solve_batch(plans, gap_tol=GAP, time_limit=600.0)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    st2 = solver.run_stats()
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * B * args.steps / e2e_s
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (bnb_nodes_kernel) --------------------------------
+    fp64_peak = solver.measure_fp64_peak()
+    flops = algorithmic_flops(st, N)
+    node_ms_last = st["node_kernel_ms"]
+    achieved_tf = flops / (node_ms_last * 1e-3) / 1e12 if node_ms_last > 0 else 0.0
+    peaks = measured_peaks()
+    # algorithmic HBM bytes: every node relaxation reads its record and writes its children
+    ndec = 6 * N + 5 * plans[0].O * N
+    node_bytes = 2.0 * (ndec + 32)
+    hbm_gbs = st["nodes"] * node_bytes / (node_ms_last * 1e-3) / 1e9 if node_ms_last > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "node_kernel_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    roofline = {
+        "kernel": "bnb_nodes_kernel", "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+        "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": traffic,
+        "peak_source": "DFMA micro-benchmark in this run (MEASURED_PEAKS.json has no FP64 figure)",
+        "kernel_share_of_step": node_ms / total_ms if total_ms else None,
+        "note": "latency-bound FP64 kernel (one warp per node relaxation, serial Riccati sweeps); see DESIGN.md",
+        "hbm": {"achieved": hbm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": hbm_gbs / peaks["hbm_gbs"] if peaks["hbm_gbs"] else None, "peak_source": peaks["source"]},
+        "nodes_per_s": st["nodes"] / (node_ms_last * 1e-3) if node_ms_last > 0 else None,
+        "ipm_iters_per_node": st["qp_iters"] / max(st["nodes"], 1),
+    }
+
+    # ---- single-plan latency ----------------------------------------------------------------
+    lat_e2e, lat_dev = [], []
+    for k in range(min(args.latency_plans, B)):
+        t0 = time.perf_counter()
+        solver.solve(plans[k], gap_tol=GAP, time_limit=60.0)
+        lat_e2e.append(1e3 * (time.perf_counter() - t0))
+        lat_dev.append(solver.run_stats()["total_ms"])
+
+    # ---- CPU baseline (rank 0, bounded sample, one core) --------------------------------------
+    sample = min(args.cpu_sample, B)
+    cpu_rate, cpu_dt, cpu_ok = cpu_oracle_rate(plans[:sample], 1)
+    # parity spot check of the sample against the oracle (objective within 1e-4 relative)
+    from oracle import oracle as O
+    mism = 0
+    for k in range(min(8, sample)):
+        xo, io = O.solve(plans[k], gap_tol=GAP, time_limit=60.0)
+        if io.status != infos[k].status or (io.status == 0 and abs(io.objective - infos[k].objective) > 1e-4 * max(abs(io.objective), 1e-9)):
+            mism += 1
+
+    line = {
+        "metric": "MIQP plans/sec at 1e-4 gap", "value": value, "unit": "plans/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "plans_per_gpu_per_step": B, "gap": GAP, "cache": "L2 flushed between steps (256 MiB write)",
+                   "nodes_per_plan_per_round": args.nodes_per_round or "auto"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "plans/s", "h2d_bytes_per_step": st2["h2d_bytes"], "d2h_bytes_per_step": st2["d2h_bytes"],
+                "ms_per_step": 1e3 * e2e_s / args.steps},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "cpu_baseline": {"value": cpu_rate, "unit": "plans/s", "cores": 1, "kind": "port",
+                         "sample": f"first {sample} plans of the batch, oracle/miqp_oracle_bnb.c, {cpu_dt:.1f} s"},
+        "latency_p50_ms": {"e2e": statistics.median(lat_e2e), "device": statistics.median(lat_dev), "plans": len(lat_e2e)},
+        "solved": {"proven_optimal": n_ok_all, "plans": world * B, "worst_violation": worst_viol,
+                   "oracle_mismatches_in_sample": mism, "nodes_per_plan": st["nodes"] / B, "rounds": st["rounds"]},
+        "wall_s_timed_region": t_wall,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -158,6 +158,10 @@ typedef struct MiqpB200RunStats {
 } MiqpB200RunStats;
 int miqp_b200_run_stats(const MiqpB200Solver *s, MiqpB200RunStats *out);
 
+/* FP64 FMA throughput of the device in TFLOP/s (DFMA micro-benchmark, best of 5): the
+ * roofline denominator of the node kernel, which MEASURED_PEAKS.json does not provide. */
+int miqp_b200_measure_fp64_peak(MiqpB200Solver *s, double *tflops);
+
 #ifdef __cplusplus
 }
 #endif

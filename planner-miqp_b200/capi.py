@@ -21,7 +21,7 @@ DECLARED_SYMBOLS = [
     "miqp_b200_version", "miqp_b200_default_options", "miqp_b200_create", "miqp_b200_destroy",
     "miqp_b200_last_error", "miqp_b200_layout", "miqp_b200_sizes", "miqp_b200_assemble",
     "miqp_b200_evaluate", "miqp_b200_solve_batch", "miqp_b200_batch_upload", "miqp_b200_batch_run",
-    "miqp_b200_batch_fetch", "miqp_b200_run_stats",
+    "miqp_b200_batch_fetch", "miqp_b200_run_stats", "miqp_b200_measure_fp64_peak",
 ]
 
 
@@ -125,6 +125,7 @@ def load_library():
     lib.miqp_b200_batch_run.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     lib.miqp_b200_batch_fetch.argtypes = [C.c_void_p, C.POINTER(_dp), C.POINTER(CSolveInfo)]
     lib.miqp_b200_run_stats.argtypes = [C.c_void_p, C.POINTER(CRunStats)]
+    lib.miqp_b200_measure_fp64_peak.argtypes = [C.c_void_p, _dp]
     _lib = lib
     return lib
 
@@ -327,6 +328,11 @@ class Solver:
         st = CRunStats()
         self._check(self._lib.miqp_b200_run_stats(self._h, C.byref(st)), "miqp_b200_run_stats")
         return {n: getattr(st, n) for n, _ in CRunStats._fields_}
+
+    def measure_fp64_peak(self) -> float:
+        tf = C.c_double()
+        self._check(self._lib.miqp_b200_measure_fp64_peak(self._h, C.byref(tf)), "miqp_b200_measure_fp64_peak")
+        return tf.value
 
     @staticmethod
     def _info(i: CSolveInfo) -> SolveInfo:

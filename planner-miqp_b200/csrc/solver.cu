@@ -22,6 +22,7 @@
 #include "kernels.cuh"
 
 using namespace miqp;
+namespace miqp { double measure_fp64_tflops(int num_sms, cudaStream_t st, int reps); }
 
 namespace {
 
@@ -718,6 +719,15 @@ int miqp_b200_solve_batch(MiqpB200Solver *s, const MiqpB200Problem *problems, in
   rc = miqp_b200_batch_run(s, nullptr);
   if (rc != MIQP_B200_OK) return rc;
   return miqp_b200_batch_fetch(s, x_out, infos);
+}
+
+int miqp_b200_measure_fp64_peak(MiqpB200Solver *s, double *tflops) {
+  if (!s || !tflops) return MIQP_B200_ERR_ARG;
+  if (cudaSetDevice(s->opt.device) != cudaSuccess) return fail(s, MIQP_B200_ERR_CUDA, "cudaSetDevice failed");
+  const double tf = miqp::measure_fp64_tflops(s->num_sms, s->stream, 5);
+  if (tf <= 0.0) return fail(s, MIQP_B200_ERR_CUDA, "fp64 micro-benchmark failed");
+  *tflops = tf;
+  return MIQP_B200_OK;
 }
 
 int miqp_b200_run_stats(const MiqpB200Solver *s, MiqpB200RunStats *out) {

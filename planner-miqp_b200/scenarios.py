@@ -1,0 +1,73 @@
+"""Synthetic planning scenarios of the shapes named in BASELINE.json.
+
+Every scenario is generated from a seed with the reference's default settings
+(src/miqp_planner_data.hpp:190-242) through ``PlanBuilder``; no data set is involved.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from .model_parameters import PlanBuilder, Settings, default_settings
+
+
+def settings_for(nr_regions=32, nr_steps=40, ts=0.25, gap=1e-4, time_limit=10.0) -> Settings:
+    s = default_settings()
+    s.nr_regions, s.nr_steps, s.ts = nr_regions, nr_steps, ts
+    s.relative_mip_gap_tolerance, s.max_solution_time = gap, time_limit
+    return s
+
+
+def lane_following(seed: int = 0, nr_regions=16, nr_steps=20):
+    """config 1c: miqp_planner_test `plan1` shape (test/miqp_planner_test.cc:279-308)."""
+    rng = np.random.default_rng(seed)
+    s = settings_for(nr_regions, nr_steps)
+    b = PlanBuilder(s)
+    v0 = 4.0 + (rng.uniform(-1, 1) if seed else 0.0)
+    b.add_car([0, v0, 0, rng.uniform(-0.5, 0.5) if seed else 0.0, 0.1, 0], [[0, 0], [200, 0]], 5.0, 1.0)
+    b.add_environment_polygon([[-49, -49], [249, -49], [249, 49], [-49, 49]])
+    return b
+
+
+def obstacle_scenario(seed: int = 0, nr_regions=32, nr_steps=40, ts=0.25, n_static=1, n_dynamic=1, soft=False):
+    """config 2: single agent, static + dynamic-occupancy obstacles, N=40, 32 fitted regions.
+
+    Environment rectangle [-10,200]x[-10,20] shrunk by the collision radius; the ego starts at
+    x0=[0,5,0,0,0.1,0] and follows the x axis at 5 m/s; static 1x1 boxes at (20+U[0,20], +-1.5)
+    (centre offset +-U[0.3,1.5] so that the inflated box blocks the lane) and dynamic 1x1 boxes
+    from (10, +-U[2.5,4]) moving along +x at U[2,6] m/s, all inflated by the collision radius
+    to 3x3 squares with 4 edges (src/miqp_planner.cpp:444-488)."""
+    rng = np.random.default_rng(1000 + seed)
+    s = settings_for(nr_regions, nr_steps, ts)
+    b = PlanBuilder(s)
+    v0 = 5.0 + rng.uniform(-1.0, 1.0)
+    b.add_car([0, v0, 0, rng.uniform(-0.3, 0.3), 0.1, 0], [[0, 0], [400, 0]], 5.0, 1.0)
+    r = s.collisionRadius
+    b.add_environment_polygon([[-10 + r, -10 + r], [200 - r, -10 + r], [200 - r, 20 - r], [-10 + r, 20 - r]])
+    for k in range(n_static):
+        side = 1.0 if rng.uniform() < 0.5 else -1.0
+        b.add_box_obstacle([[20.0 + rng.uniform(0, 20) + 25.0 * k, side * rng.uniform(0.3, 1.5), 0.0]], 1.0, 1.0, soft=soft)
+    for k in range(n_dynamic):
+        v = rng.uniform(2.0, 6.0)
+        y = (1.0 if rng.uniform() < 0.5 else -1.0) * rng.uniform(2.5, 4.0)
+        centers = [[10.0 + 15.0 * k + v * s.ts * i, y, 0.0] for i in range(nr_steps)]
+        b.add_box_obstacle(centers, 1.0, 1.0, soft=soft)
+    return b
+
+
+def random_single_agent(seed: int, nr_regions=16, nr_steps=20):
+    """config 4 restricted to one agent: straight or single-bend reference, 0-2 obstacles."""
+    rng = np.random.default_rng(5000 + seed)
+    s = settings_for(nr_regions, nr_steps)
+    b = PlanBuilder(s)
+    bend = math.radians(rng.uniform(-30, 30)) if rng.uniform() < 0.5 else 0.0
+    ref = [[0, 0], [30, 0], [30 + 170 * math.cos(bend), 170 * math.sin(bend)]]
+    v0 = rng.uniform(3, 8)
+    b.add_car([0, v0, 0, rng.uniform(-0.5, 0.5), 0.05, 0], ref, v0, 1.0)
+    if rng.uniform() < 0.5:
+        b.add_environment_polygon([[-20, -60], [220, -60], [220, 60], [-20, 60]])
+    for k in range(int(rng.integers(0, 3))):
+        side = 1.0 if rng.uniform() < 0.5 else -1.0
+        b.add_box_obstacle([[15.0 + rng.uniform(0, 20) + 20 * k, side * rng.uniform(1.0, 2.0), 0.0]], 1.0, 1.0)
+    return b
