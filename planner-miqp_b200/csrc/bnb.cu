@@ -427,35 +427,40 @@ __device__ __forceinline__ void effective_regions(const WarpCtx &w) {
   __syncwarp();
 }
 
-__host__ __device__ inline int node_smem_dec_offset(int maxN) {
-  int b = maxN * (S_STRIDE + V_STRIDE + 1) * 8;  // S, V, auxd
-  b += maxN * 4 * 4;                             // jeff + aux[3N]
-  return (b + 15) & ~15;
+// shared memory of one warp: S[N][S_STRIDE] V[N][V_STRIDE] T[T_SIZE] auxd[N] | rows[kmax][N] (16-byte
+// aligned) | jeff[N] aux[3N] | dec imp alternatives
+struct NodeSmem { int off_rows, off_int, off_dec, total; };
+__host__ __device__ inline NodeSmem node_smem_layout(int maxN, int kmax, int ndec_stride) {
+  NodeSmem L;
+  int b = (maxN * (S_STRIDE + V_STRIDE + 1) + T_SIZE) * 8;
+  b = (b + 15) & ~15;
+  L.off_rows = b; b += kmax * maxN * 16;
+  L.off_int = b; b += maxN * 4 * 4;
+  b = (b + 15) & ~15;
+  L.off_dec = b; b += 2 * ndec_stride + 272;
+  L.total = (b + 15) & ~15;
+  return L;
 }
-int node_kernel_smem_per_warp(int maxN, int ndec_stride) {
-  int b = node_smem_dec_offset(maxN) + 2 * ndec_stride + 272;  // dec, imp, alternatives
-  return (b + 15) & ~15;
-}
+int node_kernel_smem_per_warp(int maxN, int kmax, int ndec_stride) { return node_smem_layout(maxN, kmax, ndec_stride).total; }
 
 __global__ void __launch_bounds__(128) bnb_nodes_kernel(BnbState st, const DevProb *probs, const double *dblob,
                                                         const int *iblob, int smem_per_warp, int maxN) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int gw = blockIdx.x * (blockDim.x >> 5) + warp;
   unsigned char *base = smem_raw + (size_t)warp * smem_per_warp;
+  const NodeSmem L = node_smem_layout(maxN, st.kmax, st.ndec_stride);
   WarpCtx w;
   w.D = dblob; w.I = iblob; w.lane = lane;
   w.S = reinterpret_cast<double *>(base);
   w.V = w.S + maxN * S_STRIDE;
-  w.auxd = w.V + maxN * V_STRIDE;
-  w.jeff = reinterpret_cast<int *>(w.auxd + maxN);
+  w.T = w.V + maxN * V_STRIDE;
+  w.auxd = w.T + T_SIZE;
+  w.rows = reinterpret_cast<double2 *>(base + L.off_rows);
+  w.jeff = reinterpret_cast<int *>(base + L.off_int);
   w.aux = w.jeff + maxN;
-  w.dec = base + node_smem_dec_offset(maxN);
+  w.dec = base + L.off_dec;
   w.imp = w.dec + st.ndec_stride;
   unsigned char *alts = w.imp + st.ndec_stride;
-  w.npad = st.npad;
-  w.arr_stride = (long)st.kmax * st.npad;
-  w.rs = st.rowscratch + (long)gw * 4 * w.arr_stride;
   const int nwork = *reinterpret_cast<volatile int *>(st.work_cnt);
 
   for (;;) {

@@ -21,7 +21,7 @@ struct BnbState {
   int zstride;          // doubles per incumbent trajectory (max C*N*8 + 4*P*N)
   int kmax;             // row slots per stage (max over plans)
   int npad;             // stages padded to a multiple of 32 (max over plans)
-  int nwarps;           // resident warps of the node kernel (row scratch slots)
+  int nwarps;           // resident warps of the node kernel
   int sel_per_plan;     // K: node relaxations taken per plan per round
   int work_cap;
   // node pools [count][cap]
@@ -45,7 +45,6 @@ struct BnbState {
   unsigned long long *stat_nodes, *stat_iters, *stat_rows;
   // round control
   int2 *work; int *work_cnt; int *work_next; int *active; int *err;
-  double *rowscratch;   // [nwarps][4][kmax][npad]
 };
 
 void launch_bnb_init(const BnbState &st, const DevProb *probs, const unsigned char *warm_dec /* [count][ndec_stride] or null */,
@@ -56,7 +55,7 @@ int launch_bnb_nodes(const BnbState &st, const DevProb *probs, const double *dbl
                      int smem_per_warp, int warps_per_cta, int ctas, int maxN, cudaStream_t s);
 void launch_bnb_finish(const BnbState &st, const DevProb *probs, const double *dblob, const int *iblob,
                        double *xall, double *best_bound, cudaStream_t s);
-int node_kernel_smem_per_warp(int maxN, int ndec_stride);
+int node_kernel_smem_per_warp(int maxN, int kmax, int ndec_stride);
 int node_kernel_max_ctas(int smem_per_cta, int threads);
 
 }  // namespace miqp

@@ -17,9 +17,11 @@
 // a stage (row generation, residuals, Hessian accumulation, step lengths), lanes = matrix
 // entries for the backward Riccati factorisation, and the cheap vector sweeps are done
 // redundantly by all lanes without any synchronisation.  Inequality rows are never stored:
-// their coefficients are regenerated from the small per-plan tables in every pass; only
-// (s, lambda, rp, ds*dl) per row live in a warp-private, L2-resident global scratch laid
-// out [array][slot][stage] so that lanes (stages) access it coalesced.
+// their coefficients are regenerated from the small per-plan tables in every pass; only the
+// slack and multiplier (s, lambda) of every row live in shared memory, laid out
+// [slot][stage] so that lanes (stages) access consecutive 16-byte pairs; residuals, the
+// affine step and the pending Newton step are recomputed from the stage vectors instead of
+// being stored (3 dot products per row instead of 2 more arrays).
 //
 // This file handles one car per plan (C == 1); the multi-car kernel couples the cars of a
 // stage through the pair rows and is a separate instantiation.
@@ -33,10 +35,11 @@ constexpr unsigned FULL = 0xffffffffu;
 
 // per-stage shared-memory records (strides are odd so that lane = stage accesses are
 // bank-conflict free for 64-bit words)
-constexpr int S_STRIDE = 41;  // [0..20] Pxx packed lower, [21..32] G = Phi_ux (2x6), [33..35] Phi_uu, [36..37] Muu diag, [38..40] Finv
-constexpr int S_G = 21, S_PUU = 33, S_MUU = 36, S_FINV = 38;
-constexpr int V_STRIDE = 41;  // z[8] g[8] dz[8] p[6] nu[6] phiu[2] k[2]
-constexpr int V_Z = 0, V_G = 8, V_DZ = 16, V_P = 24, V_NU = 30, V_PHIU = 36, V_K = 38;
+constexpr int S_STRIDE = 39;  // [0..20] Mxx packed lower, [21..32] G = Phi_ux (2x6), [33..35] Finv, [36..37] Muu diag
+constexpr int S_G = 21, S_FINV = 33, S_MUU = 36;
+constexpr int V_STRIDE = 35;  // z[8] g[8] dz[8] dza[8] k[2]
+constexpr int V_Z = 0, V_G = 8, V_DZ = 16, V_DZA = 24, V_K = 32;
+constexpr int T_P = 0, T_PV = 48, T_PUU = 60, T_PHIU = 63, T_SIZE = 66;  // warp scratch: 2 x P (24), 2 x p (6), Phi_uu (3), phi_u (2)
 
 __device__ __forceinline__ int pidx(int a, int b) { return a >= b ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a; }
 
@@ -51,9 +54,8 @@ struct WarpCtx {
   int *jeff;            // effective region per stage (-1 unknown)
   int *aux;             // [3N] scan tables: best alt, region_decided, blame
   double *auxd;         // [N] scan: best non-frozen violation
-  double *rs;           // row scratch of this warp
-  long arr_stride;      // kmax * npad
-  int npad;
+  double *T;            // [T_SIZE] Riccati scratch (value function of the next stage)
+  double2 *rows;        // [kmax][N] (s, lambda) per inequality row
   int lane, N;
 };
 
@@ -192,134 +194,131 @@ __device__ __forceinline__ void visit_rows(const WarpCtx &w, int i, Vis &v) {
 // ---------------------------------------------------------------------------------------
 // row passes
 // ---------------------------------------------------------------------------------------
-struct RowIO {
-  double *base;       // rs + i
-  long arr; int npad;
-  __device__ __forceinline__ double &at(int arrk, int slot) const { return base[arrk * arr + (long)slot * npad]; }
+struct StepCtx {  // quantities of the last Newton step, needed to recompute it row by row
+  double alpha, sigmu;
+  bool pending;
 };
-enum { R_S = 0, R_LAM = 1, R_RP = 2, R_DD = 3 };
+
+__device__ __forceinline__ double dot6(const double a[6], const double y[8]) {
+  double v = 0.0;
+#pragma unroll
+  for (int t = 0; t < 6; ++t) v += a[t] * y[t];
+  return v;
+}
 
 struct PassInit {  // s = max(h - g.z, 1), lambda = 1
-  RowIO io; double y[8]; int m;
-  template <int T> __device__ __forceinline__ void bound(int slot, double sgn, double rhs) {
-    double sl = rhs - sgn * y[T];
-    io.at(R_S, slot) = sl > 1.0 ? sl : 1.0; io.at(R_LAM, slot) = 1.0; ++m;
+  double2 *rows; int N, i; double y[8];
+  __device__ __forceinline__ void put(int slot, double gz, double rhs) {
+    const double sl = rhs - gz;
+    rows[slot * N + i] = make_double2(sl > 1.0 ? sl : 1.0, 1.0);
   }
-  __device__ __forceinline__ void general(int slot, const double a[6], double rhs) {
-    double gz = 0.0;
-#pragma unroll
-    for (int t = 0; t < 6; ++t) gz += a[t] * y[t];
-    double sl = rhs - gz;
-    io.at(R_S, slot) = sl > 1.0 ? sl : 1.0; io.at(R_LAM, slot) = 1.0; ++m;
-  }
+  template <int T> __device__ __forceinline__ void bound(int slot, double sgn, double rhs) { put(slot, sgn * y[T], rhs); }
+  __device__ __forceinline__ void general(int slot, const double a[6], double rhs) { put(slot, dot6(a, y), rhs); }
 };
 
-struct PassA {  // apply pending step, residuals, Hessian and predictor gradient
-  RowIO io; double y[8];
-  double alpha; bool pending;
+struct PassA {  // apply the pending step, residuals, Hessian and predictor gradient
+  double2 *rows; int N, i; StepCtx sc;
+  double y[8], d[8], da[8];
   double H[21], Huu[2], gx[8], gl[8];
   double rpn, musum, lmax; int m;
-  __device__ __forceinline__ void load(int slot, double &s, double &lam) {
-    s = io.at(R_S, slot); lam = io.at(R_LAM, slot);
-    if (pending) { s += alpha * io.at(R_RP, slot); lam += alpha * io.at(R_DD, slot); }
-  }
-  __device__ __forceinline__ void stats(int slot, double s, double lam, double rp) {
-    io.at(R_S, slot) = s; io.at(R_LAM, slot) = lam; io.at(R_RP, slot) = rp;
+  // returns (weight, weight*rp, lambda) of the row after the update
+  __device__ __forceinline__ void core(int slot, double gz, double gdz, double gda, double rhs, double &wgt, double &wr, double &lam_out) {
+    double2 v = rows[slot * N + i];
+    double s = v.x, lam = v.y;
+    if (sc.pending) {
+      const double rp_old = (gz - sc.alpha * gdz) + s - rhs;
+      const double inv = 1.0 / s;
+      const double dsa = -rp_old - gda;
+      const double dla = -lam - (lam * inv) * dsa;
+      const double ds = -rp_old - gdz;
+      const double rc = s * lam + dsa * dla - sc.sigmu;
+      const double dl = -(rc + lam * ds) * inv;
+      s += sc.alpha * ds; lam += sc.alpha * dl;
+      rows[slot * N + i] = make_double2(s, lam);
+    }
+    const double rp = gz + s - rhs;
+    wgt = lam / s; wr = wgt * rp; lam_out = lam;
     rpn = fmax(rpn, fabs(rp)); musum += s * lam; lmax = fmax(lmax, lam); ++m;
   }
   template <int T> __device__ __forceinline__ void bound(int slot, double sgn, double rhs) {
-    double s, lam; load(slot, s, lam);
-    double rp = sgn * y[T] + s - rhs;
-    double wgt = lam / s;
+    double wgt, wr, lam;
+    core(slot, sgn * y[T], sgn * d[T], sgn * da[T], rhs, wgt, wr, lam);
     if (T < 6) H[T * (T + 1) / 2 + T] += wgt; else Huu[T - 6] += wgt;
-    gx[T] += sgn * (wgt * rp); gl[T] += sgn * lam;
-    stats(slot, s, lam, rp);
+    gx[T] += sgn * wr; gl[T] += sgn * lam;
   }
   __device__ __forceinline__ void general(int slot, const double a[6], double rhs) {
-    double s, lam; load(slot, s, lam);
-    double gz = 0.0;
-#pragma unroll
-    for (int t = 0; t < 6; ++t) gz += a[t] * y[t];
-    double rp = gz + s - rhs;
-    double wgt = lam / s;
+    double wgt, wr, lam;
+    core(slot, dot6(a, y), dot6(a, d), dot6(a, da), rhs, wgt, wr, lam);
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
-      double wa = wgt * a[r];
+      const double wa = wgt * a[r];
 #pragma unroll
       for (int c = 0; c <= r; ++c) H[r * (r + 1) / 2 + c] += wa * a[c];
     }
-    double wr = wgt * rp;
 #pragma unroll
     for (int t = 0; t < 6; ++t) { gx[t] += a[t] * wr; gl[t] += a[t] * lam; }
-    stats(slot, s, lam, rp);
   }
 };
 
 struct PassD {  // affine step: ratios and the three sums that give mu_aff for any step length
-  RowIO io; double d[8];
+  double2 *rows; int N, i; double y[8], da[8];
   double amin, s1, s2;
-  __device__ __forceinline__ void row(int slot, double gd) {
-    double s = io.at(R_S, slot), lam = io.at(R_LAM, slot), rp = io.at(R_RP, slot);
-    double wgt = lam / s;
-    double dsa = -rp - gd;
-    double dla = -lam - wgt * dsa;
+  __device__ __forceinline__ void row(int slot, double gz, double gda, double rhs) {
+    const double2 v = rows[slot * N + i];
+    const double s = v.x, lam = v.y;
+    const double rp = gz + s - rhs;
+    const double dsa = -rp - gda;
+    const double dla = -lam - (lam / s) * dsa;
     if (dsa < 0.0) amin = fmin(amin, -s / dsa);
     if (dla < 0.0) amin = fmin(amin, -lam / dla);
     s1 += s * dla + lam * dsa; s2 += dsa * dla;
-    io.at(R_DD, slot) = dsa * dla;
   }
-  template <int T> __device__ __forceinline__ void bound(int slot, double sgn, double) { row(slot, sgn * d[T]); }
-  __device__ __forceinline__ void general(int slot, const double a[6], double) {
-    double gd = 0.0;
-#pragma unroll
-    for (int t = 0; t < 6; ++t) gd += a[t] * d[t];
-    row(slot, gd);
-  }
+  template <int T> __device__ __forceinline__ void bound(int slot, double sgn, double rhs) { row(slot, sgn * y[T], sgn * da[T], rhs); }
+  __device__ __forceinline__ void general(int slot, const double a[6], double rhs) { row(slot, dot6(a, y), dot6(a, da), rhs); }
 };
 
 struct PassE {  // corrector gradient
-  RowIO io; double sigmu; double gx[8];
-  __device__ __forceinline__ double coef(int slot) {
-    double s = io.at(R_S, slot), lam = io.at(R_LAM, slot), rp = io.at(R_RP, slot), dd = io.at(R_DD, slot);
-    return (lam * rp - (dd - sigmu)) / s;
+  double2 *rows; int N, i; double sigmu; double y[8], da[8]; double gx[8];
+  __device__ __forceinline__ double coef(int slot, double gz, double gda, double rhs) {
+    const double2 v = rows[slot * N + i];
+    const double s = v.x, lam = v.y;
+    const double inv = 1.0 / s;
+    const double rp = gz + s - rhs;
+    const double dsa = -rp - gda;
+    const double dla = -lam - (lam * inv) * dsa;
+    return (lam * rp - (dsa * dla - sigmu)) * inv;
   }
-  template <int T> __device__ __forceinline__ void bound(int slot, double sgn, double) { gx[T] += sgn * coef(slot); }
-  __device__ __forceinline__ void general(int slot, const double a[6], double) {
-    double cf = coef(slot);
+  template <int T> __device__ __forceinline__ void bound(int slot, double sgn, double rhs) { gx[T] += sgn * coef(slot, sgn * y[T], sgn * da[T], rhs); }
+  __device__ __forceinline__ void general(int slot, const double a[6], double rhs) {
+    const double cf = coef(slot, dot6(a, y), dot6(a, da), rhs);
 #pragma unroll
     for (int t = 0; t < 6; ++t) gx[t] += a[t] * cf;
   }
 };
 
-struct PassG {  // final step: ds, dl (stored in the rp / dd slots) and the step length
-  RowIO io; double d[8]; double sigmu; double amin;
-  __device__ __forceinline__ void row(int slot, double gd) {
-    double s = io.at(R_S, slot), lam = io.at(R_LAM, slot), rp = io.at(R_RP, slot), dd = io.at(R_DD, slot);
-    double ds = -rp - gd;
-    double rc = s * lam + dd - sigmu;
-    double dl = -(rc + lam * ds) / s;
+struct PassG {  // step length of the combined step
+  double2 *rows; int N, i; double sigmu; double y[8], d[8], da[8]; double amin;
+  __device__ __forceinline__ void row(int slot, double gz, double gdz, double gda, double rhs) {
+    const double2 v = rows[slot * N + i];
+    const double s = v.x, lam = v.y;
+    const double inv = 1.0 / s;
+    const double rp = gz + s - rhs;
+    const double dsa = -rp - gda;
+    const double dla = -lam - (lam * inv) * dsa;
+    const double ds = -rp - gdz;
+    const double rc = s * lam + dsa * dla - sigmu;
+    const double dl = -(rc + lam * ds) * inv;
     if (ds < 0.0) amin = fmin(amin, -s / ds);
     if (dl < 0.0) amin = fmin(amin, -lam / dl);
-    io.at(R_RP, slot) = ds; io.at(R_DD, slot) = dl;
   }
-  template <int T> __device__ __forceinline__ void bound(int slot, double sgn, double) { row(slot, sgn * d[T]); }
-  __device__ __forceinline__ void general(int slot, const double a[6], double) {
-    double gd = 0.0;
-#pragma unroll
-    for (int t = 0; t < 6; ++t) gd += a[t] * d[t];
-    row(slot, gd);
-  }
+  template <int T> __device__ __forceinline__ void bound(int slot, double sgn, double rhs) { row(slot, sgn * y[T], sgn * d[T], sgn * da[T], rhs); }
+  __device__ __forceinline__ void general(int slot, const double a[6], double rhs) { row(slot, dot6(a, y), dot6(a, d), dot6(a, da), rhs); }
 };
 
 struct PassViol {  // worst primal violation of the current point
   double y[8]; double worst;
   template <int T> __device__ __forceinline__ void bound(int, double sgn, double rhs) { worst = fmax(worst, sgn * y[T] - rhs); }
-  __device__ __forceinline__ void general(int, const double a[6], double rhs) {
-    double gz = 0.0;
-#pragma unroll
-    for (int t = 0; t < 6; ++t) gz += a[t] * y[t];
-    worst = fmax(worst, gz - rhs);
-  }
+  __device__ __forceinline__ void general(int, const double a[6], double rhs) { worst = fmax(worst, dot6(a, y) - rhs); }
 };
 
 // ---------------------------------------------------------------------------------------
@@ -341,7 +340,7 @@ __device__ __forceinline__ void ab_column(const DevProb &p, int a, int &row0, in
 }
 
 struct PhiEntry {  // one entry (a,b) of Phi = M + [A B]' P [A B]
-  int a, b, n;
+  int a, b;
   int pi[9]; double cf[9];
   __device__ __forceinline__ void setup(const DevProb &p, int e) {
     if (e < 21) { a = 0; while ((a + 1) * (a + 2) / 2 <= e) ++a; b = e - a * (a + 1) / 2; }
@@ -349,7 +348,6 @@ struct PhiEntry {  // one entry (a,b) of Phi = M + [A B]' P [A B]
     else { a = (e == 33) ? 6 : 7; b = (e == 35) ? 7 : 6; }
     int ra, ca, rb, cb; double fa[3], fb[3];
     ab_column(p, a, ra, ca, fa); ab_column(p, b, rb, cb, fb);
-    n = ca * cb;
 #pragma unroll
     for (int k = 0; k < 3; ++k)
 #pragma unroll
@@ -367,51 +365,56 @@ struct PhiEntry {  // one entry (a,b) of Phi = M + [A B]' P [A B]
   }
 };
 
-// Backward factorisation + predictor vector.  On return S_i holds P_i, G_i, Finv_i and V_i
-// holds p_i, k_i for every stage.
+// Backward factorisation + predictor vector.  On return S_i holds G_i, Finv_i and V_i holds
+// k_i for every stage; the value function (P, p) of the next stage only lives in the warp
+// scratch (double buffered).
 __device__ __forceinline__ void riccati_factor(const WarpCtx &w, const PhiEntry &e1, const PhiEntry &e2) {
   const DevProb &p = *w.p;
   const int lane = w.lane, N = w.N;
-  // terminal stage: P = Mxx (in place), p = g_x
-  if (lane < 6) w.V[(N - 1) * V_STRIDE + V_P + lane] = w.V[(N - 1) * V_STRIDE + V_G + lane];
+  double *T = w.T;
+  // terminal stage: P = Mxx, p = g_x
+  {
+    const int nb = (N - 1) & 1;
+    if (lane < 21) T[T_P + 24 * nb + lane] = w.S[(N - 1) * S_STRIDE + lane];
+    if (lane < 6) T[T_PV + 6 * nb + lane] = w.V[(N - 1) * V_STRIDE + V_G + lane];
+  }
   __syncwarp();
   int prow0 = 0, pcnt = 0; double pcf[3] = {0, 0, 0};
   if (lane < 8) ab_column(p, lane, prow0, pcnt, pcf);
   for (int i = N - 2; i >= 0; --i) {
     double *Si = w.S + i * S_STRIDE, *Vi = w.V + i * V_STRIDE;
-    const double *Pn = w.S + (i + 1) * S_STRIDE, *pn = w.V + (i + 1) * V_STRIDE + V_P;
+    const double *Pn = T + T_P + 24 * ((i + 1) & 1), *pn = T + T_PV + 6 * ((i + 1) & 1);
+    double *Pc = T + T_P + 24 * (i & 1), *pc = T + T_PV + 6 * (i & 1);
     // phase 1: Phi entries
     double phi1 = e1.eval(Pn);
-    if (lane < 21) phi1 += Si[lane];                       // Mxx
-    else {                                                 // lanes 21..31: entries 21..31 of G
-      Si[lane] = phi1;                                     // M_ux = 0
-    }
+    if (lane < 21) phi1 += Si[lane];                       // + Mxx
+    else Si[lane] = phi1;                                  // lanes 21..31: G entries 21..31 (M_ux = 0)
     double phix = 0.0;
     if (lane < 8) {                                        // phi = g + [A B]' p_next
       double v = Vi[V_G + lane];
 #pragma unroll
       for (int k = 0; k < 3; ++k) if (k < pcnt) v += pcf[k] * pn[prow0 + k];
-      if (lane < 6) phix = v; else Vi[V_PHIU + lane - 6] = v;
+      if (lane < 6) phix = v; else T[T_PHIU + lane - 6] = v;
     }
     if (lane >= 21 && lane < 25) {                         // entries 32..35
       double phi2 = e2.eval(Pn);
       const int e = lane + 11;
-      if (e == 33) phi2 += Si[S_MUU]; else if (e == 35) phi2 += Si[S_MUU + 1];
-      Si[e] = phi2;
+      if (e == 32) Si[32] = phi2;
+      else { if (e == 33) phi2 += Si[S_MUU]; else if (e == 35) phi2 += Si[S_MUU + 1]; T[T_PUU + e - 33] = phi2; }
     }
     __syncwarp();
     // phase 2: Finv, P_i, p_i, k_i
-    const double f00 = Si[S_PUU], f10 = Si[S_PUU + 1], f11 = Si[S_PUU + 2];
+    const double f00 = T[T_PUU], f10 = T[T_PUU + 1], f11 = T[T_PUU + 2];
     const double idet = 1.0 / (f00 * f11 - f10 * f10);
     const double i00 = f11 * idet, i10 = -f10 * idet, i11 = f00 * idet;
-    const double pu0 = Vi[V_PHIU], pu1 = Vi[V_PHIU + 1];
+    const double pu0 = T[T_PHIU], pu1 = T[T_PHIU + 1];
     const double k0 = -(i00 * pu0 + i10 * pu1), k1 = -(i10 * pu0 + i11 * pu1);
     if (lane < 21) {
       const double g0a = Si[S_G + e1.a], g1a = Si[S_G + 6 + e1.a], g0b = Si[S_G + e1.b], g1b = Si[S_G + 6 + e1.b];
       const double w0 = i00 * g0b + i10 * g1b, w1 = i10 * g0b + i11 * g1b;
-      Si[lane] = phi1 - (g0a * w0 + g1a * w1);
+      Pc[lane] = phi1 - (g0a * w0 + g1a * w1);
     }
-    if (lane < 6) Vi[V_P + lane] = phix + Si[S_G + lane] * k0 + Si[S_G + 6 + lane] * k1;
+    if (lane < 6) pc[lane] = phix + Si[S_G + lane] * k0 + Si[S_G + 6 + lane] * k1;
     if (lane == 31) { Si[S_FINV] = i00; Si[S_FINV + 1] = i10; Si[S_FINV + 2] = i11; Vi[V_K] = k0; Vi[V_K + 1] = k1; }
     __syncwarp();
   }
@@ -425,7 +428,6 @@ __device__ __forceinline__ void riccati_vector(const WarpCtx &w) {
   double pn[6];
 #pragma unroll
   for (int t = 0; t < 6; ++t) pn[t] = w.V[(N - 1) * V_STRIDE + V_G + t];
-  if (w.lane < 6) w.V[(N - 1) * V_STRIDE + V_P + w.lane] = w.V[(N - 1) * V_STRIDE + V_G + w.lane];
   for (int i = N - 2; i >= 0; --i) {
     const double *Si = w.S + i * S_STRIDE;
     double *Vi = w.V + i * V_STRIDE;
@@ -442,15 +444,13 @@ __device__ __forceinline__ void riccati_vector(const WarpCtx &w) {
     const double k0 = -(i00 * phi[6] + i10 * phi[7]), k1 = -(i10 * phi[6] + i11 * phi[7]);
 #pragma unroll
     for (int t = 0; t < 6; ++t) pn[t] = phi[t] + Si[S_G + t] * k0 + Si[S_G + 6 + t] * k1;
-#pragma unroll
-    for (int t = 0; t < 6; ++t) if (w.lane == t) Vi[V_P + t] = pn[t];
     if (w.lane == 6) { Vi[V_K] = k0; Vi[V_K + 1] = k1; }
   }
   __syncwarp();
 }
 
-// forward sweep, all lanes redundantly; writes dz_i (V_DZ)
-__device__ __forceinline__ void riccati_forward(const WarpCtx &w) {
+// forward sweep, all lanes redundantly; writes the step of every stage at offset `dst`
+__device__ __forceinline__ void riccati_forward(const WarpCtx &w, int dst) {
   const DevProb &p = *w.p;
   const int N = w.N;
   const double ts = p.ts, c2 = p.c2, c3 = p.c3;
@@ -468,9 +468,9 @@ __device__ __forceinline__ void riccati_forward(const WarpCtx &w) {
       du1 = Vi[V_K + 1] - (i10 * t0 + i11 * t1);
     }
 #pragma unroll
-    for (int t = 0; t < 6; ++t) if (w.lane == t) Vi[V_DZ + t] = dx[t];
-    if (w.lane == 6) Vi[V_DZ + 6] = du0;
-    if (w.lane == 7) Vi[V_DZ + 7] = du1;
+    for (int t = 0; t < 6; ++t) if (w.lane == t) Vi[dst + t] = dx[t];
+    if (w.lane == 6) Vi[dst + 6] = du0;
+    if (w.lane == 7) Vi[dst + 7] = du1;
 #pragma unroll
     for (int ax = 0; ax < 2; ++ax) {
       const double P = dx[3 * ax], Vv = dx[3 * ax + 1], A = dx[3 * ax + 2], U = ax ? du1 : du0;
@@ -512,84 +512,66 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
   }
   if (__any_sync(FULL, bad)) return res;
 
-  // start: zero jerk (free response), s = max(h - g.z, 1), lambda = 1, nu = 0
+  // start: zero jerk (free response), s = max(h - g.z, 1), lambda = 1
   const double x0[6] = {D[p.o_x0], D[p.o_x0 + 1], D[p.o_x0 + 2], D[p.o_x0 + 3], D[p.o_x0 + 4], D[p.o_x0 + 5]};
   double cn = 0.0;
   for (int i = lane; i < N; i += 32) {
     double *Vi = w.V + i * V_STRIDE;
     const double t = i * p.ts;
+    PassInit v; v.rows = w.rows; v.N = N; v.i = i;
 #pragma unroll
     for (int ax = 0; ax < 2; ++ax) {
       const double P = x0[3 * ax], Vv = x0[3 * ax + 1], A = x0[3 * ax + 2];
-      Vi[V_Z + 3 * ax] = P + t * Vv + 0.5 * t * t * A;
-      Vi[V_Z + 3 * ax + 1] = Vv + t * A;
-      Vi[V_Z + 3 * ax + 2] = A;
+      v.y[3 * ax] = P + t * Vv + 0.5 * t * t * A;
+      v.y[3 * ax + 1] = Vv + t * A;
+      v.y[3 * ax + 2] = A;
     }
-    Vi[V_Z + 6] = 0.0; Vi[V_Z + 7] = 0.0;
+    v.y[6] = 0.0; v.y[7] = 0.0;
 #pragma unroll
-    for (int t6 = 0; t6 < 6; ++t6) Vi[V_NU + t6] = 0.0;
+    for (int t8 = 0; t8 < 8; ++t8) { Vi[V_Z + t8] = v.y[t8]; Vi[V_DZ + t8] = 0.0; Vi[V_DZA + t8] = 0.0; }
     const double *cst = D + p.o_cost + 16 * i;
 #pragma unroll
     for (int t8 = 0; t8 < 8; ++t8) cn = fmax(cn, fabs(cst[8 + t8]));
+    visit_rows(w, i, v);
   }
   cn = warp_max(cn);
   __syncwarp();
-  for (int i = lane; i < N; i += 32) {
-    PassInit v; v.io = RowIO{w.rs + i, w.arr_stride, w.npad}; v.m = 0;
-#pragma unroll
-    for (int t = 0; t < 8; ++t) v.y[t] = w.V[i * V_STRIDE + V_Z + t];
-    visit_rows(w, i, v);
-  }
 
-  double alpha = 0.0; bool pending = false;
+  StepCtx sc; sc.alpha = 0.0; sc.sigmu = 0.0; sc.pending = false;
   int status = 2, stall = 0, it = 0;
+  double rdn = 0.0;
   for (it = 0; it < 100; ++it) {
     // ---- pass A ----
-    double rpn = 0.0, musum = 0.0, lmax = 0.0, rdn = 0.0; int m = 0;
+    double rpn = 0.0, musum = 0.0, lmax = 0.0, rd0 = 0.0; int m = 0;
     for (int i = lane; i < N; i += 32) {
       double *Vi = w.V + i * V_STRIDE, *Si = w.S + i * S_STRIDE;
-      PassA v; v.io = RowIO{w.rs + i, w.arr_stride, w.npad}; v.alpha = alpha; v.pending = pending;
+      PassA v; v.rows = w.rows; v.N = N; v.i = i; v.sc = sc;
       v.rpn = 0.0; v.musum = 0.0; v.lmax = 0.0; v.m = 0;
 #pragma unroll
       for (int t = 0; t < 21; ++t) v.H[t] = 0.0;
       v.Huu[0] = v.Huu[1] = 0.0;
 #pragma unroll
-      for (int t = 0; t < 8; ++t) { v.y[t] = Vi[V_Z + t]; v.gx[t] = 0.0; v.gl[t] = 0.0; }
+      for (int t = 0; t < 8; ++t) { v.y[t] = Vi[V_Z + t]; v.d[t] = Vi[V_DZ + t]; v.da[t] = Vi[V_DZA + t]; v.gx[t] = 0.0; v.gl[t] = 0.0; }
       visit_rows(w, i, v);
       const double *cst = D + p.o_cost + 16 * i;
-      // stage Hessian and predictor gradient
 #pragma unroll
       for (int t = 0; t < 6; ++t) v.H[t * (t + 1) / 2 + t] += cst[t];
 #pragma unroll
       for (int t = 0; t < 21; ++t) Si[t] = v.H[t];
       Si[S_MUU] = v.Huu[0] + cst[6] + 1e-10; Si[S_MUU + 1] = v.Huu[1] + cst[7] + 1e-10;
-      double q[8];
 #pragma unroll
-      for (int t = 0; t < 8; ++t) { q[t] = cst[t] * v.y[t] + cst[8 + t]; Vi[V_G + t] = q[t] + v.gx[t]; }
-      // dual residual: q + G'lambda + [A' nu_{i+1} - nu_i ; B' nu_{i+1}]
-      double nn[6] = {0, 0, 0, 0, 0, 0};
-      if (i + 1 < N) {
-#pragma unroll
-        for (int t = 0; t < 6; ++t) nn[t] = w.V[(i + 1) * V_STRIDE + V_NU + t];
-      }
-      if (i > 0) {
-#pragma unroll
-        for (int ax = 0; ax < 2; ++ax) {
-          const double np_ = nn[3 * ax], nv = nn[3 * ax + 1], na = nn[3 * ax + 2];
-          rdn = fmax(rdn, fabs(q[3 * ax] + v.gl[3 * ax] + np_ - Vi[V_NU + 3 * ax]));
-          rdn = fmax(rdn, fabs(q[3 * ax + 1] + v.gl[3 * ax + 1] + p.ts * np_ + nv - Vi[V_NU + 3 * ax + 1]));
-          rdn = fmax(rdn, fabs(q[3 * ax + 2] + v.gl[3 * ax + 2] + p.c2 * np_ + p.ts * nv + na - Vi[V_NU + 3 * ax + 2]));
-        }
-      }
-      if (i < N - 1) {
-#pragma unroll
-        for (int ax = 0; ax < 2; ++ax)
-          rdn = fmax(rdn, fabs(q[6 + ax] + v.gl[6 + ax] + p.c3 * nn[3 * ax] + p.c2 * nn[3 * ax + 1] + p.ts * nn[3 * ax + 2]));
+      for (int t = 0; t < 8; ++t) {
+        const double q = cst[t] * v.y[t] + cst[8 + t];
+        Vi[V_G + t] = q + v.gx[t];
+        // dual residual at the start (all dynamics multipliers zero); it contracts by
+        // (1 - alpha) with every Newton step afterwards
+        if (it == 0 && ((t < 6 && i > 0) || (t >= 6 && i < N - 1))) rd0 = fmax(rd0, fabs(q + v.gl[t]));
       }
       rpn = fmax(rpn, v.rpn); musum += v.musum; lmax = fmax(lmax, v.lmax); m += v.m;
     }
-    pending = false;
-    rpn = warp_max(rpn); rdn = warp_max(rdn); lmax = warp_max(lmax); musum = warp_sum(musum); m = warp_sum_i(m);
+    sc.pending = false;
+    rpn = warp_max(rpn); lmax = warp_max(lmax); musum = warp_sum(musum); m = warp_sum_i(m);
+    if (it == 0) rdn = warp_max(rd0);
     res.rows += m;
     const double mu = (m > 0) ? musum / m : 0.0;
     __syncwarp();
@@ -597,12 +579,13 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
     if (lmax > 1e13) { status = 1; break; }
     // ---- predictor ----
     riccati_factor(w, e1, e2);
-    riccati_forward(w);
+    riccati_forward(w, V_DZA);
     double amin = 1.0, s1 = 0.0, s2 = 0.0;
     for (int i = lane; i < N; i += 32) {
-      PassD v; v.io = RowIO{w.rs + i, w.arr_stride, w.npad}; v.amin = 1.0; v.s1 = 0.0; v.s2 = 0.0;
+      const double *Vi = w.V + i * V_STRIDE;
+      PassD v; v.rows = w.rows; v.N = N; v.i = i; v.amin = 1.0; v.s1 = 0.0; v.s2 = 0.0;
 #pragma unroll
-      for (int t = 0; t < 8; ++t) v.d[t] = w.V[i * V_STRIDE + V_DZ + t];
+      for (int t = 0; t < 8; ++t) { v.y[t] = Vi[V_Z + t]; v.da[t] = Vi[V_DZA + t]; }
       visit_rows(w, i, v);
       amin = fmin(amin, v.amin); s1 += v.s1; s2 += v.s2;
     }
@@ -613,52 +596,42 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
       const double r = mu_aff / mu;
       sigma = r * r * r;
       if (sigma > 1.0) sigma = 1.0;
-      if (sigma < 0.0) sigma = 0.0;
+      if (!(sigma >= 0.0)) sigma = 0.0;
     }
     const double sigmu = sigma * mu;
     // ---- corrector ----
     for (int i = lane; i < N; i += 32) {
       double *Vi = w.V + i * V_STRIDE;
-      PassE v; v.io = RowIO{w.rs + i, w.arr_stride, w.npad}; v.sigmu = sigmu;
+      PassE v; v.rows = w.rows; v.N = N; v.i = i; v.sigmu = sigmu;
 #pragma unroll
-      for (int t = 0; t < 8; ++t) v.gx[t] = 0.0;
+      for (int t = 0; t < 8; ++t) { v.y[t] = Vi[V_Z + t]; v.da[t] = Vi[V_DZA + t]; v.gx[t] = 0.0; }
       visit_rows(w, i, v);
       const double *cst = D + p.o_cost + 16 * i;
 #pragma unroll
-      for (int t = 0; t < 8; ++t) Vi[V_G + t] = cst[t] * Vi[V_Z + t] + cst[8 + t] + v.gx[t];
+      for (int t = 0; t < 8; ++t) Vi[V_G + t] = cst[t] * v.y[t] + cst[8 + t] + v.gx[t];
     }
     __syncwarp();
     riccati_vector(w);
-    riccati_forward(w);
+    riccati_forward(w, V_DZ);
     amin = 1e300;
     for (int i = lane; i < N; i += 32) {
-      PassG v; v.io = RowIO{w.rs + i, w.arr_stride, w.npad}; v.sigmu = sigmu; v.amin = 1e300;
+      const double *Vi = w.V + i * V_STRIDE;
+      PassG v; v.rows = w.rows; v.N = N; v.i = i; v.sigmu = sigmu; v.amin = 1e300;
 #pragma unroll
-      for (int t = 0; t < 8; ++t) v.d[t] = w.V[i * V_STRIDE + V_DZ + t];
+      for (int t = 0; t < 8; ++t) { v.y[t] = Vi[V_Z + t]; v.d[t] = Vi[V_DZ + t]; v.da[t] = Vi[V_DZA + t]; }
       visit_rows(w, i, v);
       amin = fmin(amin, v.amin);
     }
     amin = warp_min(amin);
-    alpha = 0.995 * amin;
+    double alpha = 0.995 * amin;
     if (alpha > 1.0) alpha = 1.0;
     if (!(alpha >= 0.0)) { status = 2; break; }  // NaN: singular stage system
-    pending = true;
-    // z += alpha dz ; nu += alpha (nu~ - nu) with nu~_i = P_i dx_i + p_i
-    for (int i = lane; i < N; i += 32) {
+    sc.alpha = alpha; sc.sigmu = sigmu; sc.pending = true;
+    rdn *= (1.0 - alpha);
+    for (int i = lane; i < N; i += 32) {   // z += alpha dz (rows are updated lazily by the next pass A)
       double *Vi = w.V + i * V_STRIDE;
-      const double *Si = w.S + i * S_STRIDE;
-      double dz[8];
 #pragma unroll
-      for (int t = 0; t < 8; ++t) { dz[t] = Vi[V_DZ + t]; Vi[V_Z + t] += alpha * dz[t]; }
-      if (i > 0) {
-#pragma unroll
-        for (int r = 0; r < 6; ++r) {
-          double nt = Vi[V_P + r];
-#pragma unroll
-          for (int c = 0; c < 6; ++c) nt += Si[pidx(r, c)] * dz[c];
-          Vi[V_NU + r] += alpha * (nt - Vi[V_NU + r]);
-        }
-      }
+      for (int t = 0; t < 8; ++t) Vi[V_Z + t] += alpha * Vi[V_DZ + t];
     }
     __syncwarp();
     if (alpha < 1e-6) { if (++stall >= 5) { status = 2; break; } } else stall = 0;

@@ -308,7 +308,7 @@ struct MiqpB200Solver {
   // bnb state buffers
   BnbState st;
   DevBuf<unsigned char> b_dec, b_incdec;
-  DevBuf<double> b_bound, b_ub, b_cutoff, b_pruned, b_incz, b_rowscratch;
+  DevBuf<double> b_bound, b_ub, b_cutoff, b_pruned, b_incz;
   DevBuf<int2> b_meta, b_work;
   DevBuf<unsigned long long> b_uid, b_keybuf, b_incuid, b_stats;
   DevBuf<int> b_open, b_opencnt, b_free, b_freecnt, b_sel, b_selcnt, b_done, b_lock, b_ctrl;
@@ -364,8 +364,8 @@ void setup_bnb(MiqpB200Solver *s) {
   st.kmax = pk.max_kmax;
   st.npad = ((pk.maxN + 31) / 32) * 32;
   // node kernel geometry
-  s->smem_per_warp = node_kernel_smem_per_warp(pk.maxN, st.ndec_stride);
-  s->warps_per_cta = 4;
+  s->smem_per_warp = node_kernel_smem_per_warp(pk.maxN, st.kmax, st.ndec_stride);
+  s->warps_per_cta = 1;
   int per_sm = 0;
   while (s->warps_per_cta >= 1) {
     per_sm = node_kernel_max_ctas(s->smem_per_warp * s->warps_per_cta, s->warps_per_cta * 32);
@@ -417,7 +417,6 @@ void setup_bnb(MiqpB200Solver *s) {
   s->b_work.ensure(st.work_cap); st.work = s->b_work.p;
   s->b_ctrl.ensure(4);
   st.work_cnt = s->b_ctrl.p; st.work_next = s->b_ctrl.p + 1; st.active = s->b_ctrl.p + 2; st.err = s->b_ctrl.p + 3;
-  s->b_rowscratch.ensure((size_t)st.nwarps * 4 * st.kmax * st.npad); st.rowscratch = s->b_rowscratch.p;
   s->d_x.ensure(std::max<long>(pk.total_cols, 1));
   s->d_viol.ensure(count); s->d_obj.ensure(count); s->d_bb.ensure(count);
 }
@@ -470,7 +469,7 @@ void miqp_b200_destroy(MiqpB200Solver *s) {
   s->d_probs.release(); s->d_dblob.release(); s->d_iblob.release(); s->d_x.release(); s->d_viol.release();
   s->d_obj.release(); s->d_bb.release(); s->d_warm.release(); s->d_haswarm.release();
   s->b_dec.release(); s->b_incdec.release(); s->b_bound.release(); s->b_ub.release(); s->b_cutoff.release();
-  s->b_pruned.release(); s->b_incz.release(); s->b_rowscratch.release(); s->b_meta.release(); s->b_work.release();
+  s->b_pruned.release(); s->b_incz.release(); s->b_meta.release(); s->b_work.release();
   s->b_uid.release(); s->b_keybuf.release(); s->b_incuid.release(); s->b_stats.release(); s->b_open.release();
   s->b_opencnt.release(); s->b_free.release(); s->b_freecnt.release(); s->b_sel.release(); s->b_selcnt.release();
   s->b_done.release(); s->b_lock.release(); s->b_ctrl.release();

@@ -232,17 +232,15 @@ class PolyLine:
         self.s = np.concatenate([[0.0], np.cumsum(seg)])
 
     def nearest_s(self, x, y):
-        best, bs = float("inf"), 0.0
-        for k in range(len(self.pts) - 1):
-            a, b = self.pts[k], self.pts[k + 1]
-            d = b - a
-            L2 = float(d @ d)
-            t = 0.0 if L2 == 0 else min(max(((x - a[0]) * d[0] + (y - a[1]) * d[1]) / L2, 0.0), 1.0)
-            q = a + t * d
-            dist = (q[0] - x) ** 2 + (q[1] - y) ** 2
-            if dist < best:
-                best, bs = dist, self.s[k] + t * math.sqrt(L2)
-        return bs
+        a, b = self.pts[:-1], self.pts[1:]
+        d = b - a
+        L2 = np.einsum("ij,ij->i", d, d)
+        t = np.where(L2 > 0, ((x - a[:, 0]) * d[:, 0] + (y - a[:, 1]) * d[:, 1]) / np.where(L2 > 0, L2, 1.0), 0.0)
+        t = np.clip(t, 0.0, 1.0)
+        q = a + t[:, None] * d
+        dist = (q[:, 0] - x) ** 2 + (q[:, 1] - y) ** 2
+        k = int(np.argmin(dist))          # first minimum, as a sequential scan with '<' finds it
+        return float(self.s[k] + t[k] * math.sqrt(L2[k]))
 
     def point_at(self, s):
         s = min(max(s, 0.0), self.s[-1])
