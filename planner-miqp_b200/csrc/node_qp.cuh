@@ -41,6 +41,19 @@ constexpr int V_STRIDE = 35;  // z[8] g[8] dz[8] dza[8] k[2]
 constexpr int V_Z = 0, V_G = 8, V_DZ = 16, V_DZA = 24, V_K = 32;
 constexpr int T_P = 0, T_PV = 48, T_PUU = 60, T_PHIU = 63, T_SIZE = 66;  // warp scratch: 2 x P (24), 2 x p (6), Phi_uu (3), phi_u (2)
 
+// 1/x for positive normal x (slacks, multipliers, pivots): MUFU.RCP64H seed (about 20 bits)
+// and one third-order Newton step (e + e^2), i.e. 1 MUFU + 3 DFMA instead of the IEEE
+// division sequence with its slow path.  Relative error < 2^-52.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  const double e = fma(-x, r, 1.0);
+  const double t = fma(e, e, e);
+  r = fma(r, t, r);
+  const double e2 = fma(-x, r, 1.0);   // one more first-order step: exact to rounding
+  return fma(r, e2, r);
+}
+
 __device__ __forceinline__ int pidx(int a, int b) { return a >= b ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a; }
 
 struct WarpCtx {
@@ -227,7 +240,7 @@ struct PassA {  // apply the pending step, residuals, Hessian and predictor grad
     double s = v.x, lam = v.y;
     if (sc.pending) {
       const double rp_old = (gz - sc.alpha * gdz) + s - rhs;
-      const double inv = 1.0 / s;
+      const double inv = fast_rcp(s);
       const double dsa = -rp_old - gda;
       const double dla = -lam - (lam * inv) * dsa;
       const double ds = -rp_old - gdz;
@@ -237,7 +250,7 @@ struct PassA {  // apply the pending step, residuals, Hessian and predictor grad
       rows[slot * N + i] = make_double2(s, lam);
     }
     const double rp = gz + s - rhs;
-    wgt = lam / s; wr = wgt * rp; lam_out = lam;
+    wgt = lam * fast_rcp(s); wr = wgt * rp; lam_out = lam;
     rpn = fmax(rpn, fabs(rp)); musum += s * lam; lmax = fmax(lmax, lam); ++m;
   }
   template <int T> __device__ __forceinline__ void bound(int slot, double sgn, double rhs) {
@@ -262,15 +275,16 @@ struct PassA {  // apply the pending step, residuals, Hessian and predictor grad
 
 struct PassD {  // affine step: ratios and the three sums that give mu_aff for any step length
   double2 *rows; int N, i; double y[8], da[8];
-  double amin, s1, s2;
+  double rmax, s1, s2;   // rmax = 1 / (largest feasible affine step), kept >= 1
   __device__ __forceinline__ void row(int slot, double gz, double gda, double rhs) {
     const double2 v = rows[slot * N + i];
     const double s = v.x, lam = v.y;
     const double rp = gz + s - rhs;
     const double dsa = -rp - gda;
-    const double dla = -lam - (lam / s) * dsa;
-    if (dsa < 0.0) amin = fmin(amin, -s / dsa);
-    if (dla < 0.0) amin = fmin(amin, -lam / dla);
+    const double t = dsa * fast_rcp(s);
+    const double dla = -lam - lam * t;
+    // s + a dsa >= 0  <=>  1/a >= -dsa/s = -t ;  lam + a dla >= 0  <=>  1/a >= -dla/lam = 1 + t
+    rmax = fmax(rmax, fmax(-t, 1.0 + t));
     s1 += s * dla + lam * dsa; s2 += dsa * dla;
   }
   template <int T> __device__ __forceinline__ void bound(int slot, double sgn, double rhs) { row(slot, sgn * y[T], sgn * da[T], rhs); }
@@ -282,7 +296,7 @@ struct PassE {  // corrector gradient
   __device__ __forceinline__ double coef(int slot, double gz, double gda, double rhs) {
     const double2 v = rows[slot * N + i];
     const double s = v.x, lam = v.y;
-    const double inv = 1.0 / s;
+    const double inv = fast_rcp(s);
     const double rp = gz + s - rhs;
     const double dsa = -rp - gda;
     const double dla = -lam - (lam * inv) * dsa;
@@ -297,19 +311,19 @@ struct PassE {  // corrector gradient
 };
 
 struct PassG {  // step length of the combined step
-  double2 *rows; int N, i; double sigmu; double y[8], d[8], da[8]; double amin;
+  double2 *rows; int N, i; double sigmu; double y[8], d[8], da[8];
+  double rmax;   // 1 / (largest step that keeps s and lambda non-negative), starts at 0
   __device__ __forceinline__ void row(int slot, double gz, double gdz, double gda, double rhs) {
     const double2 v = rows[slot * N + i];
     const double s = v.x, lam = v.y;
-    const double inv = 1.0 / s;
+    const double inv = fast_rcp(s);
     const double rp = gz + s - rhs;
     const double dsa = -rp - gda;
     const double dla = -lam - (lam * inv) * dsa;
     const double ds = -rp - gdz;
     const double rc = s * lam + dsa * dla - sigmu;
     const double dl = -(rc + lam * ds) * inv;
-    if (ds < 0.0) amin = fmin(amin, -s / ds);
-    if (dl < 0.0) amin = fmin(amin, -lam / dl);
+    rmax = fmax(rmax, fmax(-ds * inv, -dl * fast_rcp(lam)));
   }
   template <int T> __device__ __forceinline__ void bound(int slot, double sgn, double rhs) { row(slot, sgn * y[T], sgn * d[T], sgn * da[T], rhs); }
   __device__ __forceinline__ void general(int slot, const double a[6], double rhs) { row(slot, dot6(a, y), dot6(a, d), dot6(a, da), rhs); }
@@ -405,7 +419,7 @@ __device__ __forceinline__ void riccati_factor(const WarpCtx &w, const PhiEntry 
     __syncwarp();
     // phase 2: Finv, P_i, p_i, k_i
     const double f00 = T[T_PUU], f10 = T[T_PUU + 1], f11 = T[T_PUU + 2];
-    const double idet = 1.0 / (f00 * f11 - f10 * f10);
+    const double idet = fast_rcp(f00 * f11 - f10 * f10);
     const double i00 = f11 * idet, i10 = -f10 * idet, i11 = f00 * idet;
     const double pu0 = T[T_PHIU], pu1 = T[T_PHIU + 1];
     const double k0 = -(i00 * pu0 + i10 * pu1), k1 = -(i10 * pu0 + i11 * pu1);
@@ -467,10 +481,13 @@ __device__ __forceinline__ void riccati_forward(const WarpCtx &w, int dst) {
       du0 = Vi[V_K] - (i00 * t0 + i10 * t1);
       du1 = Vi[V_K + 1] - (i10 * t0 + i11 * t1);
     }
-#pragma unroll
-    for (int t = 0; t < 6; ++t) if (w.lane == t) Vi[dst + t] = dx[t];
-    if (w.lane == 6) Vi[dst + 6] = du0;
-    if (w.lane == 7) Vi[dst + 7] = du1;
+    {  // lane t < 8 stores component t (one predicated store instead of eight branches)
+      double val = dx[0];
+      val = (w.lane == 1) ? dx[1] : val; val = (w.lane == 2) ? dx[2] : val; val = (w.lane == 3) ? dx[3] : val;
+      val = (w.lane == 4) ? dx[4] : val; val = (w.lane == 5) ? dx[5] : val;
+      val = (w.lane == 6) ? du0 : val;   val = (w.lane == 7) ? du1 : val;
+      if (w.lane < 8) Vi[dst + w.lane] = val;
+    }
 #pragma unroll
     for (int ax = 0; ax < 2; ++ax) {
       const double P = dx[3 * ax], Vv = dx[3 * ax + 1], A = dx[3 * ax + 2], U = ax ? du1 : du0;
@@ -580,16 +597,17 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
     // ---- predictor ----
     riccati_factor(w, e1, e2);
     riccati_forward(w, V_DZA);
-    double amin = 1.0, s1 = 0.0, s2 = 0.0;
+    double rmax = 1.0, s1 = 0.0, s2 = 0.0;
     for (int i = lane; i < N; i += 32) {
       const double *Vi = w.V + i * V_STRIDE;
-      PassD v; v.rows = w.rows; v.N = N; v.i = i; v.amin = 1.0; v.s1 = 0.0; v.s2 = 0.0;
+      PassD v; v.rows = w.rows; v.N = N; v.i = i; v.rmax = 1.0; v.s1 = 0.0; v.s2 = 0.0;
 #pragma unroll
       for (int t = 0; t < 8; ++t) { v.y[t] = Vi[V_Z + t]; v.da[t] = Vi[V_DZA + t]; }
       visit_rows(w, i, v);
-      amin = fmin(amin, v.amin); s1 += v.s1; s2 += v.s2;
+      rmax = fmax(rmax, v.rmax); s1 += v.s1; s2 += v.s2;
     }
-    amin = warp_min(amin); s1 = warp_sum(s1); s2 = warp_sum(s2);
+    rmax = warp_max(rmax); s1 = warp_sum(s1); s2 = warp_sum(s2);
+    double amin = 1.0 / rmax;
     double sigma = 0.0;
     if (m > 0 && mu > 0.0) {
       const double mu_aff = (musum + amin * s1 + amin * amin * s2) / m;
@@ -613,19 +631,20 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
     __syncwarp();
     riccati_vector(w);
     riccati_forward(w, V_DZ);
-    amin = 1e300;
+    rmax = 0.0;
+    bool bad_step = false;
     for (int i = lane; i < N; i += 32) {
       const double *Vi = w.V + i * V_STRIDE;
-      PassG v; v.rows = w.rows; v.N = N; v.i = i; v.sigmu = sigmu; v.amin = 1e300;
+      PassG v; v.rows = w.rows; v.N = N; v.i = i; v.sigmu = sigmu; v.rmax = 0.0;
 #pragma unroll
       for (int t = 0; t < 8; ++t) { v.y[t] = Vi[V_Z + t]; v.d[t] = Vi[V_DZ + t]; v.da[t] = Vi[V_DZA + t]; }
+      bad_step |= !(fabs(v.d[Y_UX]) + fabs(v.d[Y_UY]) + fabs(v.d[Y_PX]) + fabs(v.d[Y_PY]) < 1e300);  // NaN / inf step
       visit_rows(w, i, v);
-      amin = fmin(amin, v.amin);
+      rmax = fmax(rmax, v.rmax);
     }
-    amin = warp_min(amin);
-    double alpha = 0.995 * amin;
-    if (alpha > 1.0) alpha = 1.0;
-    if (!(alpha >= 0.0)) { status = 2; break; }  // NaN: singular stage system
+    rmax = warp_max(rmax);
+    if (__any_sync(FULL, bad_step)) { status = 2; break; }  // singular stage system
+    double alpha = (rmax > 0.995) ? 0.995 / rmax : 1.0;
     sc.alpha = alpha; sc.sigmu = sigmu; sc.pending = true;
     rdn *= (1.0 - alpha);
     for (int i = lane; i < N; i += 32) {   // z += alpha dz (rows are updated lazily by the next pass A)
