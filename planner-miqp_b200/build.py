@@ -14,7 +14,7 @@ LIB = os.path.join(HERE, "libmiqp_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=off", "-Xptxas", "-v"]
 # formulation.cu is compared bit for bit with the oracle: no FMA contraction there
-UNITS = [("formulation.cu", ["--fmad=false"]), ("bnb.cu", []), ("solver.cu", []), ("peaks.cu", [])]
+UNITS = [("formulation.cu", ["--fmad=false"]), ("bnb.cu", []), ("bnb_multi.cu", []), ("solver.cu", []), ("peaks.cu", [])]
 
 
 def _newest_src() -> float:

@@ -21,32 +21,9 @@
 // The host only launches rounds and polls one integer (number of unfinished plans).
 #include "kernels.cuh"
 #include "node_qp.cuh"
+#include "bnb_common.cuh"
 
 namespace miqp {
-
-// ---------------------------------------------------------------------------------------
-// small device helpers
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void atomic_min_double(double *addr, double v) {
-  unsigned long long *a = reinterpret_cast<unsigned long long *>(addr);
-  unsigned long long old = *a;
-  while (__longlong_as_double((long long)old) > v) {
-    unsigned long long assumed = old;
-    old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
-    if (old == assumed) break;
-  }
-}
-
-__device__ __forceinline__ unsigned long long ordered_bits(double v) {
-  long long b = __double_as_longlong(v);
-  unsigned long long u = (unsigned long long)b;
-  return (b < 0) ? ~u : (u | 0x8000000000000000ULL);
-}
-
-__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
-  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
-  return x;
-}
 
 // priority key, smaller = earlier.  Without incumbent: depth first (deepest, then the least
 // violated alternative, then bound); with incumbent: best bound first, then deepest.
@@ -90,7 +67,7 @@ __global__ void bnb_init_kernel(BnbState st, const DevProb *probs, const unsigne
     st.done[s] = 0; st.lock[s] = 0;
     st.stat_nodes[s] = 0; st.stat_iters[s] = 0; st.stat_rows[s] = 0;
     st.inc_uid[s] = ~0ULL;
-    if (s == 0) { *st.work_cnt = 0; *st.work_next = 0; *st.active = 0; *st.err = 0; }
+    if (s == 0) { *st.work_cnt = 0; *st.work_next = 0; *st.active = 0; *st.err = 0; *st.work_cnt2 = 0; *st.work_next2 = 0; }
   }
 }
 
@@ -221,16 +198,17 @@ __global__ void __launch_bounds__(SEL_THREADS) bnb_select_kernel(BnbState st, co
     st.free_cnt[s] = s_free;
     st.cutoff[s] = cutoff;
     if (nsel_total == 0) st.done[s] = 1;  // frontier exhausted (everything pruned or solved)
-    else { atomicAdd(st.active, 1); s_wbase = atomicAdd(st.work_cnt, nsel_total); }
+    else { atomicAdd(st.active, 1); s_wbase = atomicAdd((p.C > 1 || st.force_multi) ? st.work_cnt2 : st.work_cnt, nsel_total); }
   }
   __syncthreads();
   if (nsel_total > 0) {
     const int wb = s_wbase;
-    for (int k = tid; k < nsel_total; k += SEL_THREADS) st.work[wb + k] = make_int2(s, st.sel_idx[(long)s * K + k]);
+    int2 *wl = (p.C > 1 || st.force_multi) ? st.work2 : st.work;   // plans with several cars go to the CTA-per-node kernel
+    for (int k = tid; k < nsel_total; k += SEL_THREADS) wl[wb + k] = make_int2(s, st.sel_idx[(long)s * K + k]);
   }
 }
 
-__global__ void bnb_round_reset_kernel(BnbState st) { *st.work_cnt = 0; *st.work_next = 0; *st.active = 0; }
+__global__ void bnb_round_reset_kernel(BnbState st) { *st.work_cnt = 0; *st.work_next = 0; *st.active = 0; *st.work_cnt2 = 0; *st.work_next2 = 0; }
 
 void launch_bnb_select(const BnbState &st, const DevProb *probs, cudaStream_t s) {
   bnb_round_reset_kernel<<<1, 1, 0, s>>>(st);
@@ -706,6 +684,23 @@ __global__ void bnb_finish_kernel(BnbState st, const DevProb *probs, const doubl
         }
         if (d == OBS_SOFT) { if (pt == 0) x[col_so(p, c, o, i)] = 1.0; else x[col_sof(p, c, o, i, 4 - pt)] = 1.0; }
       }
+    }
+  }
+  // collision sides and slacks of every pair (agent_collision_constraints.mod:38-73): the binary of
+  // the chosen side is 0, the other three are 1; indices (k1, k2) = (a, b-1), upper triangle
+  for (int q = tid; q < p.P * N; q += nt) {
+    const int pr = q / N, i = q % N;
+    int a = 0, rem = pr;
+    while (rem >= C - 1 - a) { rem -= C - 1 - a; ++a; }
+    const int b = a + 1 + rem;
+    for (int qd = 0; qd < 4; ++qd) {
+      unsigned char d = dec[p.off_pair + (pr * N + i) * 4 + qd];
+      if (d > 3) d = 0;
+      for (int side = 0; side < 4; ++side) x[col_c2c(p, a, b - 1, i, qd * 4 + side)] = (side == d) ? 0.0 : 1.0;
+    }
+    for (int sq = 0; sq < 4; ++sq) {
+      const double v = z[(long)C * N * 8 + (pr * N + i) * 4 + sq];
+      x[col_sv(p, a, b - 1, i, sq)] = v > 0.0 ? v : 0.0;
     }
   }
 }

@@ -24,6 +24,7 @@ struct BnbState {
   int nwarps;           // resident warps of the node kernel
   int sel_per_plan;     // K: node relaxations taken per plan per round
   int work_cap;
+  int force_multi;      // route every plan to the CTA-per-node kernel (test hook)
   // node pools [count][cap]
   unsigned char *dec;
   double *bound;
@@ -45,6 +46,7 @@ struct BnbState {
   unsigned long long *stat_nodes, *stat_iters, *stat_rows;
   // round control
   int2 *work; int *work_cnt; int *work_next; int *active; int *err;
+  int2 *work2; int *work_cnt2; int *work_next2;   // plans with NumCars > 1 (bnb_multi.cu)
 };
 
 void launch_bnb_init(const BnbState &st, const DevProb *probs, const unsigned char *warm_dec /* [count][ndec_stride] or null */,
@@ -57,5 +59,13 @@ void launch_bnb_finish(const BnbState &st, const DevProb *probs, const double *d
                        double *xall, double *best_bound, cudaStream_t s);
 int node_kernel_smem_per_warp(int maxN, int kmax, int ndec_stride);
 int node_kernel_max_ctas(int smem_per_cta, int threads);
+
+// ---- bnb_multi.cu ---------------------------------------------------------------------
+// CTA-per-node kernel for plans with several cars.  ws_bytes = workspace of one node (max over the
+// plans of the batch); it lives in shared memory when it fits, else in gws[ctas][ws_bytes].
+long multi_workspace_bytes(int C, int N, int P, int kmax, int ndec_stride);
+int multi_kernel_max_ctas(int smem_bytes, int threads);
+int launch_bnb_nodes_multi(const BnbState &st, const DevProb *probs, const double *dblob, const int *iblob,
+                           double *gws, long ws_bytes, int use_smem, int threads, int ctas, cudaStream_t s);
 
 }  // namespace miqp

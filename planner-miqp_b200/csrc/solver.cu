@@ -12,6 +12,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -20,8 +21,10 @@
 
 #include "../../include/miqp_b200.h"
 #include "kernels.cuh"
+#include "host_pack.hpp"
 
 using namespace miqp;
+using namespace miqp::hostpack;
 namespace miqp { double measure_fp64_tflops(int num_sms, cudaStream_t st, int reps); }
 
 namespace {
@@ -49,241 +52,6 @@ struct DevBuf {
   }
   void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
-
-struct Packed {
-  std::vector<DevProb> probs;
-  std::vector<double> dblob;
-  std::vector<int> iblob;
-  long total_rows = 0, total_nnz = 0, total_cols = 0, max_rows = 0;
-  int maxN = 0, max_ndec = 0, max_kmax = 0, max_z = 0, maxC = 0;
-};
-
-long push_d(std::vector<double> &b, const double *src, size_t n) {
-  long off = (long)b.size();
-  if (src) b.insert(b.end(), src, src + n); else b.resize(b.size() + n, 0.0);
-  return off;
-}
-long push_i(std::vector<int> &b, const int *src, size_t n) {
-  long off = (long)b.size();
-  if (src) b.insert(b.end(), src, src + n); else b.resize(b.size() + n, 0);
-  return off;
-}
-
-void layout_of(const MiqpB200Problem &q, MiqpB200Layout &l) {
-  l.C = q.C; l.N = q.N; l.R = q.R; l.O = q.O; l.L = q.L; l.E = q.E; l.K = q.C - 1;
-  const int C = q.C, N = q.N, R = q.R, O = q.O, L = q.L, E = q.E, K = l.K;
-  int b = 12 * C * N;
-  l.base_nwe = b;  b += 5 * C * E * N;
-  l.base_ar = b;   b += C * N * R;
-  l.base_rcna = b; b += 5 * C * N;
-  l.base_dcc = b;  b += C * O * N * L;
-  l.base_dcf = b;  b += 4 * C * O * N * L;
-  l.base_so = b;   b += C * O * N;
-  l.base_sof = b;  b += 4 * C * O * N;
-  l.base_c2c = b;  b += 16 * K * K * N;
-  l.base_sv = b;   b += 4 * K * K * N;
-  l.ncols = b;
-}
-
-// closed-form sizes of the big-M model (same arithmetic as prepare_tables_kernel)
-void model_sizes(const MiqpB200Problem &q, long &rows, long &nnz) {
-  const long C = q.C, N = q.N, R = q.R, O = q.O, E = q.E;
-  long nE = q.E > 0 ? q.env_off[q.E] : 0;
-  long rr = 0, nn = 0;
-  for (int c = 0; c < C; ++c) {
-    long rp = 0;
-    for (int j = 0; j < R; ++j) rp += (q.possible_region[c * R + j] == 1);
-    rr += 20 * rp + (R - rp) + 1;
-    nn += 76 * rp + (R - rp) + R;
-  }
-  rows = 12 * C + 5 * R * C + 5 * C + 6 * C * (N - 1) + 12 * C * N + rr * (N - 1) + 15 * R * C * (N - 1);
-  nnz = 12 * C + 9 * R * C + 5 * C + 24 * C * (N - 1) + 12 * C * N + nn * (N - 1) + 35 * R * C * (N - 1);
-  if (E > 0) { rows += C * N * (5 * nE + 5); nnz += C * N * (15 * nE + 5 * E); }
-  if (O > 0)
-    for (int i = 0; i < N; ++i)
-      for (int o = 0; o < O; ++o) {
-        long ne = q.obs_nedges[o * N + i], soft = (q.obs_soft[o] == 1);
-        rows += C * (5 * ne + 5); nnz += C * (15 * ne + 5 * (ne + soft));
-      }
-  if (C > 1) {
-    long K = C - 1, Z = K * (K - 1) / 2, P = C * (C - 1) / 2;
-    rows += 20 * Z * N + 24 * P * N; nnz += 20 * Z * N + 76 * P * N;
-  }
-}
-
-std::string validate(const MiqpB200Problem &q) {
-  if (q.N < 2 || q.N > 64) return "NumSteps must be in [2,64]";
-  if (q.R < 1 || q.R > 64) return "nr_regions must be in [1,64]";
-  if (q.C < 1 || q.C > 8) return "NumCars must be in [1,8]";
-  if (q.O < 0 || q.E < 0 || q.L < 0) return "negative dimension";
-  if (q.O > 0 && q.L > 16) return "max_lines_obstacles must be <= 16";
-  if (q.E > 250 || q.L > 250) return "too many polygons";
-  if (!q.x0 || !q.frac || !q.possible_region || !q.initial_region) return "null array";
-  for (int c = 0; c < q.C; ++c)
-    if (q.initial_region[c] < 1 || q.initial_region[c] > q.R) return "initial_region out of range";
-  if (q.O > 0)
-    for (int k = 0; k < q.O * q.N; ++k)
-      if (q.obs_nedges[k] < 0 || q.obs_nedges[k] > q.L) return "obstacle polygon with more edges than max_lines_obstacles";
-  return "";
-}
-
-// mode alternatives of a car: every possible region with its non-dominated low-speed half planes
-void mode_alternatives(const MiqpB200Problem &q, int c, std::vector<int> &out) {
-  out.clear();
-  for (int j = 0; j < q.R; ++j) {
-    if (q.possible_region[c * q.R + j] != 1) continue;
-    const double *f = q.frac + 4 * j;
-    const double d1x = f[0], d1y = f[1], d2x = f[2], d2y = f[3];
-    int useful[4];
-    useful[0] = (d1x > 1e-9 || d2x > 1e-9); useful[1] = (d1y > 1e-9 || d2y > 1e-9);
-    useful[2] = (d1x < -1e-9 || d2x < -1e-9); useful[3] = (d1y < -1e-9 || d2y < -1e-9);
-    const bool x_dom = (std::fabs(d1x) >= std::fabs(d1y) - 1e-9) && (std::fabs(d2x) >= std::fabs(d2y) - 1e-9);
-    const bool y_dom = (std::fabs(d1y) >= std::fabs(d1x) - 1e-9) && (std::fabs(d2y) >= std::fabs(d2x) - 1e-9);
-    if (x_dom && (useful[0] || useful[2])) { useful[1] = 0; useful[3] = 0; }
-    else if (y_dom && (useful[1] || useful[3])) { useful[0] = 0; useful[2] = 0; }
-    for (int h = 0; h < 4; ++h) if (useful[h]) out.push_back(j * 4 + h);
-  }
-}
-
-void pack_one(const MiqpB200Problem &q, Packed &pk) {
-  DevProb p;
-  std::memset(&p, 0, sizeof p);
-  const int N = q.N, R = q.R, C = q.C, O = q.O, L = q.L, E = q.E;
-  p.N = N; p.R = R; p.C = C; p.O = O; p.L = L; p.E = E; p.K = C - 1; p.P = C * (C - 1) / 2;
-  p.nEnvEdges = (E > 0) ? q.env_off[E] : 0;
-  p.maxEnvEdges = 0;
-  for (int e = 0; e < E; ++e) p.maxEnvEdges = std::max(p.maxEnvEdges, q.env_off[e + 1] - q.env_off[e]);
-  p.ts = q.ts;
-  p.c2 = 0.5 * (q.ts * q.ts);
-  p.c3 = (1.0 / 6.0) * ((q.ts * q.ts) * q.ts);
-  p.min_vel = q.min_vel; p.max_vel = q.max_vel;
-  p.total_min_acc = q.total_min_acc; p.total_max_acc = q.total_max_acc;
-  p.total_min_jerk = q.total_min_jerk; p.total_max_jerk = q.total_max_jerk;
-  p.maximum_slack = q.maximum_slack; p.w_slack = q.w_slack; p.w_slack_obs = q.w_slack_obs;
-  p.vm = q.min_region_change_speed; p.gap_tol = q.gap_tol;
-  auto &d = pk.dblob; auto &ib = pk.iblob;
-  p.o_safety = push_d(d, q.safety, N);
-  p.o_safety_slack = push_d(d, q.safety_slack, N);
-  const double *w[8] = {q.w_pos_x, q.w_vel_x, q.w_acc_x, q.w_pos_y, q.w_vel_y, q.w_acc_y, q.w_jerk_x, q.w_jerk_y};
-  for (int k = 0; k < 8; ++k) p.o_w[k] = push_d(d, w[k], C);
-  p.o_wb = push_d(d, q.wheelbase, C);
-  p.o_radius = push_d(d, q.radius, C);
-  p.o_x0 = push_d(d, q.x0, 6 * C);
-  p.o_front0 = push_d(d, nullptr, 2 * C);
-  for (int c = 0; c < C; ++c) {  // initialization.mod:25-29, initial_conditions.mod:20-23
-    const double *x0 = q.x0 + 6 * c;
-    const double th = std::atan2(x0[4], x0[1]);
-    const double ct = std::cos(th), st = std::sin(th), wb = q.wheelbase[c];
-    d[p.o_front0 + 2 * c] = x0[0] + ct * wb;
-    d[p.o_front0 + 2 * c + 1] = x0[3] + st * wb;
-  }
-  const double *ref[4] = {q.x_ref, q.vx_ref, q.y_ref, q.vy_ref};
-  for (int k = 0; k < 4; ++k) p.o_ref[k] = push_d(d, ref[k], (size_t)C * N);
-  const double *lim[8] = {q.min_acc_x, q.max_acc_x, q.min_acc_y, q.max_acc_y, q.min_jerk_x, q.max_jerk_x, q.min_jerk_y, q.max_jerk_y};
-  for (int k = 0; k < 8; ++k) p.o_lim[k] = push_d(d, lim[k], (size_t)C * R);
-  p.o_obs_edges = push_d(d, O > 0 ? q.obs_edges : nullptr, (size_t)O * N * L * 4);
-  p.o_env_edges = push_d(d, p.nEnvEdges > 0 ? q.env_edges : nullptr, (size_t)p.nEnvEdges * 4);
-  p.o_frac = push_d(d, q.frac, (size_t)R * 4);
-  const double *poly[6] = {q.poly_sint_ub, q.poly_sint_lb, q.poly_coss_ub, q.poly_coss_lb, q.poly_kappa_max, q.poly_kappa_min};
-  for (int k = 0; k < 6; ++k) p.o_poly[k] = push_d(d, poly[k], (size_t)R * 3);
-  p.o_envtab = push_d(d, nullptr, (size_t)p.nEnvEdges * 3);
-  p.o_obstab = push_d(d, nullptr, (size_t)O * N * L * 3);
-  p.o_modetab = push_d(d, nullptr, (size_t)R * 20);
-  p.o_fronttab = push_d(d, nullptr, (size_t)C * R * 12);
-  p.o_cost = push_d(d, nullptr, (size_t)C * N * 16);
-
-  p.o_initreg = push_i(ib, q.initial_region, C);
-  p.o_possible = push_i(ib, q.possible_region, (size_t)C * R);
-  p.o_obs_nedges = push_i(ib, O > 0 ? q.obs_nedges : nullptr, (size_t)O * N);
-  p.o_obs_soft = push_i(ib, O > 0 ? q.obs_soft : nullptr, O);
-  p.o_env_off = push_i(ib, q.env_off, E + 1);
-  p.o_alt = push_i(ib, nullptr, (size_t)C * 4 * R);
-  p.o_nalt = push_i(ib, nullptr, C);
-  std::vector<int> alts;
-  for (int c = 0; c < C; ++c) {
-    mode_alternatives(q, c, alts);
-    ib[p.o_nalt + c] = (int)alts.size();
-    for (size_t a = 0; a < alts.size(); ++a) ib[p.o_alt + c * 4 * R + a] = alts[a];
-  }
-  p.o_posspre = push_i(ib, nullptr, (size_t)C * (R + 1));
-  p.o_obsrowpre = push_i(ib, nullptr, (size_t)N * (O + 1));
-  p.o_obsnnzpre = push_i(ib, nullptr, (size_t)N * (O + 1));
-  p.o_obsstep_rows = push_i(ib, nullptr, N + 1);
-  p.o_obsstep_nnz = push_i(ib, nullptr, N + 1);
-
-  MiqpB200Layout l; layout_of(q, l);
-  p.base_nwe = l.base_nwe; p.base_ar = l.base_ar; p.base_rcna = l.base_rcna; p.base_dcc = l.base_dcc;
-  p.base_dcf = l.base_dcf; p.base_so = l.base_so; p.base_sof = l.base_sof; p.base_c2c = l.base_c2c;
-  p.base_sv = l.base_sv; p.ncols = l.ncols;
-
-  long rows, nnz; model_sizes(q, rows, nnz);
-  p.row_base = pk.total_rows; p.nnz_base = pk.total_nnz; p.x_base = pk.total_cols;
-  pk.total_rows += rows; pk.total_nnz += nnz; pk.total_cols += l.ncols;
-  pk.max_rows = std::max(pk.max_rows, rows);
-
-  p.off_mode = 0; p.off_env = p.off_mode + C * N; p.off_obs = p.off_env + 5 * C * N;
-  p.off_pair = p.off_obs + 5 * C * O * N; p.ndec = p.off_pair + 4 * p.P * N;
-  p.ndec_pad = (p.ndec + 15) & ~15;
-  p.kmax = 12 + 5 + (E > 0 ? 5 * p.maxEnvEdges : 0) + 5 * O;
-  pk.maxN = std::max(pk.maxN, N); pk.max_ndec = std::max(pk.max_ndec, p.ndec_pad);
-  pk.max_kmax = std::max(pk.max_kmax, p.kmax); pk.maxC = std::max(pk.maxC, C);
-  pk.max_z = std::max(pk.max_z, C * N * 8 + 4 * p.P * N);
-  pk.probs.push_back(p);
-}
-
-// decisions of a full column vector (MIP start / warm start)
-void decisions_from_solution(const MiqpB200Problem &q, const DevProb &p, const std::vector<int> &alts_all,
-                             const double *x, unsigned char *dec) {
-  const int C = p.C, N = p.N, R = p.R, E = p.E, O = p.O, L = p.L, K = p.K;
-  std::memset(dec, UNDEC, (size_t)p.ndec_pad);
-  std::vector<int> alts;
-  for (int c = 0; c < C; ++c) {
-    mode_alternatives(q, c, alts);
-    for (int i = 0; i < N; ++i) {
-      int j = 0;
-      for (int jj = 0; jj < R; ++jj) if (x[col_ar(p, c, i, jj)] > 0.5) j = jj;
-      if (i > 0) {
-        const double rho = x[col_rcna(p, 4, c, i)];
-        if (rho > 0.5) dec[p.off_mode + c * N + i] = MODE_FROZEN;
-        else {
-          int h = -1;
-          for (int t = 0; t < 4; ++t) if (x[col_rcna(p, t, c, i)] < 0.5) { h = t; break; }
-          if (h < 0) h = 0;
-          bool found = false; int firsth = -1;
-          for (int alt : alts) if ((alt >> 2) == j) { if (firsth < 0) firsth = alt & 3; if ((alt & 3) == h) found = true; }
-          if (!found && firsth >= 0) h = firsth;
-          dec[p.off_mode + c * N + i] = (unsigned char)(j * 4 + h);
-        }
-      }
-      for (int pt = 0; pt < 5; ++pt) {
-        if (E > 1) {
-          int e = 0;
-          for (int ee = 0; ee < E; ++ee) if (x[col_nwe(p, pt, c, ee, i)] < 0.5) { e = ee; break; }
-          dec[p.off_env + (c * N + i) * 5 + pt] = (unsigned char)e;
-        }
-        for (int o = 0; o < O; ++o) {
-          const int ne = q.obs_nedges[o * N + i];
-          int dd = OBS_SOFT;
-          for (int ed = 0; ed < ne; ++ed) {
-            const double v = (pt == 0) ? x[col_dcc(p, c, o, i, ed)] : x[col_dcf(p, c, o, i, ed, 4 - pt)];
-            if (v < 0.5) { dd = ed; break; }
-          }
-          dec[p.off_obs + ((c * O + o) * N + i) * 5 + pt] = (unsigned char)dd;
-        }
-      }
-    }
-  }
-  int pr = 0;
-  for (int a = 0; a < C - 1; ++a)
-    for (int b = a + 1; b < C; ++b, ++pr)
-      for (int i = 0; i < N; ++i)
-        for (int qd = 0; qd < 4; ++qd) {
-          int dd = 0;
-          for (int side = 0; side < 4; ++side) if (x[col_c2c(p, a, b - 1, i, qd * 4 + side)] < 0.5) { dd = side; break; }
-          dec[p.off_pair + (pr * N + i) * 4 + qd] = (unsigned char)dd;
-        }
-  (void)alts_all; (void)L; (void)K;
-}
 
 }  // namespace
 
@@ -313,6 +81,11 @@ struct MiqpB200Solver {
   DevBuf<unsigned long long> b_uid, b_keybuf, b_incuid, b_stats;
   DevBuf<int> b_open, b_opencnt, b_free, b_freecnt, b_sel, b_selcnt, b_done, b_lock, b_ctrl;
   int smem_per_warp = 0, warps_per_cta = 4, ctas = 0;
+  // CTA-per-node kernel for plans with several cars
+  int n_single = 0, n_multi = 0, multi_threads = 64, multi_ctas = 0, multi_use_smem = 1;
+  long multi_ws_bytes = 0;
+  DevBuf<double> b_multi_ws;
+  DevBuf<int2> b_work2;
   bool uploaded = false, ran = false;
   double last_seconds = 0.0;
   bool timed_out = false;
@@ -320,6 +93,7 @@ struct MiqpB200Solver {
   std::vector<double> h_x, h_viol, h_obj, h_bb, h_ub;
   std::vector<unsigned long long> h_stats;
   std::vector<int> h_done;
+  int single_maxN = 2;
 };
 
 namespace {
@@ -363,18 +137,41 @@ void setup_bnb(MiqpB200Solver *s) {
   st.zstride = pk.max_z;
   st.kmax = pk.max_kmax;
   st.npad = ((pk.maxN + 31) / 32) * 32;
-  // node kernel geometry
-  s->smem_per_warp = node_kernel_smem_per_warp(pk.maxN, st.kmax, st.ndec_stride);
-  s->warps_per_cta = 1;
-  int per_sm = 0;
-  while (s->warps_per_cta >= 1) {
-    per_sm = node_kernel_max_ctas(s->smem_per_warp * s->warps_per_cta, s->warps_per_cta * 32);
-    if (per_sm > 0) break;
-    s->warps_per_cta /= 2;
+  // node kernel geometry: warp-per-node kernel for single-car plans, CTA-per-node kernel otherwise
+  int maxN1 = 0, kmax1 = 0, maxCm = 0;
+  s->n_single = 0; s->n_multi = 0; s->multi_ws_bytes = 0;
+  const char *fm = std::getenv("MIQP_B200_FORCE_MULTI");   // test hook: run single-car plans through the CTA-per-node kernel
+  st.force_multi = (fm && fm[0] == '1') ? 1 : 0;
+  for (const DevProb &p : pk.probs) {
+    if (p.C == 1 && !st.force_multi) { ++s->n_single; maxN1 = std::max(maxN1, p.N); kmax1 = std::max(kmax1, p.kmax); }
+    else {
+      ++s->n_multi; maxCm = std::max(maxCm, p.C);
+      s->multi_ws_bytes = std::max(s->multi_ws_bytes, multi_workspace_bytes(p.C, p.N, p.P, p.kmax, st.ndec_stride));
+    }
   }
-  if (per_sm <= 0) throw std::runtime_error("node kernel does not fit in shared memory for this horizon");
-  s->ctas = per_sm * s->num_sms;
-  st.nwarps = s->ctas * s->warps_per_cta;
+  st.kmax = std::max(kmax1, 1);
+  s->single_maxN = std::max(maxN1, 2);
+  st.nwarps = 0; s->ctas = 0; s->multi_ctas = 0;
+  if (s->n_single > 0) {
+    s->smem_per_warp = node_kernel_smem_per_warp(s->single_maxN, st.kmax, st.ndec_stride);
+    s->warps_per_cta = 1;
+    const int per_sm = node_kernel_max_ctas(s->smem_per_warp * s->warps_per_cta, s->warps_per_cta * 32);
+    if (per_sm <= 0) throw std::runtime_error("node kernel does not fit in shared memory for this horizon");
+    s->ctas = per_sm * s->num_sms;
+    st.nwarps += s->ctas * s->warps_per_cta;
+  }
+  if (s->n_multi > 0) {
+    s->multi_threads = (maxCm <= 2) ? 64 : 128;
+    int per_sm = (s->multi_ws_bytes <= 220 * 1024) ? multi_kernel_max_ctas((int)s->multi_ws_bytes, s->multi_threads) : 0;
+    if (per_sm > 0) { s->multi_use_smem = 1; }
+    else {  // working set of a node does not fit in shared memory: per-CTA slice of HBM (L2 resident)
+      s->multi_use_smem = 0;
+      per_sm = std::min(4, std::max(1, multi_kernel_max_ctas(0, s->multi_threads)));
+    }
+    s->multi_ctas = per_sm * s->num_sms;
+    if (!s->multi_use_smem) s->b_multi_ws.ensure((size_t)s->multi_ctas * (size_t)s->multi_ws_bytes / 8 + 16);
+    st.nwarps += s->multi_ctas;
+  }
   // nodes per plan per round: fill the resident warps about twice
   int K = s->opt.nodes_per_round;
   if (K <= 0) { K = (2 * st.nwarps + count - 1) / count; if (K < 1) K = 1; if (K > 1024) K = 1024; }
@@ -415,8 +212,10 @@ void setup_bnb(MiqpB200Solver *s) {
   s->b_stats.ensure((size_t)3 * count);
   st.stat_nodes = s->b_stats.p; st.stat_iters = s->b_stats.p + count; st.stat_rows = s->b_stats.p + 2 * count;
   s->b_work.ensure(st.work_cap); st.work = s->b_work.p;
-  s->b_ctrl.ensure(4);
+  s->b_work2.ensure(st.work_cap); st.work2 = s->b_work2.p;
+  s->b_ctrl.ensure(8);
   st.work_cnt = s->b_ctrl.p; st.work_next = s->b_ctrl.p + 1; st.active = s->b_ctrl.p + 2; st.err = s->b_ctrl.p + 3;
+  st.work_cnt2 = s->b_ctrl.p + 4; st.work_next2 = s->b_ctrl.p + 5;
   s->d_x.ensure(std::max<long>(pk.total_cols, 1));
   s->d_viol.ensure(count); s->d_obj.ensure(count); s->d_bb.ensure(count);
 }
@@ -472,7 +271,7 @@ void miqp_b200_destroy(MiqpB200Solver *s) {
   s->b_pruned.release(); s->b_incz.release(); s->b_meta.release(); s->b_work.release();
   s->b_uid.release(); s->b_keybuf.release(); s->b_incuid.release(); s->b_stats.release(); s->b_open.release();
   s->b_opencnt.release(); s->b_free.release(); s->b_freecnt.release(); s->b_sel.release(); s->b_selcnt.release();
-  s->b_done.release(); s->b_lock.release(); s->b_ctrl.release();
+  s->b_done.release(); s->b_lock.release(); s->b_ctrl.release(); s->b_multi_ws.release(); s->b_work2.release();
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   if (s->evr0) cudaEventDestroy(s->evr0);
@@ -573,8 +372,6 @@ int miqp_b200_batch_upload(MiqpB200Solver *s, const MiqpB200Problem *problems, i
     CK(cudaSetDevice(s->opt.device));
     s->uploaded = false; s->ran = false;
     pack_batch(s, problems, count);
-    for (int k = 0; k < count; ++k)
-      if (problems[k].C != 1) return fail(s, MIQP_B200_ERR_UNSUPPORTED, "node kernel is built for NumCars == 1 in this release");
     upload_packed(s);
     setup_bnb(s);
     // MIP starts
@@ -619,16 +416,25 @@ int miqp_b200_batch_run(MiqpB200Solver *s, float *device_ms) {
     launch_bnb_init(s->st, s->d_probs.p, s->any_warm ? s->d_warm.p : nullptr, s->any_warm ? s->d_haswarm.p : nullptr, s->stream);
     ++launches;
     s->timed_out = false;
-    int ctrl[4] = {0, 0, 0, 0};
+    int ctrl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (;;) {
       launch_bnb_select(s->st, s->d_probs.p, s->stream);
       launches += 2;
       CK(cudaEventRecord(s->evr0, s->stream));
-      int rc = launch_bnb_nodes(s->st, s->d_probs.p, s->d_dblob.p, s->d_iblob.p, s->smem_per_warp, s->warps_per_cta,
-                                s->ctas, s->pk.maxN, s->stream);
-      if (rc != 0) throw std::runtime_error(std::string("node kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
+      if (s->n_single > 0) {
+        int rc = launch_bnb_nodes(s->st, s->d_probs.p, s->d_dblob.p, s->d_iblob.p, s->smem_per_warp, s->warps_per_cta,
+                                  s->ctas, s->single_maxN, s->stream);
+        if (rc != 0) throw std::runtime_error(std::string("node kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
+        ++launches; ++node_launches;
+      }
+      if (s->n_multi > 0) {
+        int rc = launch_bnb_nodes_multi(s->st, s->d_probs.p, s->d_dblob.p, s->d_iblob.p, s->b_multi_ws.p, s->multi_ws_bytes,
+                                        s->multi_use_smem, s->multi_threads, s->multi_ctas, s->stream);
+        if (rc != 0) throw std::runtime_error(std::string("multi-car node kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
+        ++launches; ++node_launches;
+      }
       CK(cudaEventRecord(s->evr1, s->stream));
-      ++launches; ++node_launches; ++rounds;
+      ++rounds;
       CK(cudaMemcpyAsync(ctrl, s->b_ctrl.p, sizeof ctrl, cudaMemcpyDeviceToHost, s->stream));
       CK(cudaStreamSynchronize(s->stream));
       float ms = 0.f;

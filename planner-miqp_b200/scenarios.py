@@ -71,3 +71,50 @@ def random_single_agent(seed: int, nr_regions=16, nr_steps=20):
         side = 1.0 if rng.uniform() < 0.5 else -1.0
         b.add_box_obstacle([[15.0 + rng.uniform(0, 20) + 20 * k, side * rng.uniform(1.0, 2.0), 0.0]], 1.0, 1.0)
     return b
+
+
+def parallel_lanes(n_cars: int, nr_steps=5, lane_offset=4.5, nr_regions=16, stagger=0.0, v=5.0):
+    """n cars side by side on parallel straight references (shape of the reference's n_agents test,
+    test/miqp_planner_test.cc:1528-1565: N=5).  With lane_offset below RR + slack (= 5 m) the
+    collision rows and their slacks are active."""
+    s = settings_for(nr_regions, nr_steps)
+    b = PlanBuilder(s)
+    for c in range(n_cars):
+        y = lane_offset * c
+        b.add_car([stagger * c, v, 0, y, 0.0, 0], [[-20, y], [100, y]], v, 1.0)
+    return b
+
+
+def two_agent_merge(seed: int = 0, nr_regions=16, nr_steps=20):
+    """config 3: two-agent cooperative merge (joint MIQP, lambda = 0.5): the ego follows the x axis,
+    the other car comes from an ending lane at y = -3.5 that merges into it."""
+    rng = np.random.default_rng(3000 + seed)
+    s = settings_for(nr_regions, nr_steps)
+    b = PlanBuilder(s)
+    gap = rng.uniform(-5.0, 5.0)
+    b.add_car([0, rng.uniform(4, 6), 0, 0, 0.0, 0], [[0, 0], [100, 0]], 5.0, 1.0)
+    b.add_car([gap, rng.uniform(4, 6), 0, -3.5, 0.0, 0], [[-20, -3.5], [30, -3.5], [50, 0], [100, 0]], 5.0, 1.0)
+    r = s.collisionRadius
+    b.add_environment_polygon([[-30 + r, -8 + r], [130 - r, -8 + r], [130 - r, 8 - r], [-30 + r, 8 - r]])
+    return b
+
+
+def random_scenario(seed: int, nr_regions=16, nr_steps=20, max_agents=4):
+    """config 4: 1-4 agents on parallel lanes 6 m apart (collision rows present, rarely active),
+    straight or single-bend references, 0-2 static obstacles in the ego lane."""
+    rng = np.random.default_rng(7000 + seed)
+    n = int(rng.integers(1, max_agents + 1))
+    if n == 1:
+        return random_single_agent(seed, nr_regions, nr_steps)
+    s = settings_for(nr_regions, nr_steps)
+    b = PlanBuilder(s)
+    bend = math.radians(rng.uniform(-20, 20)) if rng.uniform() < 0.5 else 0.0
+    for c in range(n):
+        y0 = 6.0 * c
+        ref = [[-10, y0], [30, y0], [30 + 170 * math.cos(bend), y0 + 170 * math.sin(bend)]]
+        v0 = rng.uniform(3, 8)
+        b.add_car([rng.uniform(-3, 3), v0, 0, y0 + rng.uniform(-0.3, 0.3), 0.05, 0], ref, v0, 1.0)
+    for k in range(int(rng.integers(0, 2))):
+        side = 1.0 if rng.uniform() < 0.5 else -1.0
+        b.add_box_obstacle([[20.0 + rng.uniform(0, 15), side * rng.uniform(1.2, 2.0), 0.0]], 1.0, 1.0)
+    return b

@@ -1,0 +1,101 @@
+// multi_emu.cpp -- TEST INFRASTRUCTURE.  Compiles the multi-car node processing of the CUDA
+// backend (planner-miqp_b200/csrc/bnb_multi_core.cuh, node_qp_multi.cuh) for the host with one
+// emulated thread (MQ_EMULATE) and wraps it in a plain sequential branch and bound, so that the
+// logic of the device code (row generation, slack elimination, Riccati sweeps, scan, branching)
+// can be checked against the CPU oracle without a GPU.  Never loaded by the product.
+#define MQ_EMULATE 1
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstdio>
+#include <queue>
+#include <vector>
+
+#include "../../planner-miqp_b200/csrc/host_pack.hpp"
+#include "../../planner-miqp_b200/csrc/formulation_tables.cuh"
+#include "../../planner-miqp_b200/csrc/bnb_multi_core.cuh"
+
+using namespace miqp;
+using namespace miqp::hostpack;
+
+namespace {
+struct Node { double bound; int depth, rank; unsigned long long uid; std::vector<unsigned char> dec; };
+struct Cmp {
+  bool have_inc;
+  bool before(const Node &x, const Node &y) const {
+    if (!have_inc) { if (x.depth != y.depth) return x.depth > y.depth; if (x.rank != y.rank) return x.rank < y.rank; if (x.bound != y.bound) return x.bound < y.bound; return x.uid < y.uid; }
+    if (x.bound != y.bound) return x.bound < y.bound;
+    if (x.depth != y.depth) return x.depth > y.depth;
+    return x.uid < y.uid;
+  }
+};
+}  // namespace
+
+extern "C" int emu_multi_solve(const MiqpB200Problem *q, double gap_tol, double time_limit, long max_nodes,
+                               double *obj_out, double *bound_out, long *nodes_out, long *iters_out,
+                               double *traj_out /* [C][N][8] */, double *sig_out /* [P][N][4] */,
+                               unsigned char *dec_out /* [ndec_pad] */, int verbose) {
+  Packed pk;
+  std::string v = validate(*q);
+  if (!v.empty()) { fprintf(stderr, "emu: %s\n", v.c_str()); return -2; }
+  pack_one(*q, pk);
+  DevProb &p = pk.probs[0];
+  prepare_tables_parallel(p, pk.dblob.data(), pk.iblob.data(), 0, 1);
+  prepare_tables_serial(p, pk.dblob.data(), pk.iblob.data());
+  const int nds = p.ndec_pad;
+  const MLayout L = multi_layout(p.C, p.N, p.P, p.kmax, nds);
+  std::vector<double> ws((size_t)L.total_bytes / 8 + 8, 0.0);
+  MCtx k;
+  k.D = pk.dblob.data(); k.I = pk.iblob.data(); k.tid = 0; k.nthr = 1;
+  multi_bind(k, &p, ws.data(), nds);
+  MShared sh;
+
+  std::vector<Node> open;
+  Node root; root.bound = -HUGE_VAL; root.depth = 0; root.rank = 0; root.uid = 1; root.dec.assign(nds, UNDEC);
+  open.push_back(root);
+  double ub = HUGE_VAL, pruned_lb = HUGE_VAL;
+  long nodes = 0, iters = 0; unsigned long long next_uid = 2;
+  Cmp cmp; cmp.have_inc = false;
+  const auto t0 = std::chrono::steady_clock::now();
+  bool timed_out = false;
+  while (!open.empty()) {
+    if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > time_limit || (max_nodes > 0 && nodes >= max_nodes)) { timed_out = true; break; }
+    size_t bi = 0;
+    for (size_t a = 1; a < open.size(); ++a) if (cmp.before(open[a], open[bi])) bi = a;
+    Node nd = open[bi]; open[bi] = open.back(); open.pop_back();
+    const double cutoff = (ub < HUGE_VAL) ? ub - gap_tol * fabs(ub) : HUGE_VAL;
+    if (nd.bound >= cutoff) { pruned_lb = std::min(pruned_lb, nd.bound); continue; }
+    ++nodes;
+    memcpy(k.dec, nd.dec.data(), nds);
+    MNodeOut out = m_process_node(k, &sh, nd.bound, cutoff, nds);
+    iters += out.iters;
+    if (verbose > 1) fprintf(stderr, "emu node %ld depth %d what %d obj %.6f kind %d c%d i%d q%d viol %.3g open %zu ub %.6f iters %d\n", nodes, nd.depth, out.what, out.obj, sh.br.kind, sh.br.c, sh.br.i, sh.br.q, sh.br.viol, open.size(), ub, out.iters);
+    if (out.what == MN_INFEASIBLE) continue;
+    if (out.what == MN_PRUNED) { pruned_lb = std::min(pruned_lb, out.obj); continue; }
+    if (out.what == MN_INCUMBENT) {
+      if (out.obj < ub) {
+        ub = out.obj; cmp.have_inc = true;
+        for (int c = 0; c < p.C; ++c) for (int i = 0; i < p.N; ++i) for (int t = 0; t < 8; ++t) traj_out[(c * p.N + i) * 8 + t] = k.Z[(long)i * k.nz + 8 * c + t];
+        for (int e = 0; e < p.P * p.N * 4; ++e) sig_out[e] = k.sig[e * SG_SIZE + SG_VAL];
+        memcpy(dec_out, k.dec, nds);
+        if (verbose) fprintf(stderr, "emu incumbent %.8f after %ld nodes\n", ub, nodes);
+      }
+      continue;
+    }
+    const unsigned char *src = out.from_imp ? k.imp : k.dec;
+    for (int a = 0; a < out.nalt; ++a) {
+      Node ch; ch.bound = out.obj; ch.depth = nd.depth + 1; ch.rank = a; ch.uid = next_uid++;
+      ch.dec.assign(src, src + nds);
+      if (out.soff >= 0) { ch.dec[out.soff] = sh.alts[a]; if (sh.alts[a] == k.imp[out.soff]) ch.rank = -1; }
+      else ch.rank = 0;
+      open.push_back(ch);
+    }
+  }
+  double lb = pruned_lb;
+  for (const Node &n : open) lb = std::min(lb, n.bound);
+  if (!timed_out && open.empty() && lb == HUGE_VAL) lb = ub;
+  if (ub < HUGE_VAL && lb > ub) lb = ub;
+  *obj_out = ub; *bound_out = lb; *nodes_out = nodes; *iters_out = iters;
+  if (!(ub < HUGE_VAL)) return timed_out ? 3 : 1;
+  return 0;
+}

@@ -1,0 +1,42 @@
+"""Host logic of the multi-car node processing (planner-miqp_b200/csrc/node_qp_multi.cuh,
+bnb_multi_core.cuh), compiled for the CPU with one emulated thread (tests/emu) and wrapped in a
+sequential branch and bound, against the oracle.  Objective parity 1e-6 relative where the
+oracle proves a 1e-4 gap (north_star tolerance: 1e-4)."""
+import os
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+import emu  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+import planner_miqp_b200  # noqa: F401,E402
+from planner_miqp_b200.scenarios import parallel_lanes  # noqa: E402
+
+
+def both(p, gap=1e-4):
+    r = emu.solve(p, gap, 60.0)
+    xo, io = O.solve(p, gap_tol=gap, time_limit=60.0)
+    return r, io
+
+
+def test_single_car_fixtures_through_generic_code(testcase_problem, sos_problem):
+    for p, pin in ((testcase_problem, 9.57603), (sos_problem, None)):
+        r, io = both(p)
+        assert r["status"] == 0 and io.status == 0 and io.proven
+        assert r["objective"] == pytest.approx(io.objective, rel=1e-6)
+        assert abs(r["bound"] - r["objective"]) <= 1e-4 * abs(r["objective"])
+        if pin:
+            assert abs(r["objective"] - pin) < 1e-5      # test/cplex_wrapper_test.cc:874
+
+
+@pytest.mark.parametrize("cars,steps,offset,stagger", [(2, 5, 8.0, 0.0), (2, 5, 3.5, 0.0), (2, 5, 4.5, 0.0),
+                                                      (2, 6, 4.8, 1.0), (2, 5, 2.0, 6.0)])
+def test_collision_rows_and_slacks(cars, steps, offset, stagger):
+    p = parallel_lanes(cars, steps, offset, stagger=stagger).build()
+    r, io = both(p)
+    assert io.status == 0 and io.proven
+    assert r["status"] == 0
+    assert r["objective"] == pytest.approx(io.objective, rel=1e-6, abs=1e-7)
+    assert abs(r["bound"] - r["objective"]) <= 1e-4 * abs(r["objective"]) + 1e-9
