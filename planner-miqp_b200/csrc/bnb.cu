@@ -25,16 +25,22 @@
 
 namespace miqp {
 
-// priority key, smaller = earlier.  Without incumbent: depth first (deepest, then the least
-// violated alternative, then bound); with incumbent: best bound first, then deepest.
-__device__ __forceinline__ unsigned long long node_key(double bound, int depth, int rank, unsigned long long uid, bool have_inc) {
+// priority key, smaller = earlier.  Without incumbent the search dives: the children created in the
+// last round come first (least violated alternative first, then bound); if the dive died (no
+// newborn node) it restarts from the best bound.  Deepest-first backtracking is deliberately NOT
+// used: it gets trapped below a wrong early decision (seen on 3 of 512 config-2 plans: 20k+ nodes
+// instead of ~40).  With an incumbent: best bound first, then deepest.
+__device__ __forceinline__ unsigned long long node_key(double bound, int depth, int rank, unsigned long long uid, bool have_inc, bool newborn) {
   unsigned long long d = 1023 - (unsigned long long)(depth > 1023 ? 1023 : depth);  // 10 bits
   unsigned long long r = (unsigned long long)(rank + 1 > 127 ? 127 : rank + 1);      // 7 bits
   unsigned long long b = ordered_bits(bound) >> 24;                                   // 40 bits
   unsigned long long u = uid & 127ULL;                                                // 7 bits
   if (have_inc) return (b << 24) | (d << 14) | (r << 7) | u;
-  return (d << 54) | (r << 47) | (b << 7) | u;
+  if (newborn) return (r << 47) | (b << 7) | u;
+  return (1ULL << 63) | (b << 17) | (d << 7) | u;
 }
+__device__ __forceinline__ int meta_rank(int my) { return (my & 0xff) - 1; }
+__device__ __forceinline__ int meta_birth(int my) { return my >> 8; }
 
 // ---------------------------------------------------------------------------------------
 // init
@@ -55,10 +61,10 @@ __global__ void bnb_init_kernel(BnbState st, const DevProb *probs, const unsigne
   }
   if (tid == 0) {
     st.free_cnt[s] = st.cap - nroot;
-    st.bound[pb] = -MQ_INF; st.meta[pb] = make_int2(0, 0); st.uid[pb] = 1ULL;
+    st.bound[pb] = -MQ_INF; st.meta[pb] = make_int2(0, 1); st.uid[pb] = 1ULL;
     st.open_idx[pb] = 0;
     if (nroot == 2) {  // MIP start: the fully decided node is evaluated first (cplex_wrapper.cpp:494-639)
-      st.bound[pb + 1] = -MQ_INF; st.meta[pb + 1] = make_int2(1 << 20, 0); st.uid[pb + 1] = 2ULL;
+      st.bound[pb + 1] = -MQ_INF; st.meta[pb + 1] = make_int2(1 << 20, 0); st.uid[pb + 1] = 2ULL;   // rank -1: before the root
       st.open_idx[pb + 1] = 1;
     }
     st.open_cnt[s] = nroot;
@@ -67,7 +73,7 @@ __global__ void bnb_init_kernel(BnbState st, const DevProb *probs, const unsigne
     st.done[s] = 0; st.lock[s] = 0;
     st.stat_nodes[s] = 0; st.stat_iters[s] = 0; st.stat_rows[s] = 0;
     st.inc_uid[s] = ~0ULL;
-    if (s == 0) { *st.work_cnt = 0; *st.work_next = 0; *st.active = 0; *st.err = 0; *st.work_cnt2 = 0; *st.work_next2 = 0; }
+    if (s == 0) { *st.active_prev = 0; *st.work_cnt = 0; *st.work_next = 0; *st.active = 0; *st.err = 0; *st.work_cnt2 = 0; *st.work_next2 = 0; }
   }
 }
 
@@ -92,7 +98,7 @@ __device__ __forceinline__ int block_excl_scan(int flag, int *warp_tot /*[8]*/, 
   return off + pre;
 }
 
-__global__ void __launch_bounds__(SEL_THREADS) bnb_select_kernel(BnbState st, const DevProb *probs, int round_reset) {
+__global__ void __launch_bounds__(SEL_THREADS) bnb_select_kernel(BnbState st, const DevProb *probs, int round) {
   const int s = blockIdx.x;
   const int tid = threadIdx.x;
   __shared__ int warp_tot[SEL_THREADS / 32];
@@ -103,16 +109,26 @@ __global__ void __launch_bounds__(SEL_THREADS) bnb_select_kernel(BnbState st, co
   if (st.done[s]) return;
   const DevProb &p = probs[s];
   const long pb = (long)s * st.cap;
-  const int K = st.sel_per_plan;
+  const int KS = st.sel_per_plan;   // stride of sel_idx = largest number of nodes a plan may take per round
   // 1. release the slots processed in the last round
   const int nsel_prev = st.sel_cnt[s];
   const int free0 = st.free_cnt[s];
-  for (int k = tid; k < nsel_prev; k += SEL_THREADS) st.free_stack[pb + free0 + k] = st.sel_idx[(long)s * K + k];
+  for (int k = tid; k < nsel_prev; k += SEL_THREADS) st.free_stack[pb + free0 + k] = st.sel_idx[(long)s * KS + k];
   if (tid == 0) { s_free = free0 + nsel_prev; s_out = 0; s_tie = 0; }
   // 2. cutoff snapshot
   const double ub = st.ub[s];
   const bool have_inc = ub < MQ_INF;
   const double cutoff = have_inc ? ub - p.gap_tol * fabs(ub) : MQ_INF;
+  // nodes taken this round: one dive head per plan until an incumbent exists; afterwards the base
+  // count, raised when few plans are still active so that the resident warps stay busy
+  int K = st.sel_dive;
+  if (have_inc) {
+    const int act = *st.active_prev > 0 ? *st.active_prev : st.count;
+    K = st.sel_base;
+    const int fill = st.nwarps / act;
+    if (fill > K) K = fill;
+    if (K > KS) K = KS;
+  }
   __syncthreads();
   // 3. prune by bound, compute keys, compact in place
   const int n0 = st.open_cnt[s];
@@ -124,7 +140,7 @@ __global__ void __launch_bounds__(SEL_THREADS) bnb_select_kernel(BnbState st, co
       slot = st.open_idx[pb + idx];
       const double b = st.bound[pb + slot];
       keep = (b < cutoff);
-      if (keep) { int2 m = st.meta[pb + slot]; key = node_key(b, m.x, m.y, st.uid[pb + slot], have_inc); }
+      if (keep) { int2 m = st.meta[pb + slot]; key = node_key(b, m.x, meta_rank(m.y), st.uid[pb + slot], have_inc, meta_birth(m.y) == round - 1); }
       else { pruned = fmin(pruned, b); int pos = atomicAdd(&s_free, 1); st.free_stack[pb + pos] = slot; }
     }
     int total; const int rank = block_excl_scan(keep, warp_tot, total);
@@ -185,7 +201,7 @@ __global__ void __launch_bounds__(SEL_THREADS) bnb_select_kernel(BnbState st, co
     int tsel; const int rsel = block_excl_scan(sel, warp_tot, tsel);
     int tkeep; const int rkeep = block_excl_scan(keep, warp_tot, tkeep);
     const int out0 = s_out;
-    if (sel) st.sel_idx[(long)s * K + nsel_total + rsel] = slot;
+    if (sel) st.sel_idx[(long)s * KS + nsel_total + rsel] = slot;
     if (keep) { st.open_idx[pb + out0 + rkeep] = slot; st.keybuf[pb + out0 + rkeep] = key; }
     nsel_total += tsel;
     __syncthreads();
@@ -204,15 +220,15 @@ __global__ void __launch_bounds__(SEL_THREADS) bnb_select_kernel(BnbState st, co
   if (nsel_total > 0) {
     const int wb = s_wbase;
     int2 *wl = (p.C > 1 || st.force_multi) ? st.work2 : st.work;   // plans with several cars go to the CTA-per-node kernel
-    for (int k = tid; k < nsel_total; k += SEL_THREADS) wl[wb + k] = make_int2(s, st.sel_idx[(long)s * K + k]);
+    for (int k = tid; k < nsel_total; k += SEL_THREADS) wl[wb + k] = make_int2(s, st.sel_idx[(long)s * KS + k]);
   }
 }
 
-__global__ void bnb_round_reset_kernel(BnbState st) { *st.work_cnt = 0; *st.work_next = 0; *st.active = 0; *st.work_cnt2 = 0; *st.work_next2 = 0; }
+__global__ void bnb_round_reset_kernel(BnbState st) { *st.active_prev = *st.active; *st.work_cnt = 0; *st.work_next = 0; *st.active = 0; *st.work_cnt2 = 0; *st.work_next2 = 0; }
 
-void launch_bnb_select(const BnbState &st, const DevProb *probs, cudaStream_t s) {
+void launch_bnb_select(const BnbState &st, const DevProb *probs, int round, cudaStream_t s) {
   bnb_round_reset_kernel<<<1, 1, 0, s>>>(st);
-  bnb_select_kernel<<<st.count, SEL_THREADS, 0, s>>>(st, probs, 0);
+  bnb_select_kernel<<<st.count, SEL_THREADS, 0, s>>>(st, probs, round);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -412,7 +428,10 @@ __host__ __device__ inline NodeSmem node_smem_layout(int maxN, int kmax, int nde
   NodeSmem L;
   int b = (maxN * (S_STRIDE + V_STRIDE + 1) + T_SIZE) * 8;
   b = (b + 15) & ~15;
-  L.off_rows = b; b += kmax * maxN * 16;
+  L.off_rows = b;   // (s, lambda) records: see RowIO (node_qp.cuh)
+#ifndef MQ_ROWS_L2
+  b += (kmax + 1) * maxN * 16;
+#endif
   L.off_int = b; b += maxN * 4 * 4;
   b = (b + 15) & ~15;
   L.off_dec = b; b += 2 * ndec_stride + 272;
@@ -422,7 +441,7 @@ __host__ __device__ inline NodeSmem node_smem_layout(int maxN, int kmax, int nde
 int node_kernel_smem_per_warp(int maxN, int kmax, int ndec_stride) { return node_smem_layout(maxN, kmax, ndec_stride).total; }
 
 __global__ void __launch_bounds__(128) bnb_nodes_kernel(BnbState st, const DevProb *probs, const double *dblob,
-                                                        const int *iblob, int smem_per_warp, int maxN) {
+                                                        const int *iblob, int smem_per_warp, int maxN, int round) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char *base = smem_raw + (size_t)warp * smem_per_warp;
@@ -433,7 +452,11 @@ __global__ void __launch_bounds__(128) bnb_nodes_kernel(BnbState st, const DevPr
   w.V = w.S + maxN * S_STRIDE;
   w.T = w.V + maxN * V_STRIDE;
   w.auxd = w.T + T_SIZE;
+#ifndef MQ_ROWS_L2
   w.rows = reinterpret_cast<double2 *>(base + L.off_rows);
+#else
+  w.rows = st.rows_ws + (size_t)(blockIdx.x * (blockDim.x >> 5) + warp) * (size_t)(st.kmax + 1) * maxN;
+#endif
   w.jeff = reinterpret_cast<int *>(base + L.off_int);
   w.aux = w.jeff + maxN;
   w.dec = base + L.off_dec;
@@ -538,7 +561,7 @@ __global__ void __launch_bounds__(128) bnb_nodes_kernel(BnbState st, const DevPr
         int rank = 0;
         if (soff >= 0) { dst[soff] = alts[a]; rank = (alts[a] == w.imp[soff]) ? -1 : a; }
         st.bound[pb + cs] = obj;
-        st.meta[pb + cs] = make_int2(nmeta.x >= (1 << 20) ? nmeta.x : nmeta.x + 1, rank);
+        st.meta[pb + cs] = make_int2(nmeta.x >= (1 << 20) ? nmeta.x : nmeta.x + 1, (round << 8) | (rank + 1));
         st.uid[pb + cs] = mix64(nuid * 0x9e3779b97f4a7c15ULL + (unsigned long long)(a + 1));
         st.open_idx[pb + opos + a] = cs;
       }
@@ -555,9 +578,9 @@ int node_kernel_max_ctas(int smem_per_cta, int threads) {
 }
 
 int launch_bnb_nodes(const BnbState &st, const DevProb *probs, const double *dblob, const int *iblob,
-                     int smem_per_warp, int warps_per_cta, int ctas, int maxN, cudaStream_t s) {
+                     int smem_per_warp, int warps_per_cta, int ctas, int maxN, int round, cudaStream_t s) {
   bnb_nodes_kernel<<<ctas, warps_per_cta * 32, (size_t)smem_per_warp * warps_per_cta, s>>>(st, probs, dblob, iblob,
-                                                                                             smem_per_warp, maxN);
+                                                                                             smem_per_warp, maxN, round);
   return (int)cudaGetLastError();
 }
 

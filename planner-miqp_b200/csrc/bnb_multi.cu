@@ -19,7 +19,7 @@ long multi_workspace_bytes(int C, int N, int P, int kmax, int ndec_stride) {
 }
 
 __global__ void __launch_bounds__(MULTI_MAX_THREADS) bnb_nodes_multi_kernel(BnbState st, const DevProb *probs, const double *dblob,
-                                                                            const int *iblob, double *gws, long ws_bytes, int use_smem) {
+                                                                            const int *iblob, double *gws, long ws_bytes, int use_smem, int round) {
   extern __shared__ __align__(16) unsigned char smem_multi[];
   __shared__ MShared sh;
   __shared__ int s_i[4];
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(MULTI_MAX_THREADS) bnb_nodes_multi_kernel(BnbS
           int rank = 0;
           if (out.soff >= 0) { dst[out.soff] = sh.alts[a]; rank = (sh.alts[a] == k.imp[out.soff]) ? -1 : a; }
           st.bound[pb + cs] = out.obj;
-          st.meta[pb + cs] = make_int2(nmeta.x >= (1 << 20) ? nmeta.x : nmeta.x + 1, rank);
+          st.meta[pb + cs] = make_int2(nmeta.x >= (1 << 20) ? nmeta.x : nmeta.x + 1, (round << 8) | (rank + 1));
           st.uid[pb + cs] = mix64(nuid * 0x9e3779b97f4a7c15ULL + (unsigned long long)(a + 1));
           st.open_idx[pb + opos + a] = cs;
         }
@@ -134,8 +134,8 @@ int multi_kernel_max_ctas(int smem_bytes, int threads) {
 }
 
 int launch_bnb_nodes_multi(const BnbState &st, const DevProb *probs, const double *dblob, const int *iblob,
-                           double *gws, long ws_bytes, int use_smem, int threads, int ctas, cudaStream_t s) {
-  bnb_nodes_multi_kernel<<<ctas, threads, use_smem ? (size_t)ws_bytes : 0, s>>>(st, probs, dblob, iblob, gws, ws_bytes, use_smem);
+                           double *gws, long ws_bytes, int use_smem, int threads, int ctas, int round, cudaStream_t s) {
+  bnb_nodes_multi_kernel<<<ctas, threads, use_smem ? (size_t)ws_bytes : 0, s>>>(st, probs, dblob, iblob, gws, ws_bytes, use_smem, round);
   return (int)cudaGetLastError();
 }
 

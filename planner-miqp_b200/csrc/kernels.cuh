@@ -22,7 +22,9 @@ struct BnbState {
   int kmax;             // row slots per stage (max over plans)
   int npad;             // stages padded to a multiple of 32 (max over plans)
   int nwarps;           // resident warps of the node kernel
-  int sel_per_plan;     // K: node relaxations taken per plan per round
+  int sel_per_plan;     // stride of sel_idx: most node relaxations a plan may take in one round
+  int sel_base;         // nodes per plan per round once an incumbent exists (raised when few plans are active)
+  int sel_dive;         // nodes per plan per round while diving for the first incumbent
   int work_cap;
   int force_multi;      // route every plan to the CTA-per-node kernel (test hook)
   // node pools [count][cap]
@@ -45,16 +47,17 @@ struct BnbState {
   unsigned long long *inc_uid;  // tie break between equal incumbents (deterministic result)
   unsigned long long *stat_nodes, *stat_iters, *stat_rows;
   // round control
-  int2 *work; int *work_cnt; int *work_next; int *active; int *err;
+  int2 *work; int *work_cnt; int *work_next; int *active; int *err; int *active_prev;
+  double2 *rows_ws;     // [nwarps][kmax+1][maxN] (s, lambda) records of the warp-per-node kernel
   int2 *work2; int *work_cnt2; int *work_next2;   // plans with NumCars > 1 (bnb_multi.cu)
 };
 
 void launch_bnb_init(const BnbState &st, const DevProb *probs, const unsigned char *warm_dec /* [count][ndec_stride] or null */,
                      const int *has_warm, cudaStream_t s);
-void launch_bnb_select(const BnbState &st, const DevProb *probs, cudaStream_t s);
+void launch_bnb_select(const BnbState &st, const DevProb *probs, int round, cudaStream_t s);
 // returns 0 or a cudaError
 int launch_bnb_nodes(const BnbState &st, const DevProb *probs, const double *dblob, const int *iblob,
-                     int smem_per_warp, int warps_per_cta, int ctas, int maxN, cudaStream_t s);
+                     int smem_per_warp, int warps_per_cta, int ctas, int maxN, int round, cudaStream_t s);
 void launch_bnb_finish(const BnbState &st, const DevProb *probs, const double *dblob, const int *iblob,
                        double *xall, double *best_bound, cudaStream_t s);
 int node_kernel_smem_per_warp(int maxN, int kmax, int ndec_stride);
@@ -66,6 +69,6 @@ int node_kernel_max_ctas(int smem_per_cta, int threads);
 long multi_workspace_bytes(int C, int N, int P, int kmax, int ndec_stride);
 int multi_kernel_max_ctas(int smem_bytes, int threads);
 int launch_bnb_nodes_multi(const BnbState &st, const DevProb *probs, const double *dblob, const int *iblob,
-                           double *gws, long ws_bytes, int use_smem, int threads, int ctas, cudaStream_t s);
+                           double *gws, long ws_bytes, int use_smem, int threads, int ctas, int round, cudaStream_t s);
 
 }  // namespace miqp

@@ -68,7 +68,7 @@ struct WarpCtx {
   int *aux;             // [3N] scan tables: best alt, region_decided, blame
   double *auxd;         // [N] scan: best non-frozen violation
   double *T;            // [T_SIZE] Riccati scratch (value function of the next stage)
-  double2 *rows;        // [kmax][N] (s, lambda) per inequality row
+  double2 *rows;        // [kmax+1][N] (s, lambda) per inequality row
   int lane, N;
 };
 
@@ -212,6 +212,32 @@ struct StepCtx {  // quantities of the last Newton step, needed to recompute it 
   bool pending;
 };
 
+// (s, lambda) of the inequality rows of one stage, [slot][stage] in the warp's shared memory.
+// Measured alternative (-DMQ_ROWS_L2): the records in a per-warp slice of HBM that stays L2
+// resident, with the record of slot+1 requested while slot is processed; it halves the shared
+// memory of a node (8 instead of 4 warps per SM at N=40) but runs 1.6x SLOWER (2048 config-2
+// plans: 652 ms vs 405 ms) -- the L2 round trip per row is not hidden by one more warp per
+// scheduler.  profiles/r1_ab_rows_l2_vs_smem.md
+struct RowIO {
+  double2 *base;   // rows + i
+  int N, pslot;
+  double2 pref;
+  __device__ __forceinline__ void init(double2 *rows, int N_, int i) { base = rows + i; N = N_; pslot = -1; pref = make_double2(1.0, 1.0); }
+#ifndef MQ_ROWS_L2   // default: records in shared memory
+  __device__ __forceinline__ double2 ld(int slot) { return base[slot * N]; }
+  __device__ __forceinline__ void st(int slot, double2 v) { base[slot * N] = v; }
+#else
+  __device__ __forceinline__ double2 ld(int slot) {
+    double2 v;
+    if (slot == pslot) v = pref; else v = __ldcg(base + slot * N);
+    pslot = slot + 1;
+    pref = __ldcg(base + (slot + 1) * N);   // one spare slot row is allocated behind the last one
+    return v;
+  }
+  __device__ __forceinline__ void st(int slot, double2 v) { __stcg(base + slot * N, v); }
+#endif
+};
+
 __device__ __forceinline__ double dot6(const double a[6], const double y[8]) {
   double v = 0.0;
 #pragma unroll
@@ -220,23 +246,23 @@ __device__ __forceinline__ double dot6(const double a[6], const double y[8]) {
 }
 
 struct PassInit {  // s = max(h - g.z, 1), lambda = 1
-  double2 *rows; int N, i; double y[8];
+  RowIO io; double y[8];
   __device__ __forceinline__ void put(int slot, double gz, double rhs) {
     const double sl = rhs - gz;
-    rows[slot * N + i] = make_double2(sl > 1.0 ? sl : 1.0, 1.0);
+    io.st(slot, make_double2(sl > 1.0 ? sl : 1.0, 1.0));
   }
   template <int T> __device__ __forceinline__ void bound(int slot, double sgn, double rhs) { put(slot, sgn * y[T], rhs); }
   __device__ __forceinline__ void general(int slot, const double a[6], double rhs) { put(slot, dot6(a, y), rhs); }
 };
 
 struct PassA {  // apply the pending step, residuals, Hessian and predictor gradient
-  double2 *rows; int N, i; StepCtx sc;
+  RowIO io; StepCtx sc;
   double y[8], d[8], da[8];
   double H[21], Huu[2], gx[8], gl[8];
   double rpn, musum, lmax; int m;
   // returns (weight, weight*rp, lambda) of the row after the update
   __device__ __forceinline__ void core(int slot, double gz, double gdz, double gda, double rhs, double &wgt, double &wr, double &lam_out) {
-    double2 v = rows[slot * N + i];
+    double2 v = io.ld(slot);
     double s = v.x, lam = v.y;
     if (sc.pending) {
       const double rp_old = (gz - sc.alpha * gdz) + s - rhs;
@@ -247,7 +273,7 @@ struct PassA {  // apply the pending step, residuals, Hessian and predictor grad
       const double rc = s * lam + dsa * dla - sc.sigmu;
       const double dl = -(rc + lam * ds) * inv;
       s += sc.alpha * ds; lam += sc.alpha * dl;
-      rows[slot * N + i] = make_double2(s, lam);
+      io.st(slot, make_double2(s, lam));
     }
     const double rp = gz + s - rhs;
     wgt = lam * fast_rcp(s); wr = wgt * rp; lam_out = lam;
@@ -274,10 +300,10 @@ struct PassA {  // apply the pending step, residuals, Hessian and predictor grad
 };
 
 struct PassD {  // affine step: ratios and the three sums that give mu_aff for any step length
-  double2 *rows; int N, i; double y[8], da[8];
+  RowIO io; double y[8], da[8];
   double rmax, s1, s2;   // rmax = 1 / (largest feasible affine step), kept >= 1
   __device__ __forceinline__ void row(int slot, double gz, double gda, double rhs) {
-    const double2 v = rows[slot * N + i];
+    const double2 v = io.ld(slot);
     const double s = v.x, lam = v.y;
     const double rp = gz + s - rhs;
     const double dsa = -rp - gda;
@@ -292,9 +318,9 @@ struct PassD {  // affine step: ratios and the three sums that give mu_aff for a
 };
 
 struct PassE {  // corrector gradient
-  double2 *rows; int N, i; double sigmu; double y[8], da[8]; double gx[8];
+  RowIO io; double sigmu; double y[8], da[8]; double gx[8];
   __device__ __forceinline__ double coef(int slot, double gz, double gda, double rhs) {
-    const double2 v = rows[slot * N + i];
+    const double2 v = io.ld(slot);
     const double s = v.x, lam = v.y;
     const double inv = fast_rcp(s);
     const double rp = gz + s - rhs;
@@ -311,10 +337,10 @@ struct PassE {  // corrector gradient
 };
 
 struct PassG {  // step length of the combined step
-  double2 *rows; int N, i; double sigmu; double y[8], d[8], da[8];
+  RowIO io; double sigmu; double y[8], d[8], da[8];
   double rmax;   // 1 / (largest step that keeps s and lambda non-negative), starts at 0
   __device__ __forceinline__ void row(int slot, double gz, double gdz, double gda, double rhs) {
-    const double2 v = rows[slot * N + i];
+    const double2 v = io.ld(slot);
     const double s = v.x, lam = v.y;
     const double inv = fast_rcp(s);
     const double rp = gz + s - rhs;
@@ -535,7 +561,7 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
   for (int i = lane; i < N; i += 32) {
     double *Vi = w.V + i * V_STRIDE;
     const double t = i * p.ts;
-    PassInit v; v.rows = w.rows; v.N = N; v.i = i;
+    PassInit v; v.io.init(w.rows, N, i);
 #pragma unroll
     for (int ax = 0; ax < 2; ++ax) {
       const double P = x0[3 * ax], Vv = x0[3 * ax + 1], A = x0[3 * ax + 2];
@@ -562,7 +588,7 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
     double rpn = 0.0, musum = 0.0, lmax = 0.0, rd0 = 0.0; int m = 0;
     for (int i = lane; i < N; i += 32) {
       double *Vi = w.V + i * V_STRIDE, *Si = w.S + i * S_STRIDE;
-      PassA v; v.rows = w.rows; v.N = N; v.i = i; v.sc = sc;
+      PassA v; v.io.init(w.rows, N, i); v.sc = sc;
       v.rpn = 0.0; v.musum = 0.0; v.lmax = 0.0; v.m = 0;
 #pragma unroll
       for (int t = 0; t < 21; ++t) v.H[t] = 0.0;
@@ -600,7 +626,7 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
     double rmax = 1.0, s1 = 0.0, s2 = 0.0;
     for (int i = lane; i < N; i += 32) {
       const double *Vi = w.V + i * V_STRIDE;
-      PassD v; v.rows = w.rows; v.N = N; v.i = i; v.rmax = 1.0; v.s1 = 0.0; v.s2 = 0.0;
+      PassD v; v.io.init(w.rows, N, i); v.rmax = 1.0; v.s1 = 0.0; v.s2 = 0.0;
 #pragma unroll
       for (int t = 0; t < 8; ++t) { v.y[t] = Vi[V_Z + t]; v.da[t] = Vi[V_DZA + t]; }
       visit_rows(w, i, v);
@@ -620,7 +646,7 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
     // ---- corrector ----
     for (int i = lane; i < N; i += 32) {
       double *Vi = w.V + i * V_STRIDE;
-      PassE v; v.rows = w.rows; v.N = N; v.i = i; v.sigmu = sigmu;
+      PassE v; v.io.init(w.rows, N, i); v.sigmu = sigmu;
 #pragma unroll
       for (int t = 0; t < 8; ++t) { v.y[t] = Vi[V_Z + t]; v.da[t] = Vi[V_DZA + t]; v.gx[t] = 0.0; }
       visit_rows(w, i, v);
@@ -635,7 +661,7 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
     bool bad_step = false;
     for (int i = lane; i < N; i += 32) {
       const double *Vi = w.V + i * V_STRIDE;
-      PassG v; v.rows = w.rows; v.N = N; v.i = i; v.sigmu = sigmu; v.rmax = 0.0;
+      PassG v; v.io.init(w.rows, N, i); v.sigmu = sigmu; v.rmax = 0.0;
 #pragma unroll
       for (int t = 0; t < 8; ++t) { v.y[t] = Vi[V_Z + t]; v.d[t] = Vi[V_DZ + t]; v.da[t] = Vi[V_DZA + t]; }
       bad_step |= !(fabs(v.d[Y_UX]) + fabs(v.d[Y_UY]) + fabs(v.d[Y_PX]) + fabs(v.d[Y_PY]) < 1e300);  // NaN / inf step

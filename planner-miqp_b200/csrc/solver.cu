@@ -86,6 +86,7 @@ struct MiqpB200Solver {
   long multi_ws_bytes = 0;
   DevBuf<double> b_multi_ws;
   DevBuf<int2> b_work2;
+  DevBuf<double2> b_rows_ws;
   bool uploaded = false, ran = false;
   double last_seconds = 0.0;
   bool timed_out = false;
@@ -159,6 +160,8 @@ void setup_bnb(MiqpB200Solver *s) {
     if (per_sm <= 0) throw std::runtime_error("node kernel does not fit in shared memory for this horizon");
     s->ctas = per_sm * s->num_sms;
     st.nwarps += s->ctas * s->warps_per_cta;
+    s->b_rows_ws.ensure((size_t)s->ctas * s->warps_per_cta * (size_t)(st.kmax + 1) * s->single_maxN);
+    st.rows_ws = s->b_rows_ws.p;
   }
   if (s->n_multi > 0) {
     s->multi_threads = (maxCm <= 2) ? 64 : 128;
@@ -172,10 +175,15 @@ void setup_bnb(MiqpB200Solver *s) {
     if (!s->multi_use_smem) s->b_multi_ws.ensure((size_t)s->multi_ctas * (size_t)s->multi_ws_bytes / 8 + 16);
     st.nwarps += s->multi_ctas;
   }
-  // nodes per plan per round: fill the resident warps about twice
+  // nodes per plan per round.  Base count: enough to fill the resident warps once (every extra node
+  // per round is speculative: 37 -> 45 -> 53 nodes per config-2 plan at 1 / 3 / 5); one dive head
+  // per plan until an incumbent exists; up to KS when few plans are still active.
   int K = s->opt.nodes_per_round;
-  if (K <= 0) { K = (2 * st.nwarps + count - 1) / count; if (K < 1) K = 1; if (K > 1024) K = 1024; }
-  st.sel_per_plan = K;
+  if (K <= 0) { K = (st.nwarps + count - 1) / count; if (K < 1) K = 1; if (K > 64) K = 64; }
+  st.sel_base = K;
+  st.sel_dive = std::max(1, std::min(8, st.nwarps / std::max(count, 1)));   // several dive heads only when warps would idle
+  int KS = std::max(K, std::min(64, std::max(1, st.nwarps)));
+  st.sel_per_plan = KS;
   // pool capacity per plan
   int cap = s->opt.pool_capacity;
   if (cap <= 0) {
@@ -186,9 +194,9 @@ void setup_bnb(MiqpB200Solver *s) {
     if (c < 256) c = 256;
     cap = (int)c;
   }
-  if (cap < 4 * K + 64) cap = 4 * K + 64;
+  if (cap < 4 * KS + 64) cap = 4 * KS + 64;
   st.cap = cap;
-  st.work_cap = count * K;
+  st.work_cap = count * KS;
   const size_t nodes = (size_t)count * cap;
   s->b_dec.ensure(nodes * st.ndec_stride); st.dec = s->b_dec.p;
   s->b_bound.ensure(nodes); st.bound = s->b_bound.p;
@@ -199,7 +207,7 @@ void setup_bnb(MiqpB200Solver *s) {
   s->b_keybuf.ensure(nodes); st.keybuf = s->b_keybuf.p;
   s->b_opencnt.ensure(count); st.open_cnt = s->b_opencnt.p;
   s->b_freecnt.ensure(count); st.free_cnt = s->b_freecnt.p;
-  s->b_sel.ensure((size_t)count * K); st.sel_idx = s->b_sel.p;
+  s->b_sel.ensure((size_t)count * KS); st.sel_idx = s->b_sel.p;
   s->b_selcnt.ensure(count); st.sel_cnt = s->b_selcnt.p;
   s->b_ub.ensure(count); st.ub = s->b_ub.p;
   s->b_cutoff.ensure(count); st.cutoff = s->b_cutoff.p;
@@ -215,7 +223,7 @@ void setup_bnb(MiqpB200Solver *s) {
   s->b_work2.ensure(st.work_cap); st.work2 = s->b_work2.p;
   s->b_ctrl.ensure(8);
   st.work_cnt = s->b_ctrl.p; st.work_next = s->b_ctrl.p + 1; st.active = s->b_ctrl.p + 2; st.err = s->b_ctrl.p + 3;
-  st.work_cnt2 = s->b_ctrl.p + 4; st.work_next2 = s->b_ctrl.p + 5;
+  st.work_cnt2 = s->b_ctrl.p + 4; st.work_next2 = s->b_ctrl.p + 5; st.active_prev = s->b_ctrl.p + 6;
   s->d_x.ensure(std::max<long>(pk.total_cols, 1));
   s->d_viol.ensure(count); s->d_obj.ensure(count); s->d_bb.ensure(count);
 }
@@ -271,7 +279,7 @@ void miqp_b200_destroy(MiqpB200Solver *s) {
   s->b_pruned.release(); s->b_incz.release(); s->b_meta.release(); s->b_work.release();
   s->b_uid.release(); s->b_keybuf.release(); s->b_incuid.release(); s->b_stats.release(); s->b_open.release();
   s->b_opencnt.release(); s->b_free.release(); s->b_freecnt.release(); s->b_sel.release(); s->b_selcnt.release();
-  s->b_done.release(); s->b_lock.release(); s->b_ctrl.release(); s->b_multi_ws.release(); s->b_work2.release();
+  s->b_done.release(); s->b_lock.release(); s->b_ctrl.release(); s->b_multi_ws.release(); s->b_work2.release(); s->b_rows_ws.release();
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   if (s->evr0) cudaEventDestroy(s->evr0);
@@ -418,18 +426,18 @@ int miqp_b200_batch_run(MiqpB200Solver *s, float *device_ms) {
     s->timed_out = false;
     int ctrl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (;;) {
-      launch_bnb_select(s->st, s->d_probs.p, s->stream);
+      launch_bnb_select(s->st, s->d_probs.p, (int)rounds + 1, s->stream);
       launches += 2;
       CK(cudaEventRecord(s->evr0, s->stream));
       if (s->n_single > 0) {
         int rc = launch_bnb_nodes(s->st, s->d_probs.p, s->d_dblob.p, s->d_iblob.p, s->smem_per_warp, s->warps_per_cta,
-                                  s->ctas, s->single_maxN, s->stream);
+                                  s->ctas, s->single_maxN, (int)rounds + 1, s->stream);
         if (rc != 0) throw std::runtime_error(std::string("node kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
         ++launches; ++node_launches;
       }
       if (s->n_multi > 0) {
         int rc = launch_bnb_nodes_multi(s->st, s->d_probs.p, s->d_dblob.p, s->d_iblob.p, s->b_multi_ws.p, s->multi_ws_bytes,
-                                        s->multi_use_smem, s->multi_threads, s->multi_ctas, s->stream);
+                                        s->multi_use_smem, s->multi_threads, s->multi_ctas, (int)rounds + 1, s->stream);
         if (rc != 0) throw std::runtime_error(std::string("multi-car node kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
         ++launches; ++node_launches;
       }

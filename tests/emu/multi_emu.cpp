@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <chrono>
+#include <cstdlib>
 #include <cstdio>
 #include <queue>
 #include <vector>
@@ -19,10 +20,18 @@ using namespace miqp;
 using namespace miqp::hostpack;
 
 namespace {
-struct Node { double bound; int depth, rank; unsigned long long uid; std::vector<unsigned char> dec; };
+struct Node { double bound; int depth, rank; long birth; unsigned long long uid; std::vector<unsigned char> dec; };
 struct Cmp {
-  bool have_inc;
+  bool have_inc; long round; int policy;   // policy 0: deepest first; 1: children of the last round first, else best bound
   bool before(const Node &x, const Node &y) const {
+    if (!have_inc && policy == 1) {
+      const bool nx = (x.birth == round - 1), ny = (y.birth == round - 1);
+      if (nx != ny) return nx;
+      if (nx) { if (x.rank != y.rank) return x.rank < y.rank; if (x.bound != y.bound) return x.bound < y.bound; return x.uid < y.uid; }
+      if (x.bound != y.bound) return x.bound < y.bound;
+      if (x.depth != y.depth) return x.depth > y.depth;
+      return x.uid < y.uid;
+    }
     if (!have_inc) { if (x.depth != y.depth) return x.depth > y.depth; if (x.rank != y.rank) return x.rank < y.rank; if (x.bound != y.bound) return x.bound < y.bound; return x.uid < y.uid; }
     if (x.bound != y.bound) return x.bound < y.bound;
     if (x.depth != y.depth) return x.depth > y.depth;
@@ -51,19 +60,35 @@ extern "C" int emu_multi_solve(const MiqpB200Problem *q, double gap_tol, double 
   MShared sh;
 
   std::vector<Node> open;
-  Node root; root.bound = -HUGE_VAL; root.depth = 0; root.rank = 0; root.uid = 1; root.dec.assign(nds, UNDEC);
+  Node root; root.bound = -HUGE_VAL; root.depth = 0; root.rank = 0; root.uid = 1; root.birth = -5; root.dec.assign(nds, UNDEC);
   open.push_back(root);
   double ub = HUGE_VAL, pruned_lb = HUGE_VAL;
   long nodes = 0, iters = 0; unsigned long long next_uid = 2;
-  Cmp cmp; cmp.have_inc = false;
+  Cmp cmp; cmp.have_inc = false; cmp.round = 0; { const char *ep = std::getenv("EMU_POLICY"); cmp.policy = ep ? std::atoi(ep) : 1; }
+  const char *ekd = std::getenv("EMU_KDIVE"); const int Kdive = ekd ? std::atoi(ekd) : 0;
   const auto t0 = std::chrono::steady_clock::now();
   bool timed_out = false;
-  while (!open.empty()) {
+  const char *ek = std::getenv("EMU_K");
+  const int K = ek ? std::atoi(ek) : 1;   // nodes taken per round with one cutoff snapshot (as the device does)
+  long rounds = 0;
+  std::vector<Node> batch;
+  while (!open.empty() || !batch.empty()) {
     if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > time_limit || (max_nodes > 0 && nodes >= max_nodes)) { timed_out = true; break; }
-    size_t bi = 0;
-    for (size_t a = 1; a < open.size(); ++a) if (cmp.before(open[a], open[bi])) bi = a;
-    Node nd = open[bi]; open[bi] = open.back(); open.pop_back();
-    const double cutoff = (ub < HUGE_VAL) ? ub - gap_tol * fabs(ub) : HUGE_VAL;
+    static double cutoff_round = HUGE_VAL;
+    if (batch.empty()) {
+      ++rounds;
+      cutoff_round = (ub < HUGE_VAL) ? ub - gap_tol * fabs(ub) : HUGE_VAL;
+      cmp.round = rounds;
+      Cmp snap = cmp;
+      const int Kr = (!cmp.have_inc && Kdive > 0) ? Kdive : K;
+      for (int t = 0; t < Kr && !open.empty(); ++t) {
+        size_t bi = 0;
+        for (size_t a = 1; a < open.size(); ++a) if (snap.before(open[a], open[bi])) bi = a;
+        batch.push_back(open[bi]); open[bi] = open.back(); open.pop_back();
+      }
+    }
+    Node nd = batch.back(); batch.pop_back();
+    const double cutoff = cutoff_round;
     if (nd.bound >= cutoff) { pruned_lb = std::min(pruned_lb, nd.bound); continue; }
     ++nodes;
     memcpy(k.dec, nd.dec.data(), nds);
@@ -84,7 +109,7 @@ extern "C" int emu_multi_solve(const MiqpB200Problem *q, double gap_tol, double 
     }
     const unsigned char *src = out.from_imp ? k.imp : k.dec;
     for (int a = 0; a < out.nalt; ++a) {
-      Node ch; ch.bound = out.obj; ch.depth = nd.depth + 1; ch.rank = a; ch.uid = next_uid++;
+      Node ch; ch.bound = out.obj; ch.depth = nd.depth + 1; ch.rank = a; ch.uid = next_uid++; ch.birth = rounds;
       ch.dec.assign(src, src + nds);
       if (out.soff >= 0) { ch.dec[out.soff] = sh.alts[a]; if (sh.alts[a] == k.imp[out.soff]) ch.rank = -1; }
       else ch.rank = 0;
@@ -96,6 +121,7 @@ extern "C" int emu_multi_solve(const MiqpB200Problem *q, double gap_tol, double 
   if (!timed_out && open.empty() && lb == HUGE_VAL) lb = ub;
   if (ub < HUGE_VAL && lb > ub) lb = ub;
   *obj_out = ub; *bound_out = lb; *nodes_out = nodes; *iters_out = iters;
+  if (verbose) fprintf(stderr, "emu rounds %ld nodes %ld\n", rounds, nodes);
   if (!(ub < HUGE_VAL)) return timed_out ? 3 : 1;
   return 0;
 }
