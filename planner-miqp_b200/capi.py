@@ -199,6 +199,14 @@ def to_c(p, gap_tol=None, time_limit=None, keep=None) -> CProblem:
     return s
 
 
+def ncols_of(p) -> int:
+    """number of columns of the OPL model (decision_variables.mod), closed form of miqp_b200_layout"""
+    C_, N, R, O, L, E = p.C, p.N, p.R, p.O, p.L, p.E
+    K = C_ - 1
+    return (12 * C_ * N + 5 * C_ * E * N + C_ * N * R + 5 * C_ * N + C_ * O * N * L + 4 * C_ * O * N * L
+            + C_ * O * N + 4 * C_ * O * N + 16 * K * K * N + 4 * K * K * N)
+
+
 def layout(p) -> CLayout:
     keep = []
     cp = to_c(p, keep=keep)
@@ -288,8 +296,24 @@ class Solver:
                     a, ptr = _d(w)
                     keep.append(a)
                     warm_arr[k] = ptr
-        ncols = [layout(p).ncols for p in problems]
+        ncols = [ncols_of(p) for p in problems]
         return arr, warm_arr, ncols, keep
+
+    def prepare(self, problems, gap_tol=None, time_limit=None, warm=None):
+        """Builds the C structs and the output buffers of a batch once (host memory); the result can be
+        passed to solve_prepared() repeatedly.  What a C/C++ caller of the ABI holds anyway."""
+        n = len(problems)
+        arr, warm_arr, ncols, keep = self._pack(problems, gap_tol, time_limit, warm)
+        xs = [np.zeros(c) for c in ncols]
+        xptr = (_dp * n)(*[x.ctypes.data_as(_dp) for x in xs])
+        infos = (CSolveInfo * n)()
+        return dict(n=n, arr=arr, warm=warm_arr, xs=xs, xptr=xptr, infos=infos, keep=keep)
+
+    def solve_prepared(self, b):
+        """One miqp_b200_solve_batch call on host buffers: pack + H2D + device solve + D2H."""
+        self._check(self._lib.miqp_b200_solve_batch(self._h, b["arr"], b["n"], b["warm"], b["xptr"], b["infos"]),
+                    "miqp_b200_solve_batch")
+        return b["xs"], b["infos"]
 
     def solve_batch(self, problems, gap_tol=None, time_limit=None, warm=None):
         """Host buffers in, host buffers out (H2D + solve + D2H).  Returns (xs, infos)."""

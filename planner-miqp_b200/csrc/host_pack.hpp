@@ -4,6 +4,7 @@
 // (src/cplex_wrapper.cpp:494-639).  Pure C++; used by the host driver (solver.cu).
 #pragma once
 #include <algorithm>
+#include <new>
 #include <cmath>
 #include <cstring>
 #include <string>
@@ -15,20 +16,44 @@
 namespace miqp {
 namespace hostpack {
 
+// Staging memory of the blobs: page-locked when the CUDA runtime is linked (solver.cu defines
+// MIQP_PINNED_BLOBS), so that the H2D / D2H copies of a batch are real asynchronous DMA.
+#ifdef MIQP_PINNED_BLOBS
+template <class T>
+struct PinnedAllocator {
+  using value_type = T;
+  PinnedAllocator() = default;
+  template <class U> PinnedAllocator(const PinnedAllocator<U> &) {}
+  T *allocate(size_t n) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, n * sizeof(T), cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); throw std::bad_alloc(); }
+    return static_cast<T *>(p);
+  }
+  void deallocate(T *p, size_t) { cudaFreeHost(p); }
+  template <class U> bool operator==(const PinnedAllocator<U> &) const { return true; }
+  template <class U> bool operator!=(const PinnedAllocator<U> &) const { return false; }
+};
+using DVec = std::vector<double, PinnedAllocator<double>>;
+using IVec = std::vector<int, PinnedAllocator<int>>;
+#else
+using DVec = std::vector<double>;
+using IVec = std::vector<int>;
+#endif
+
 struct Packed {
   std::vector<DevProb> probs;
-  std::vector<double> dblob;
-  std::vector<int> iblob;
+  DVec dblob;
+  IVec iblob;
   long total_rows = 0, total_nnz = 0, total_cols = 0, max_rows = 0;
   int maxN = 0, max_ndec = 0, max_kmax = 0, max_z = 0, maxC = 0;
 };
 
-inline long push_d(std::vector<double> &b, const double *src, size_t n) {
+inline long push_d(DVec &b, const double *src, size_t n) {
   long off = (long)b.size();
   if (src) b.insert(b.end(), src, src + n); else b.resize(b.size() + n, 0.0);
   return off;
 }
-inline long push_i(std::vector<int> &b, const int *src, size_t n) {
+inline long push_i(IVec &b, const int *src, size_t n) {
   long off = (long)b.size();
   if (src) b.insert(b.end(), src, src + n); else b.resize(b.size() + n, 0);
   return off;

@@ -21,6 +21,7 @@
 
 #include "../../include/miqp_b200.h"
 #include "kernels.cuh"
+#define MIQP_PINNED_BLOBS 1
 #include "host_pack.hpp"
 
 using namespace miqp;
@@ -91,7 +92,8 @@ struct MiqpB200Solver {
   double last_seconds = 0.0;
   bool timed_out = false;
   MiqpB200RunStats stats;
-  std::vector<double> h_x, h_viol, h_obj, h_bb, h_ub;
+  DVec h_x;   // page-locked: D2H target of the solution vectors
+  std::vector<double> h_viol, h_obj, h_bb, h_ub;
   std::vector<unsigned long long> h_stats;
   std::vector<int> h_done;
   int single_maxN = 2;
@@ -119,7 +121,9 @@ void upload_packed(MiqpB200Solver *s) {
 }
 
 void pack_batch(MiqpB200Solver *s, const MiqpB200Problem *problems, int count) {
-  s->pk = Packed();
+  s->pk.probs.clear(); s->pk.dblob.clear(); s->pk.iblob.clear();   // keeps the page-locked capacity of the last batch
+  s->pk.total_rows = s->pk.total_nnz = s->pk.total_cols = s->pk.max_rows = 0;
+  s->pk.maxN = s->pk.max_ndec = s->pk.max_kmax = s->pk.max_z = s->pk.maxC = 0;
   s->time_limits.clear();
   for (int k = 0; k < count; ++k) {
     std::string v = validate(problems[k]);
