@@ -221,7 +221,9 @@ inline void pack_one(const MiqpB200Problem &q, Packed &pk) {
   pk.probs.push_back(p);
 }
 
-// decisions of a full column vector (MIP start / warm start)
+// decisions of a full column vector (MIP start / warm start).  A NaN in the first binary of a
+// family at (car, step) leaves that disjunction undecided (partial MIP start: the node is then
+// completed by the least violated alternatives, see scan_node).
 inline void decisions_from_solution(const MiqpB200Problem &q, const DevProb &p, const std::vector<int> &alts_all,
                              const double *x, unsigned char *dec) {
   const int C = p.C, N = p.N, R = p.R, E = p.E, O = p.O, L = p.L, K = p.K;
@@ -232,7 +234,7 @@ inline void decisions_from_solution(const MiqpB200Problem &q, const DevProb &p, 
     for (int i = 0; i < N; ++i) {
       int j = 0;
       for (int jj = 0; jj < R; ++jj) if (x[col_ar(p, c, i, jj)] > 0.5) j = jj;
-      if (i > 0) {
+      if (i > 0 && !std::isnan(x[col_ar(p, c, i, 0)])) {
         const double rho = x[col_rcna(p, 4, c, i)];
         if (rho > 0.5) dec[p.off_mode + c * N + i] = MODE_FROZEN;
         else {
@@ -246,18 +248,20 @@ inline void decisions_from_solution(const MiqpB200Problem &q, const DevProb &p, 
         }
       }
       for (int pt = 0; pt < 5; ++pt) {
-        if (E > 1) {
+        if (E > 1 && !std::isnan(x[col_nwe(p, pt, c, 0, i)])) {
           int e = 0;
           for (int ee = 0; ee < E; ++ee) if (x[col_nwe(p, pt, c, ee, i)] < 0.5) { e = ee; break; }
           dec[p.off_env + (c * N + i) * 5 + pt] = (unsigned char)e;
         }
         for (int o = 0; o < O; ++o) {
           const int ne = q.obs_nedges[o * N + i];
+          if (ne > 0 && std::isnan((pt == 0) ? x[col_dcc(p, c, o, i, 0)] : x[col_dcf(p, c, o, i, 0, 4 - pt)])) continue;
           int dd = OBS_SOFT;
           for (int ed = 0; ed < ne; ++ed) {
             const double v = (pt == 0) ? x[col_dcc(p, c, o, i, ed)] : x[col_dcf(p, c, o, i, ed, 4 - pt)];
             if (v < 0.5) { dd = ed; break; }
           }
+          if (dd == OBS_SOFT && q.obs_soft[o] != 1) continue;   // no separating edge marked on a hard obstacle: undecided
           dec[p.off_obs + ((c * O + o) * N + i) * 5 + pt] = (unsigned char)dd;
         }
       }
@@ -268,13 +272,13 @@ inline void decisions_from_solution(const MiqpB200Problem &q, const DevProb &p, 
     for (int b = a + 1; b < C; ++b, ++pr)
       for (int i = 0; i < N; ++i)
         for (int qd = 0; qd < 4; ++qd) {
+          if (std::isnan(x[col_c2c(p, a, b - 1, i, qd * 4)])) continue;
           int dd = 0;
           for (int side = 0; side < 4; ++side) if (x[col_c2c(p, a, b - 1, i, qd * 4 + side)] < 0.5) { dd = side; break; }
           dec[p.off_pair + (pr * N + i) * 4 + qd] = (unsigned char)dd;
         }
   (void)alts_all; (void)L; (void)K;
 }
-
 
 }  // namespace hostpack
 }  // namespace miqp

@@ -118,3 +118,20 @@ def random_scenario(seed: int, nr_regions=16, nr_steps=20, max_agents=4):
         side = 1.0 if rng.uniform() < 0.5 else -1.0
         b.add_box_obstacle([[20.0 + rng.uniform(0, 15), side * rng.uniform(1.2, 2.0), 0.0]], 1.0, 1.0)
     return b
+
+
+def advance_obstacle_scenario(builder: PlanBuilder, plan, x) -> PlanBuilder:
+    """Next planning cycle of a config-2 scenario (receding horizon): the car state becomes step 1 of
+    the solution x, every obstacle prediction moves one step ahead (the last pose is extrapolated
+    with the last displacement), reference and environment stay."""
+    from .results import block_views
+    v = block_views(plan, x)
+    nb = PlanBuilder(builder.s)
+    for c, car in enumerate(builder.cars):
+        st = [v["pos_x"][c, 1], v["vel_x"][c, 1], v["acc_x"][c, 1], v["pos_y"][c, 1], v["vel_y"][c, 1], v["acc_y"][c, 1]]
+        nb.add_car(st, car["ref"], car["v_des"], car["ds"], car["track"])
+    nb.envs = [e.copy() for e in builder.envs]
+    for polys, soft in builder.obstacles:
+        last = polys[-1] + (polys[-1] - polys[-2]) if len(polys) > 1 else polys[-1]
+        nb.obstacles.append((list(polys[1:]) + [last], soft))
+    return nb

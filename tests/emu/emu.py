@@ -38,7 +38,7 @@ def lib():
     return _lib
 
 
-def solve(p, gap_tol=1e-4, time_limit=60.0, max_nodes=0, verbose=0):
+def solve(p, gap_tol=1e-4, time_limit=60.0, max_nodes=0, verbose=0, warm=None):
     import planner_miqp_b200 as P
     from planner_miqp_b200 import capi
     keep = []
@@ -57,5 +57,6 @@ def solve(p, gap_tol=1e-4, time_limit=60.0, max_nodes=0, verbose=0):
     f.restype = C.c_int
     rc = f(C.byref(cp), C.c_double(gap_tol), C.c_double(time_limit), C.c_long(max_nodes), C.byref(obj), C.byref(bnd),
            C.byref(nodes), C.byref(iters), traj.ctypes.data_as(C.c_void_p), sig.ctypes.data_as(C.c_void_p),
-           dec.ctypes.data_as(C.c_void_p), C.c_int(verbose))
+           dec.ctypes.data_as(C.c_void_p), C.c_int(verbose),
+           None if warm is None else np.ascontiguousarray(warm, dtype=np.float64).ctypes.data_as(C.c_void_p))
     return dict(status=rc, objective=obj.value, bound=bnd.value, nodes=nodes.value, iters=iters.value, traj=traj, sig=sig, dec=dec)

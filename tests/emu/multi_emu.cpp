@@ -43,7 +43,7 @@ struct Cmp {
 extern "C" int emu_multi_solve(const MiqpB200Problem *q, double gap_tol, double time_limit, long max_nodes,
                                double *obj_out, double *bound_out, long *nodes_out, long *iters_out,
                                double *traj_out /* [C][N][8] */, double *sig_out /* [P][N][4] */,
-                               unsigned char *dec_out /* [ndec_pad] */, int verbose) {
+                               unsigned char *dec_out /* [ndec_pad] */, int verbose, const double *warm /* full column vector or null */) {
   Packed pk;
   std::string v = validate(*q);
   if (!v.empty()) { fprintf(stderr, "emu: %s\n", v.c_str()); return -2; }
@@ -60,8 +60,13 @@ extern "C" int emu_multi_solve(const MiqpB200Problem *q, double gap_tol, double 
   MShared sh;
 
   std::vector<Node> open;
-  Node root; root.bound = -HUGE_VAL; root.depth = 0; root.rank = 0; root.uid = 1; root.birth = -5; root.dec.assign(nds, UNDEC);
+  Node root; root.bound = -HUGE_VAL; root.depth = 0; root.rank = 0; root.uid = 1; root.birth = 0; root.dec.assign(nds, UNDEC);
   open.push_back(root);
+  if (warm) {  // MIP start: (partially) decided node, evaluated first
+    Node wn; wn.bound = -HUGE_VAL; wn.depth = 1 << 20; wn.rank = -1; wn.uid = 0; wn.birth = 0; wn.dec.assign(nds, UNDEC);
+    std::vector<int> dummy; decisions_from_solution(*q, p, dummy, warm, wn.dec.data());
+    open.push_back(wn);
+  }
   double ub = HUGE_VAL, pruned_lb = HUGE_VAL;
   long nodes = 0, iters = 0; unsigned long long next_uid = 2;
   Cmp cmp; cmp.have_inc = false; cmp.round = 0; { const char *ep = std::getenv("EMU_POLICY"); cmp.policy = ep ? std::atoi(ep) : 1; }
