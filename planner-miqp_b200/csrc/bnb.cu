@@ -399,6 +399,72 @@ __device__ __forceinline__ int scan_node(const WarpCtx &w, Branch &br) {
 }
 
 // ---------------------------------------------------------------------------------------
+// lower bound of a child before it is solved (derivation: bnb_multi_core.cuh, tables:
+// formulation_tables.cuh): the parent's optimum z* violates a row g.z <= h of the child's
+// alternative by v > 0, hence every point of the child costs at least
+// f(z*) + 1/2 v^2 / (g' W_i g).  Children whose bound reaches the cutoff are never created.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double quad_w(const WarpCtx &w, int i, const double a[6]) {
+  const double *t = w.D + w.p->o_wtab + 14 * i;
+  double g = 0.0;
+#pragma unroll
+  for (int ax = 0; ax < 2; ++ax) {
+    const double *m = t + 7 * ax; const double *v = a + 3 * ax;
+    g += m[0] * v[0] * v[0] + 2.0 * m[1] * v[1] * v[0] + m[2] * v[1] * v[1] + 2.0 * m[3] * v[2] * v[0] + 2.0 * m[4] * v[2] * v[1] + m[5] * v[2] * v[2];
+  }
+  return g;
+}
+__device__ __forceinline__ double delta_of(double viol, double G) {
+  if (!(viol > 1e-7) || !(G > 1e-14)) return 0.0;
+  return 0.5 * viol * viol / G;
+}
+__device__ __forceinline__ double bound_delta(const WarpCtx &w, int i, int T, double viol) {
+  const double *t = w.D + w.p->o_wtab + 14 * i;
+  double G;
+  if (T < 6) { const int o = T % 3; G = t[7 * (T / 3) + (o == 0 ? 0 : o == 1 ? 2 : 5)]; }
+  else G = t[7 * (T - 6) + 6];
+  return delta_of(viol, G);
+}
+__device__ __forceinline__ double alt_delta(const WarpCtx &w, const Branch &br, int alt) {
+  const DevProb &p = *w.p;
+  const int N = w.N, i = br.i;
+  const int *rdec = w.aux + N;
+  double y[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) y[t] = w.V[i * V_STRIDE + V_Z + t];
+  double dl = 0.0, a[6], rhs;
+  if (br.kind == 1) {
+    const bool frozen = (alt == MODE_FROZEN);
+    const int j = frozen ? ((i - 1 == 0 || rdec[i - 1]) ? w.jeff[i - 1] : -1) : (alt >> 2);
+    double lo[8], hi[8];
+    stage_bounds(w, i, j, frozen, lo, hi);
+#pragma unroll
+    for (int t = 1; t < 8; ++t) {
+      if (t == Y_PY) continue;
+      if (t >= 6 && i == N - 1) continue;
+      dl = fmax(dl, bound_delta(w, i, t, y[t] - hi[t]));
+      dl = fmax(dl, bound_delta(w, i, t, lo[t] - y[t]));
+    }
+    if (!frozen) {
+#pragma unroll 1
+      for (int k = 0; k < 5; ++k) { mode_row(w, alt >> 2, alt & 3, k, a, rhs); dl = fmax(dl, delta_of(dot6(a, y) - rhs, quad_w(w, i, a))); }
+    }
+  } else if (br.kind == 2) {
+    const double *ft = w.D + p.o_fronttab + 12 * (w.jeff[i] >= 0 ? w.jeff[i] : 0);
+    for (int ed = w.I[p.o_env_off + alt]; ed < w.I[p.o_env_off + alt + 1]; ++ed) {
+      edge_row(w.D + p.o_envtab + 3 * ed, ft, br.pt, -1.0, a, rhs);
+      dl = fmax(dl, delta_of(dot6(a, y) - rhs, quad_w(w, i, a)));
+    }
+  } else if (br.kind == 3) {
+    if (alt == OBS_SOFT) return p.w_slack_obs;
+    const double *ft = w.D + p.o_fronttab + 12 * (w.jeff[i] >= 0 ? w.jeff[i] : 0);
+    edge_row(w.D + p.o_obstab + 3 * ((br.o * N + i) * p.L + alt), ft, br.pt, 1.0, a, rhs);
+    dl = delta_of(dot6(a, y) - rhs, quad_w(w, i, a));
+  }
+  return dl;
+}
+
+// ---------------------------------------------------------------------------------------
 // node kernel
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void copy_bytes16(unsigned char *dst, const unsigned char *src, int nbytes, int lane) {
@@ -544,6 +610,25 @@ __global__ void __launch_bounds__(128) bnb_nodes_kernel(BnbState st, const DevPr
       if (w.I[p.o_obs_soft + br.o] == 1) { if (lane == 0) alts[ne] = OBS_SOFT; nalt = ne + 1; }
     }
     __syncwarp();
+    // child bounds (lane = alternative); the (s, lambda) records are dead after the QP solve and
+    // serve as scratch.  Children that reach the cutoff are dropped.
+    double *cb = reinterpret_cast<double *>(w.rows);
+    if (br.kind == 0) { if (lane == 0) cb[0] = obj; }
+    else for (int a = lane; a < nalt; a += 32) cb[a] = fmax(obj, r.obj + pen + 0.999 * alt_delta(w, br, alts[a]));
+    __syncwarp();
+    {
+      int nk = 0; double pm = MQ_INF;
+      if (lane == 0) {
+        for (int a = 0; a < nalt; ++a) {
+          if (cb[a] >= cutoff) { pm = fmin(pm, cb[a]); continue; }
+          alts[nk] = alts[a]; cb[nk] = cb[a]; ++nk;
+        }
+        if (pm < MQ_INF) atomic_min_double(&st.pruned_lb[s], pm);
+      }
+      nalt = __shfl_sync(FULL, nk, 0);
+    }
+    __syncwarp();
+    if (nalt == 0) continue;
     int fbase = 0, opos = 0, ok = 1;
     if (lane == 0) {
       const int old = atomicSub(&st.free_cnt[s], nalt);
@@ -560,7 +645,7 @@ __global__ void __launch_bounds__(128) bnb_nodes_kernel(BnbState st, const DevPr
       if (lane == 0) {
         int rank = 0;
         if (soff >= 0) { dst[soff] = alts[a]; rank = (alts[a] == w.imp[soff]) ? -1 : a; }
-        st.bound[pb + cs] = obj;
+        st.bound[pb + cs] = cb[a];
         st.meta[pb + cs] = make_int2(nmeta.x >= (1 << 20) ? nmeta.x : nmeta.x + 1, (round << 8) | (rank + 1));
         st.uid[pb + cs] = mix64(nuid * 0x9e3779b97f4a7c15ULL + (unsigned long long)(a + 1));
         st.open_idx[pb + opos + a] = cs;

@@ -91,8 +91,10 @@ __global__ void __launch_bounds__(MULTI_MAX_THREADS) bnb_nodes_multi_kernel(BnbS
       __syncthreads();
       continue;
     }
-    // children
+    // children (those whose lower bound reaches the cutoff were dropped by m_process_node)
+    if (tid == 0 && out.pruned_min < MQM_INF) atomic_min_double(&st.pruned_lb[s], out.pruned_min);
     const int nalt = out.nalt;
+    if (nalt == 0) continue;
     if (tid == 0) {
       const int old = atomicSub(&st.free_cnt[s], nalt);
       if (old < nalt) { atomicAdd(&st.free_cnt[s], nalt); atomicExch(st.err, 1); s_i[1] = 0; }
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(MULTI_MAX_THREADS) bnb_nodes_multi_kernel(BnbS
         if (tid == 0) {
           int rank = 0;
           if (out.soff >= 0) { dst[out.soff] = sh.alts[a]; rank = (sh.alts[a] == k.imp[out.soff]) ? -1 : a; }
-          st.bound[pb + cs] = out.obj;
+          st.bound[pb + cs] = sh.cb[a];
           st.meta[pb + cs] = make_int2(nmeta.x >= (1 << 20) ? nmeta.x : nmeta.x + 1, (round << 8) | (rank + 1));
           st.uid[pb + cs] = mix64(nuid * 0x9e3779b97f4a7c15ULL + (unsigned long long)(a + 1));
           st.open_idx[pb + opos + a] = cs;

@@ -210,18 +210,102 @@ MQ_FN int m_scan_node(const MCtx &k, MBranch &br, MBranch *bsh, int ndec_pad) {
   return und;
 }
 
+// ---------------------------------------------------------------------------------------
+// lower bound of a child before it is solved: the parent's optimum z* violates row g.z <= h of the
+// child's alternative by v > 0; every point of the child then costs at least
+//     f(z*) + 1/2 v^2 / (g' W_i g)          (W_i: reach table of formulation_tables.cuh)
+// because f(z) >= f(z*) + 1/2 d'Qd for every z = z* + d of the parent's feasible set (z* optimal,
+// f quadratic) and d has to move by v against g at step i.  The largest such term over the rows of
+// the alternative is added to the parent's objective; children whose bound reaches the cutoff are
+// never created.
+// ---------------------------------------------------------------------------------------
+MQ_FN double m_quad_w(const MCtx &k, int c, int i, const double a[6]) {
+  const double *t = k.D + k.p->o_wtab + 14 * (c * k.N + i);
+  double g = 0.0;
+  for (int ax = 0; ax < 2; ++ax) {
+    const double *w = t + 7 * ax; const double *v = a + 3 * ax;
+    g += w[0] * v[0] * v[0] + 2.0 * w[1] * v[1] * v[0] + w[2] * v[1] * v[1] + 2.0 * w[3] * v[2] * v[0] + 2.0 * w[4] * v[2] * v[1] + w[5] * v[2] * v[2];
+  }
+  return g;
+}
+MQ_FN double m_delta(double viol, double G) {
+  if (!(viol > 1e-7) || !(G > 1e-14)) return 0.0;
+  return 0.5 * viol * viol / G;
+}
+MQ_FN double m_bound_delta(const MCtx &k, int c, int i, int T, double viol) {
+  const double *t = k.D + k.p->o_wtab + 14 * (c * k.N + i);
+  double G;
+  if (T < 6) { const int o = T % 3; G = t[7 * (T / 3) + (o == 0 ? 0 : o == 1 ? 2 : 5)]; }
+  else G = t[7 * (T - 6) + 6];
+  return m_delta(viol, G);
+}
+
+// increase of the lower bound for alternative `alt` of the branching disjunction br (>= 0)
+MQ_FN double m_alt_delta(const MCtx &k, const MBranch &br, int alt) {
+  const DevProb &p = *k.p;
+  const int N = k.N, C = k.C;
+  const int *rdec = k.aux + C * N;
+  double dl = 0.0;
+  if (br.kind == 1) {
+    const int c = br.c, i = br.i;
+    const double *y = k.Z + (long)i * k.nz + 8 * c;
+    const bool frozen = (alt == MODE_FROZEN);
+    const int j = frozen ? (rdec[c * N + i - 1] ? k.jeff[c * N + i - 1] : -1) : (alt >> 2);
+    double lo[8], hi[8];
+    m_stage_bounds(k, c, i, j, frozen, lo, hi);
+    for (int t = 1; t < 8; ++t) {
+      if (t == Y_PY) continue;
+      if (t >= 6 && i == N - 1) continue;
+      dl = fmax(dl, m_bound_delta(k, c, i, t, y[t] - hi[t]));
+      dl = fmax(dl, m_bound_delta(k, c, i, t, lo[t] - y[t]));
+    }
+    if (!frozen) {
+      double a[6], rhs;
+      for (int r = 0; r < 5; ++r) { m_mode_row(k, alt >> 2, alt & 3, r, a, rhs); dl = fmax(dl, m_delta(dot6m(a, y) - rhs, m_quad_w(k, c, i, a))); }
+    }
+  } else if (br.kind == 2) {
+    const int c = br.c, i = br.i;
+    const double *y = k.Z + (long)i * k.nz + 8 * c;
+    const double *ft = k.D + p.o_fronttab + 12 * (c * p.R + (k.jeff[c * N + i] >= 0 ? k.jeff[c * N + i] : 0));
+    double a[6], rhs;
+    for (int ed = k.I[p.o_env_off + alt]; ed < k.I[p.o_env_off + alt + 1]; ++ed) {
+      m_edge_row(k.D + p.o_envtab + 3 * ed, ft, br.pt, -1.0, a, rhs);
+      dl = fmax(dl, m_delta(dot6m(a, y) - rhs, m_quad_w(k, c, i, a)));
+    }
+  } else if (br.kind == 3) {
+    if (alt == OBS_SOFT) return p.w_slack_obs;
+    const int c = br.c, i = br.i;
+    const double *y = k.Z + (long)i * k.nz + 8 * c;
+    const double *ft = k.D + p.o_fronttab + 12 * (c * p.R + (k.jeff[c * N + i] >= 0 ? k.jeff[c * N + i] : 0));
+    double a[6], rhs;
+    m_edge_row(k.D + p.o_obstab + 3 * ((br.o * N + i) * p.L + alt), ft, br.pt, 1.0, a, rhs);
+    dl = m_delta(dot6m(a, y) - rhs, m_quad_w(k, c, i, a));
+  } else if (br.kind == 4) {
+    int a = 0, rem = br.pr;
+    while (rem >= C - 1 - a) { rem -= C - 1 - a; ++a; }
+    const int b = a + 1 + rem, i = br.i;
+    PairRow r; m_pair_row(k, a, b, i, br.q, alt, k.jeff[a * N + i], k.jeff[b * N + i], r);
+    const double *ya = k.Z + (long)i * k.nz + 8 * a, *yb = k.Z + (long)i * k.nz + 8 * b;
+    double G = m_quad_w(k, a, i, r.ca) + m_quad_w(k, b, i, r.cb);
+    if (r.slack >= 0 && m_slack_cap(k, i) > 1e-12 && p.w_slack > 0.0) G += 1.0 / (2.0 * p.w_slack);
+    dl = m_delta(dot6m(r.ca, ya) + dot6m(r.cb, yb) - r.rhs, G);
+  }
+  return dl;
+}
+
 // outcome of one node
 enum { MN_INFEASIBLE = 0, MN_PRUNED, MN_INCUMBENT, MN_BRANCH };
-struct MNodeOut { int what, iters, nalt, soff; long rows; double obj; bool from_imp; };
+struct MNodeOut { int what, iters, nalt, soff; long rows; double obj, pruned_min; bool from_imp; };
 
 // Shared scratch of the node processing that is not part of the QP workspace
-struct MShared { MBranch br; unsigned char alts[260]; };
+struct MShared { MBranch br; int nkeep; double pruned_min; unsigned char alts[260]; double cb[260]; };
 
 // k.dec holds the node; returns what to do with it.  For MN_BRANCH the children are
 // copies of (from_imp ? k.imp : k.dec) with byte soff (if >= 0) set to sh->alts[0..nalt).
 MQ_FN MNodeOut m_process_node(const MCtx &k, MShared *sh, double nbound, double cutoff, int ndec_pad) {
   const DevProb &p = *k.p;
   MNodeOut out; out.what = MN_INFEASIBLE; out.iters = 0; out.nalt = 0; out.soff = -1; out.rows = 0; out.obj = 0.0; out.from_imp = false;
+  out.pruned_min = MQM_INF;
   m_effective_regions(k);
   int nsoft = 0;
   PFOR(e, 5 * k.C * p.O * k.N) nsoft += (k.dec[p.off_obs + e] == OBS_SOFT);
@@ -238,7 +322,7 @@ MQ_FN MNodeOut m_process_node(const MCtx &k, MShared *sh, double nbound, double 
   const int und = m_scan_node(k, br, &sh->br, ndec_pad);
   if (br.kind == 0 && und == 0) { out.what = MN_INCUMBENT; return out; }
   out.what = MN_BRANCH;
-  if (br.kind == 0) { out.nalt = 1; out.from_imp = true; out.soff = -1; return out; }
+  if (br.kind == 0) { out.nalt = 1; out.from_imp = true; out.soff = -1; if (k.tid == 0) sh->cb[0] = obj; k.sync(); return out; }
   if (br.kind == 1) {
     out.soff = p.off_mode + br.c * k.N + br.i;
     const int na = k.I[p.o_nalt + br.c];
@@ -259,6 +343,20 @@ MQ_FN MNodeOut m_process_node(const MCtx &k, MShared *sh, double nbound, double 
     out.nalt = 4;
     if (k.tid == 0) for (int e = 0; e < 4; ++e) sh->alts[e] = (unsigned char)e;
   }
+  k.sync();
+  // child bounds; children that reach the cutoff are dropped here
+  PFOR(a, out.nalt) sh->cb[a] = fmax(obj, r.obj + pen + 0.999 * m_alt_delta(k, br, sh->alts[a]));
+  k.sync();
+  if (k.tid == 0) {
+    int n = 0; double pm = MQM_INF;
+    for (int a = 0; a < out.nalt; ++a) {
+      if (sh->cb[a] >= cutoff) { pm = fmin(pm, sh->cb[a]); continue; }
+      sh->alts[n] = sh->alts[a]; sh->cb[n] = sh->cb[a]; ++n;
+    }
+    sh->nkeep = n; sh->pruned_min = pm;
+  }
+  k.sync();
+  out.nalt = sh->nkeep; out.pruned_min = sh->pruned_min;
   k.sync();
   return out;
 }

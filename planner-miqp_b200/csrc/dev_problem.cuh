@@ -75,6 +75,7 @@ struct DevProb {
   long o_modetab;         // [R][4][5]  wedge1, wedge2, kappa_max, kappa_min rows: a_vx,a_ax,a_vy,a_ay,rhs (normalised)
   long o_fronttab;        // [C][R][12] wb*poly: fxu[3], fxl[3], fyu[3], fyl[3]
   long o_cost;            // [C][N][16] diag q[8] (=2w) and linear c[8] (=-2w ref) per stage
+  long o_wtab;            // [C][N][14] reach of the cost-only LQ problem: Wx (3x3 packed), Wy, var(ux), var(uy)
   double cost_const;      // sum w ref^2 (filled by prepare_tables)
 
   // ---- offsets into the int blob ----

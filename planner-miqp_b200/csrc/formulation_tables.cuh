@@ -72,6 +72,58 @@ __host__ __device__ inline void prepare_tables_parallel(DevProb &p, double *D, i
       t[8 + a] = -2.0 * w * ref[a];
     }
   }
+  // Reach tables of the cost-only LQ problem, per car and axis (triple integrator, weights
+  // q = 2w on (p, v, a), r = 2 w_jerk): W_i = covariance of the state at step i under the Gaussian
+  // exp(-J), J = 1/2 sum (x'Qx + r u^2).  For any direction g at step i
+  //     min { 1/2 d'Q d : d dynamics-consistent, g.d_i <= -v } = 1/2 v^2 / (g' W_i g),
+  // the objective increase every trajectory pays for moving by v against g at step i; the branch
+  // and bound uses it as a lower bound of a child before the child is solved (bnb.cu).
+  // Backward Riccati of the cost (P_{N-1} = Q; F_k = r + B'P_{k+1}B; K_k = B'P_{k+1}A / F_k),
+  // then forward W_{k+1} = (A - B K_k) W_k (A - B K_k)' + B B' / F_k, W_0 = 0.
+  for (int q = tid; q < 2 * C; q += nt) {
+    const int c = q / 2, ax = q % 2;
+    const double ts = p.ts, c2 = p.c2, c3 = p.c3;
+    const double Q[3] = {2.0 * D[p.o_w[3 * ax] + c], 2.0 * D[p.o_w[3 * ax + 1] + c], 2.0 * D[p.o_w[3 * ax + 2] + c]};
+    const double r = 2.0 * D[p.o_w[6 + ax] + c] + 1e-10;
+    const double A[3][3] = {{1.0, ts, c2}, {0.0, 1.0, ts}, {0.0, 0.0, 1.0}};
+    const double B[3] = {c3, c2, ts};
+    double P[3][3] = {{Q[0], 0, 0}, {0, Q[1], 0}, {0, 0, Q[2]}};
+    // the gains are parked in the table slots of their stage: K_k (3) and 1/F_k at offsets 0..3
+    for (int k = N - 2; k >= 0; --k) {
+      double PB[3], PA[3][3];
+      for (int a = 0; a < 3; ++a) { PB[a] = 0.0; for (int b = 0; b < 3; ++b) PB[a] += P[a][b] * B[b]; }
+      for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) { PA[a][b] = 0.0; for (int e = 0; e < 3; ++e) PA[a][b] += P[a][e] * A[e][b]; }
+      double F = r; for (int a = 0; a < 3; ++a) F += B[a] * PB[a];
+      double K[3]; for (int b = 0; b < 3; ++b) { K[b] = 0.0; for (int a = 0; a < 3; ++a) K[b] += B[a] * PA[a][b]; K[b] /= F; }
+      double Pn[3][3];
+      for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) {
+        double v = (a == b ? Q[a] : 0.0);
+        for (int e = 0; e < 3; ++e) v += A[e][a] * PA[e][b];
+        Pn[a][b] = v - K[a] * F * K[b];
+      }
+      for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) P[a][b] = 0.5 * (Pn[a][b] + Pn[b][a]);
+      double *t = D + p.o_wtab + 14 * (c * N + k) + 7 * ax;
+      t[0] = K[0]; t[1] = K[1]; t[2] = K[2]; t[3] = 1.0 / F;
+    }
+    double W[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int k = 0; k < N; ++k) {
+      double *t = D + p.o_wtab + 14 * (c * N + k) + 7 * ax;
+      double K[3] = {0, 0, 0}, iF = 0.0;
+      if (k < N - 1) { K[0] = t[0]; K[1] = t[1]; K[2] = t[2]; iF = t[3]; }
+      // table of stage k: W_k packed lower (00,10,11,20,21,22) and var(u_k) = K W K' + 1/F
+      double vu = iF;
+      for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) vu += K[a] * W[a][b] * K[b];
+      t[0] = W[0][0]; t[1] = W[1][0]; t[2] = W[1][1]; t[3] = W[2][0]; t[4] = W[2][1]; t[5] = W[2][2];
+      t[6] = (k < N - 1) ? vu : 0.0;
+      if (k < N - 1) {
+        double Ac[3][3], T[3][3], Wn[3][3];
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) Ac[a][b] = A[a][b] - B[a] * K[b];
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) { T[a][b] = 0.0; for (int e = 0; e < 3; ++e) T[a][b] += Ac[a][e] * W[e][b]; }
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) { double v = B[a] * B[b] * iF; for (int e = 0; e < 3; ++e) v += T[a][e] * Ac[b][e]; Wn[a][b] = v; }
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) W[a][b] = 0.5 * (Wn[a][b] + Wn[b][a]);
+      }
+    }
+  }
   // prefix of possible regions per car
   for (int c = tid; c < C; c += nt) {
     int n = 0;

@@ -181,6 +181,7 @@ inline void pack_one(const MiqpB200Problem &q, Packed &pk) {
   p.o_modetab = push_d(d, nullptr, (size_t)R * 20);
   p.o_fronttab = push_d(d, nullptr, (size_t)C * R * 12);
   p.o_cost = push_d(d, nullptr, (size_t)C * N * 16);
+  p.o_wtab = push_d(d, nullptr, (size_t)C * N * 14);
 
   p.o_initreg = push_i(ib, q.initial_region, C);
   p.o_possible = push_i(ib, q.possible_region, (size_t)C * R);

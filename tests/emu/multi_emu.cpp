@@ -112,9 +112,10 @@ extern "C" int emu_multi_solve(const MiqpB200Problem *q, double gap_tol, double 
       }
       continue;
     }
+    pruned_lb = std::min(pruned_lb, out.pruned_min);
     const unsigned char *src = out.from_imp ? k.imp : k.dec;
     for (int a = 0; a < out.nalt; ++a) {
-      Node ch; ch.bound = out.obj; ch.depth = nd.depth + 1; ch.rank = a; ch.uid = next_uid++; ch.birth = rounds;
+      Node ch; ch.bound = (std::getenv("EMU_NO_CHILD_BOUND") ? out.obj : sh.cb[a]); ch.depth = nd.depth + 1; ch.rank = a; ch.uid = next_uid++; ch.birth = rounds;
       ch.dec.assign(src, src + nds);
       if (out.soff >= 0) { ch.dec[out.soff] = sh.alts[a]; if (sh.alts[a] == k.imp[out.soff]) ch.rank = -1; }
       else ch.rank = 0;
