@@ -158,6 +158,12 @@ typedef struct MiqpB200RunStats {
 } MiqpB200RunStats;
 int miqp_b200_run_stats(const MiqpB200Solver *s, MiqpB200RunStats *out);
 
+/* Diagnostics of the last run (zeros unless the library was built with -DMQ_PROF):
+ * out256[0..100] histogram of interior-point iterations per node relaxation, out256[128..131]
+ * clock64 cycles in row passes / Riccati factorisation / vector sweeps / whole node solves,
+ * out256[132..133] infeasible node relaxations and their iterations. */
+int miqp_b200_debug_profile(MiqpB200Solver *s, unsigned long long *out256);
+
 /* FP64 FMA throughput of the device in TFLOP/s (DFMA micro-benchmark, best of 5): the
  * roofline denominator of the node kernel, which MEASURED_PEAKS.json does not provide. */
 int miqp_b200_measure_fp64_peak(MiqpB200Solver *s, double *tflops);

@@ -22,6 +22,7 @@ DECLARED_SYMBOLS = [
     "miqp_b200_last_error", "miqp_b200_layout", "miqp_b200_sizes", "miqp_b200_assemble",
     "miqp_b200_evaluate", "miqp_b200_solve_batch", "miqp_b200_batch_upload", "miqp_b200_batch_run",
     "miqp_b200_batch_fetch", "miqp_b200_run_stats", "miqp_b200_measure_fp64_peak",
+    "miqp_b200_debug_profile",
 ]
 
 
@@ -126,6 +127,7 @@ def load_library():
     lib.miqp_b200_batch_fetch.argtypes = [C.c_void_p, C.POINTER(_dp), C.POINTER(CSolveInfo)]
     lib.miqp_b200_run_stats.argtypes = [C.c_void_p, C.POINTER(CRunStats)]
     lib.miqp_b200_measure_fp64_peak.argtypes = [C.c_void_p, _dp]
+    lib.miqp_b200_debug_profile.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong)]
     _lib = lib
     return lib
 
@@ -352,6 +354,11 @@ class Solver:
         st = CRunStats()
         self._check(self._lib.miqp_b200_run_stats(self._h, C.byref(st)), "miqp_b200_run_stats")
         return {n: getattr(st, n) for n, _ in CRunStats._fields_}
+
+    def debug_profile(self):
+        out = (C.c_ulonglong * 256)()
+        self._check(self._lib.miqp_b200_debug_profile(self._h, out), "miqp_b200_debug_profile")
+        return list(out)
 
     def measure_fp64_peak(self) -> float:
         tf = C.c_double()

@@ -122,11 +122,15 @@ __global__ void __launch_bounds__(SEL_THREADS) bnb_select_kernel(BnbState st, co
   // nodes taken this round: one dive head per plan until an incumbent exists; afterwards the base
   // count, raised when few plans are still active so that the resident warps stay busy
   int K = st.sel_dive;
+  const int act = *st.active_prev > 0 ? *st.active_prev : st.count;
+  const int fill = st.nwarps / act;
   if (have_inc) {
-    const int act = *st.active_prev > 0 ? *st.active_prev : st.count;
     K = st.sel_base;
-    const int fill = st.nwarps / act;
     if (fill > K) K = fill;
+    if (K > KS) K = KS;
+  } else if (st.dive_fill > 0) {
+    const int kd = fill / st.dive_fill;
+    if (kd > K) K = kd;
     if (K > KS) K = KS;
   }
   __syncthreads();
@@ -556,7 +560,18 @@ __global__ void __launch_bounds__(128) bnb_nodes_kernel(BnbState st, const DevPr
     PhiEntry e1, e2;
     e1.setup(p, lane);
     e2.setup(p, (lane >= 21 && lane < 25) ? lane + 11 : 35);
+#ifdef MQ_PROF
+    const long long pt0 = clock64();
+#endif
     QpResult r = solve_node_qp(w, e1, e2);
+#ifdef MQ_PROF
+    if (lane == 0) {
+      atomicAdd(&st.prof[r.iters > 100 ? 100 : r.iters], 1ULL);
+      atomicAdd(&st.prof[128], (unsigned long long)r.c_rows); atomicAdd(&st.prof[129], (unsigned long long)r.c_factor);
+      atomicAdd(&st.prof[130], (unsigned long long)r.c_sweeps); atomicAdd(&st.prof[131], (unsigned long long)(clock64() - pt0));
+      if (r.status != 0) { atomicAdd(&st.prof[132], 1ULL); atomicAdd(&st.prof[133], (unsigned long long)r.iters); }
+    }
+#endif
     if (lane == 0) {
       atomicAdd(&st.stat_nodes[s], 1ULL);
       atomicAdd(&st.stat_iters[s], (unsigned long long)r.iters);

@@ -25,6 +25,7 @@ struct BnbState {
   int sel_per_plan;     // stride of sel_idx: most node relaxations a plan may take in one round
   int sel_base;         // nodes per plan per round once an incumbent exists (raised when few plans are active)
   int sel_dive;         // nodes per plan per round while diving for the first incumbent
+  int dive_fill;        // >0: while diving, widen to (resident warps / active plans) / dive_fill heads when few plans are active
   int work_cap;
   int force_multi;      // route every plan to the CTA-per-node kernel (test hook)
   // node pools [count][cap]
@@ -46,6 +47,7 @@ struct BnbState {
   unsigned char *inc_dec;  // [count][ndec_stride]
   unsigned long long *inc_uid;  // tie break between equal incumbents (deterministic result)
   unsigned long long *stat_nodes, *stat_iters, *stat_rows;
+  unsigned long long *prof;   // [256] diagnostics (filled only by -DMQ_PROF builds): [it] histogram of IPM iterations per node, [128..] cycles
   // round control
   int2 *work; int *work_cnt; int *work_next; int *active; int *err; int *active_prev;
   double2 *rows_ws;     // [nwarps][kmax+1][maxN] (s, lambda) records of the warp-per-node kernel

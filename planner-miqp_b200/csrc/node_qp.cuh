@@ -530,6 +530,9 @@ struct QpResult {
   int iters;
   double obj;     // without soft-decision penalties
   long rows;      // active rows x iterations (work counter)
+#ifdef MQ_PROF
+  long long c_rows, c_factor, c_sweeps;   // clock64 cycles: row passes / Riccati factorisation / vector + forward sweeps
+#endif
 };
 
 // Solves the node QP of w.dec.  On success V_Z holds the optimal stage vectors.
@@ -538,6 +541,13 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
   const double *D = w.D;
   const int lane = w.lane, N = w.N;
   QpResult res; res.status = 1; res.iters = 0; res.obj = 0.0; res.rows = 0;
+#ifdef MQ_PROF
+  res.c_rows = res.c_factor = res.c_sweeps = 0;
+  long long pc0 = clock64(), pc1;
+#define MQ_TICK(field) { pc1 = clock64(); res.field += pc1 - pc0; pc0 = pc1; }
+#else
+#define MQ_TICK(field)
+#endif
 
   // trivially infeasible boxes (build_node_qp of the oracle)
   int bad = 0;
@@ -621,8 +631,11 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
     if (rpn <= 1e-9 && rdn <= 1e-8 * (1.0 + cn) && mu <= 1e-10) { status = 0; break; }
     if (lmax > 1e13) { status = 1; break; }
     // ---- predictor ----
+    MQ_TICK(c_rows)
     riccati_factor(w, e1, e2);
+    MQ_TICK(c_factor)
     riccati_forward(w, V_DZA);
+    MQ_TICK(c_sweeps)
     double rmax = 1.0, s1 = 0.0, s2 = 0.0;
     for (int i = lane; i < N; i += 32) {
       const double *Vi = w.V + i * V_STRIDE;
@@ -655,8 +668,10 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
       for (int t = 0; t < 8; ++t) Vi[V_G + t] = cst[t] * v.y[t] + cst[8 + t] + v.gx[t];
     }
     __syncwarp();
+    MQ_TICK(c_rows)
     riccati_vector(w);
     riccati_forward(w, V_DZ);
+    MQ_TICK(c_sweeps)
     rmax = 0.0;
     bool bad_step = false;
     for (int i = lane; i < N; i += 32) {
@@ -682,6 +697,7 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
     if (alpha < 1e-6) { if (++stall >= 5) { status = 2; break; } } else stall = 0;
   }
   res.iters = it;
+  MQ_TICK(c_rows)
   if (status != 0) {
     // not converged: infeasible only if the primal point violates its rows
     double worst = 0.0;

@@ -1,0 +1,33 @@
+"""Per-round trace of the device search (work items, active plans, node-kernel ms) plus the
+distribution of nodes per plan.  Diagnostic only."""
+import argparse, os, sys
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, ROOT)
+import numpy as np
+import planner_miqp_b200 as P
+from planner_miqp_b200.scenarios import obstacle_scenario
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=2048)
+a = ap.parse_args()
+plans = [obstacle_scenario(k).build() for k in range(a.batch)]
+s = P.Solver(verbose=2)
+s.upload(plans, gap_tol=1e-4, time_limit=600.0)
+s.run()
+ms = s.run()
+xs, infos = s.fetch()
+n = np.array([i.nodes for i in infos]); r = np.array([i.rounds for i in infos]); it = np.array([i.qp_iters for i in infos])
+print("ms", ms, "nodes/plan mean", n.mean(), "pcts", np.percentile(n, [50, 90, 99, 100]))
+print("rounds/plan pcts", np.percentile(r, [50, 90, 99, 100]))
+print("iters/node", it.sum() / n.sum())
+prof = s.debug_profile()
+if sum(prof):
+    h = prof[:101]; tot = sum(h)
+    cum = 0; qs = {}
+    for k, v in enumerate(h):
+        cum += v
+        for q in (0.5, 0.9, 0.99, 1.0):
+            if q not in qs and cum >= q * tot: qs[q] = k
+    print("iters/node quantiles", qs, "nodes", tot, "infeasible", prof[132], "iters of infeasible", prof[133])
+    c = prof[128:132]
+    print("cycles: rows %.1f%% factor %.1f%% sweeps %.1f%% of node total; per node %.0f cycles; per iter %.0f cycles" % (
+        100 * c[0] / c[3], 100 * c[1] / c[3], 100 * c[2] / c[3], c[3] / tot, c[3] / max(sum(k * v for k, v in enumerate(h)), 1)))
