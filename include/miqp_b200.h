@@ -17,7 +17,7 @@
  * miqp_b200_layout                 decision_variables.mod:10-53 / RawResults,
  *                                  src/miqp_planner_data.hpp:46-97
  * miqp_b200_assemble               IloOplModel::generate(), src/cplex_wrapper.cpp:98 over
- *                                  cplexmodel/*.mod (row instantiation)
+ *                                  the cplexmodel .mod files (row instantiation)
  * miqp_b200_sizes                  collectCplexStatistics, src/cplex_wrapper.cpp:680-690
  * miqp_b200_evaluate               objective_function.mod:7-19 + row feasibility
  * miqp_b200_solve_batch            cplex.solve() + collectRawResults +

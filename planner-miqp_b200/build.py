@@ -30,8 +30,33 @@ def _newest_src() -> float:
     return t
 
 
+HOST = os.path.join(HERE, "host")
+CAPI_LIB = os.path.join(HERE, "libmiqp_planner_c_api.so")
+HOST_UNITS = ["b200_wrapper.cpp", "miqp_planner.cpp", "miqp_planner_c_api.cpp"]
+
+
+def build_host(force: bool = False) -> str:
+    """libmiqp_planner_c_api.so: the C++ host side (planner facade + solver driver shaped like the reference's
+    MiqpPlanner / CplexWrapper + the 17-function C API), g++, linked against libmiqp_b200.so next to it."""
+    newest = max(os.path.getmtime(os.path.join(r, f)) for r, _, fs in os.walk(HOST) for f in fs)
+    newest = max(newest, max(os.path.getmtime(os.path.join(HERE, "..", "include", f)) for f in os.listdir(os.path.join(HERE, "..", "include"))))
+    if not force and os.path.exists(CAPI_LIB) and os.path.getmtime(CAPI_LIB) >= newest:
+        return CAPI_LIB
+    gen = os.path.join(HERE, "..", "tools", "gen_fitting_tables_inc.py")
+    subprocess.run([sys.executable, gen], check=True, capture_output=True)
+    cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-Wall", "-Wno-comment", "-DPLANNER_MIQP_CAPI_NO_APOLLO=0",
+           "-o", CAPI_LIB] + [os.path.join(HOST, u) for u in HOST_UNITS] + [
+           "-L" + HERE, "-lmiqp_b200", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("host library build failed")
+    return CAPI_LIB
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_src():
+        build_host(force=False)
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
@@ -54,6 +79,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         f.write("\n".join(log))
     if verbose:
         sys.stderr.write("\n".join(log))
+    build_host(force=True)
     return LIB
 
 
