@@ -1,0 +1,144 @@
+// C++ API test of the host side (planner-miqp_b200/host): the class-level behaviour the reference's gtest
+// suites check on MiqpPlanner / CplexWrapper (test/miqp_planner_test.cc, test/cplex_wrapper_test.cc) that needs
+// no BARK.  `test_host_api cpu` runs the device-free part, `test_host_api gpu` adds the solves.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../planner-miqp_b200/host/miqp_planner.hpp"
+
+using namespace miqp::planner;
+using miqp::planner::cplex::CplexWrapper;
+
+static int failures = 0;
+#define CHECK(c) do { if (!(c)) { std::printf("FAIL %s:%d  %s\n", __FILE__, __LINE__, #c); ++failures; } } while (0)
+
+static PolyLine Line(std::initializer_list<double> pts, double inc = 0.2) {
+  std::vector<double> v(pts);
+  return PolyLine(v.data(), (int)v.size() / 2, inc);
+}
+
+static void cpu_part() {
+  Settings s = DefaultSettings();
+  CHECK(s.nr_regions == 16 && s.nr_steps == 20 && s.precision == 12 && std::fabs(s.ts - 0.25f) < 1e-7);
+  CHECK(std::string(ApolloDefaultSettings().cplexModelpath).find("cplex_modfiles") != std::string::npos);
+  MiqpPlanner planner(s);
+  auto p = planner.GetParameters();
+  CHECK(p->nr_regions == 16 && p->NumSteps == 20 && p->NumCars == 0);
+  CHECK(p->fraction_parameters.rows() == 16 && p->poly_orientation_params.POLY_SINT_UB.rows() == 16);
+  // test/miqp_planner_test.cc:127-134 spot value of the 16-region sine table
+  const double st[6] = {0, 4, 0, 0, 0.1, 0};
+  int idx = planner.AddCar(st, Line({0, 0, 50, 0}), 5, 1);
+  CHECK(idx == 0 && p->NumCars == 1);
+  CHECK(p->IntitialState(0, MIQP_STATE_VX) == 4 && p->x_ref.cols() == 20);
+  CHECK(std::fabs(p->WEIGHTS_POS_X(0) - 1.0) < 1e-12 && std::fabs(p->WEIGHTS_JERK_X(0) - 0.5) < 1e-12);   // lambda 0.5 * weight
+  CHECK(p->possible_region(0, 0) == 1 && p->possible_region(0, 15) == 1 && p->possible_region(0, 1) == 1 && p->possible_region(0, 8) == 0);
+  CHECK(std::fabs(p->total_max_acc - (float)(p->acc_limit_params.max_x.maxCoeff() + 1e-6)) < 1e-5 || p->total_max_acc >= p->acc_limit_params.max_y.maxCoeff());
+  const double st2[6] = {0, 4, 0, 4, 0.1, 0};
+  int idx2 = planner.AddCar(st2, Line({0, 4, 50, 4}), 5, 1, 0.0, false);
+  CHECK(idx2 == 1 && p->NumCars == 2 && p->WEIGHTS_POS_X(1) == 0 && p->WEIGHTS_VEL_X(1) == 2);   // untracked positions
+  int idx3 = planner.AddCar(st2, Line({0, 8, 50, 8}), 5, 1);
+  CHECK(idx3 == 2);
+  bool threw = false;
+  try { planner.RemoveCar(1); } catch (const NotImplementedException &) { threw = true; }
+  CHECK(threw);                                   // middle cars cannot be removed (src/miqp_planner.cpp:553-557)
+  planner.RemoveCar(2);
+  CHECK(p->NumCars == 2 && p->x_ref.rows() == 2);
+  planner.RemoveCar(0);                            // ego: refused, logged
+  CHECK(p->NumCars == 2);
+  threw = false;
+  try { planner.RemoveObstacle(0); } catch (const NotImplementedException &) { threw = true; }
+  CHECK(threw);
+  int oid = planner.AddObstacle({{20.0, 0.0, 0.0}}, 1.0, 1.0, false, true);
+  CHECK(oid == 0 && p->nr_obstacles == 1 && p->max_lines_obstacles == 4 && (int)p->ObstacleConvexPolygon[0].size() == 20);
+  CHECK(std::fabs(p->ObstacleConvexPolygon[0][0](0, 0) - 18.5) < 1e-12);   // 1 x 1 box inflated by the collision radius
+  planner.RemoveAllObstacles();
+  CHECK(p->nr_obstacles == 0 && p->max_lines_obstacles == 0);
+  // copies share the parameters and get their own solver (src/miqp_planner.cpp:153-175)
+  MiqpPlanner copy(planner);
+  CHECK(copy.GetParameters().get() == p.get());
+  CHECK(copy.GetCplexWrapper().getRawResults().get() != planner.GetCplexWrapper().getRawResults().get());
+  // unknown table combination
+  Settings bad = DefaultSettings(); bad.nr_regions = 64;
+  threw = false;
+  try { MiqpPlanner q(bad); } catch (const std::invalid_argument &) { threw = true; }
+  CHECK(threw);
+  // the solver class keeps the reference's configuration surface
+  CplexWrapper w("cplexmodel/", "cplexmodel.mod", CplexWrapper::CPPINPUTS, 12);
+  w.setSpecialOrderedSets(true); w.setUseBranchingPriorities(true); w.setBranchingPriorityValueExtent(1, 19);
+  w.setBufferCplexOutputsToStream(true); w.setDebugOutputPrint(false);
+  CHECK(w.getTmpWarmstartFile() == "/tmp/warmstart_debug_res.mst");
+  CHECK(w.callCplex(0.0) == FAILED_SEG_FAULT);     // no parameters bound: the solver cannot run
+  // flatten / pack / unpack round trip
+  miqp::planner::cplex::FlatProblem f;
+  miqp::planner::cplex::Flatten(*p, 12, f);
+  MiqpB200Layout l;
+  CHECK(miqp_b200_layout(&f.p, &l) == MIQP_B200_OK);
+  CHECK(l.ncols == 12 * 2 * 20 + 2 * 20 * 16 + 5 * 2 * 20 + 16 * 20 + 4 * 20);
+  std::vector<double> x(l.ncols);
+  for (int k = 0; k < l.ncols; ++k) x[k] = (k < l.base_nwe) ? 0.25 * k : (double)(k % 2);
+  RawResults r; std::vector<double> y;
+  miqp::planner::cplex::Unpack(l, x.data(), r);
+  miqp::planner::cplex::Pack(l, r, false, y);
+  bool same = true;
+  for (int k = 0; k < l.ncols; ++k) same = same && (k >= l.base_sv ? y[k] == (double)(int)x[k] : y[k] == x[k]);
+  CHECK(same);
+  miqp::planner::cplex::Pack(l, r, true, y);
+  CHECK(std::isnan(y[l.base_ar + 19 * 16]) && !std::isnan(y[l.base_ar + 18 * 16]) && !std::isnan(y[19]));
+}
+
+static void gpu_part() {
+  Settings s = DefaultSettings();
+  s.relative_mip_gap_tolerance = 1e-4f;
+  s.warmstartType = RECEDING_HORIZON_WARMSTART;
+  MatrixXd map(4, 2);
+  const double mv[8] = {-50, -50, -50, 50, 50, 50, 50, -50};
+  for (int k = 0; k < 4; ++k) { map(k, 0) = mv[2 * k]; map(k, 1) = mv[2 * k + 1]; }
+  MiqpPlanner planner(s, map);
+  double st[6] = {0, 4, 0, 0, 0.1, 0};
+  const PolyLine ref = Line({0, 0, 50, 0});
+  planner.AddCar(st, ref, 5, 1);
+  planner.GetCplexWrapper().setCollectModelStatistics(true);
+  CHECK(planner.Plan(0.0));
+  auto p = planner.GetParameters();
+  CHECK(p->initial_region(0) == 1 && p->nr_environments == 1 && (int)p->MultiEnvironmentConvexPolygon.size() == 1);
+  SolutionProperties sp = planner.GetSolutionProperties();
+  CHECK(sp.status == 101 || sp.status == 102);
+  CHECK(sp.gap <= 1e-4 && sp.max_violation <= 1e-6 && sp.NrSolutionPool == 1);
+  CHECK(sp.NrBinaryVariables == 5 * 20 + 16 * 20 + 5 * 20 && sp.NrFloatVariables == 240 && sp.NrConstraints > 8944);
+  auto rr = planner.GetSolution();
+  CHECK(rr->N == 20 && rr->NrCars == 1 && rr->pos_x(0, 0) == 0.0 && rr->active_region(0, 0, 0) == 1);
+  for (int i = 0; i < 20; ++i) { int sum = 0; for (int j = 0; j < 16; ++j) sum += rr->active_region(0, i, j); CHECK(sum == 1); }
+  CHECK(planner.HasValidWarmstart());
+  // receding horizon: the next plan starts from the shifted solution and reaches the same objective as a cold planner
+  double nxt[6]; planner.Get2ndOrderStateFromSolution(1, 0, nxt);
+  planner.UpdateCar(0, nxt, ref);
+  CHECK(planner.Plan(0.25));
+  Settings sc = s; sc.warmstartType = NO_WARMSTART;
+  MiqpPlanner cold(sc, map);
+  cold.AddCar(nxt, ref, 5, 1);
+  CHECK(cold.Plan(0.25));
+  const double a = planner.GetSolutionProperties().objective, b = cold.GetSolutionProperties().objective;
+  CHECK(std::fabs(a - b) <= 2e-4 * std::fabs(b));
+  // infeasible start: obstacle on top of the car -> FAILED_NO_SOLUT for every region combination -> Plan() false
+  MiqpPlanner blocked(sc, map);
+  blocked.AddCar(st, ref, 5, 1);
+  CHECK(blocked.AddObstacle({{0.0, 0.0, 0.0}}, 4.0, 4.0, false, true) == 0);
+  CHECK(!blocked.Plan(0.0));
+  SolutionProperties bp = blocked.GetSolutionProperties();
+  CHECK(std::isnan(bp.objective) && std::isnan(bp.gap) && bp.status == 103);
+  // batched dispatch
+  MiqpPlanner p1(sc, map), p2(sc, map);
+  double s1[6] = {0, 3, 0, 0.5, 0.1, 0}, s2[6] = {0, 6, 0, -0.5, 0.1, 0};
+  p1.AddCar(s1, ref, 5, 1); p2.AddCar(s2, ref, 5, 1);
+  std::vector<bool> ok = MiqpPlanner::PlanBatch({&p1, &p2, &blocked}, 0.0);
+  CHECK(ok.size() == 3 && ok[0] && ok[1] && !ok[2]);
+}
+
+int main(int argc, char **argv) {
+  cpu_part();
+  if (argc > 1 && std::strcmp(argv[1], "gpu") == 0) gpu_part();
+  std::printf(failures ? "%d check(s) failed\n" : "all checks passed\n", failures);
+  return failures ? 1 : 0;
+}
