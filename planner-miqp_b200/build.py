@@ -13,8 +13,6 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmiqp_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=off", "-Xptxas", "-v"]
-if os.environ.get("MIQP_ROWS_L2") == "1":   # A/B switch of the node kernel (see node_qp.cuh:RowIO)
-    COMMON.append("-DMQ_ROWS_L2")
 # formulation.cu is compared bit for bit with the oracle: no FMA contraction there
 if os.environ.get("MIQP_PROF") == "1":      # per-phase cycle counters of the node kernel (miqp_b200_debug_profile)
     COMMON.append("-DMQ_PROF")

@@ -491,17 +491,15 @@ __device__ __forceinline__ void effective_regions(const WarpCtx &w) {
   __syncwarp();
 }
 
-// shared memory of one warp: S[N][S_STRIDE] V[N][V_STRIDE] T[T_SIZE] auxd[N] | rows[kmax][N] (16-byte
-// aligned) | jeff[N] aux[3N] | dec imp alternatives
+// shared memory of one node: S[N][S_STRIDE] V[N][V_STRIDE] T[T_SIZE] auxd[N] | rows[kmax+1][NP] (16-byte
+// aligned, NP = padded stage stride, node_qp.cuh:team_row_stride) | jeff[N] aux[3N] | dec imp alternatives
 struct NodeSmem { int off_rows, off_int, off_dec, total; };
 __host__ __device__ inline NodeSmem node_smem_layout(int maxN, int kmax, int ndec_stride) {
   NodeSmem L;
   int b = (maxN * (S_STRIDE + V_STRIDE + 1) + T_SIZE) * 8;
   b = (b + 15) & ~15;
   L.off_rows = b;   // (s, lambda) records: see RowIO (node_qp.cuh)
-#ifndef MQ_ROWS_L2
-  b += (kmax + 1) * maxN * 16;
-#endif
+  b += (kmax + 1) * (maxN + 7) * 16;
   L.off_int = b; b += maxN * 4 * 4;
   b = (b + 15) & ~15;
   L.off_dec = b; b += 2 * ndec_stride + 272;
@@ -510,23 +508,24 @@ __host__ __device__ inline NodeSmem node_smem_layout(int maxN, int kmax, int nde
 }
 int node_kernel_smem_per_warp(int maxN, int kmax, int ndec_stride) { return node_smem_layout(maxN, kmax, ndec_stride).total; }
 
-__global__ void __launch_bounds__(128) bnb_nodes_kernel(BnbState st, const DevProb *probs, const double *dblob,
-                                                        const int *iblob, int smem_per_warp, int maxN, int round) {
+// One CTA = one team of NODE_TEAM_WARPS warps = one node relaxation at a time (persistent: teams pull
+// (plan, node) items from the round's work list).  255 registers x 128 threads x 2 CTAs fill the
+// register file of an SM; the third CTA that shared memory would allow (57 kB per node at N = 40) does not fit.
+__global__ void __launch_bounds__(NODE_TEAM_WARPS * 32, 2) bnb_nodes_kernel(BnbState st, const DevProb *probs, const double *dblob,
+                                                                             const int *iblob, int smem_per_node, int maxN, int round) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned char *base = smem_raw + (size_t)warp * smem_per_warp;
+  __shared__ double s_red[32];
+  __shared__ int s_wi;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  unsigned char *base = smem_raw;
   const NodeSmem L = node_smem_layout(maxN, st.kmax, st.ndec_stride);
   WarpCtx w;
-  w.D = dblob; w.I = iblob; w.lane = lane;
+  w.D = dblob; w.I = iblob; w.lane = lane; w.wid = wid; w.nw = nw; w.red = s_red;
   w.S = reinterpret_cast<double *>(base);
   w.V = w.S + maxN * S_STRIDE;
   w.T = w.V + maxN * V_STRIDE;
   w.auxd = w.T + T_SIZE;
-#ifndef MQ_ROWS_L2
   w.rows = reinterpret_cast<double2 *>(base + L.off_rows);
-#else
-  w.rows = st.rows_ws + (size_t)(blockIdx.x * (blockDim.x >> 5) + warp) * (size_t)(st.kmax + 1) * maxN;
-#endif
   w.jeff = reinterpret_cast<int *>(base + L.off_int);
   w.aux = w.jeff + maxN;
   w.dec = base + L.off_dec;
@@ -535,41 +534,52 @@ __global__ void __launch_bounds__(128) bnb_nodes_kernel(BnbState st, const DevPr
   const int nwork = *reinterpret_cast<volatile int *>(st.work_cnt);
 
   for (;;) {
-    int wi = 0;
-    if (lane == 0) wi = atomicAdd(st.work_next, 1);
-    wi = __shfl_sync(FULL, wi, 0);
+    __syncthreads();   // warp 0 has finished the previous node (scan, children) before its shared memory is reused
+    if (threadIdx.x == 0) s_wi = atomicAdd(st.work_next, 1);
+    __syncthreads();
+    const int wi = s_wi;
     if (wi >= nwork) break;
     const int2 item = st.work[wi];
     const int s = item.x, slot = item.y;
     const DevProb &p = probs[s];
     const long pb = (long)s * st.cap;
     w.p = &p; w.N = p.N;
-    copy_bytes16(w.dec, st.dec + (pb + slot) * st.ndec_stride, st.ndec_stride, lane);
-    const double nbound = st.bound[pb + slot];
-    const int2 nmeta = st.meta[pb + slot];
-    const unsigned long long nuid = st.uid[pb + slot];
-    const double cutoff = st.cutoff[s];
-    __syncwarp();
-    effective_regions(w);
-    // constant cost of SOFT obstacle decisions
-    int nsoft = 0;
-    for (int k = lane; k < 5 * p.O * p.N; k += 32) nsoft += (w.dec[p.off_obs + k] == OBS_SOFT);
-    nsoft = warp_sum_i(nsoft);
-    const double pen = nsoft * p.w_slack_obs;
+    w.sg = team_sublanes(p.N, nw); w.spw = 32 / w.sg; w.ls = lane / w.sg; w.g = lane - w.ls * w.sg;
+    w.sgmul = 65536 / w.sg + 1; w.NP = team_row_stride(p.N, w.sg);
+    double pen = 0.0;
+    if (wid == 0) {
+      copy_bytes16(w.dec, st.dec + (pb + slot) * st.ndec_stride, st.ndec_stride, lane);
+      __syncwarp();
+      effective_regions(w);
+      // constant cost of SOFT obstacle decisions
+      int nsoft = 0;
+      for (int k = lane; k < 5 * p.O * p.N; k += 32) nsoft += (w.dec[p.off_obs + k] == OBS_SOFT);
+      nsoft = warp_sum_i(nsoft);
+      pen = nsoft * p.w_slack_obs;
+    }
+    __syncthreads();
 
     PhiEntry e1, e2;
     e1.setup(p, lane);
-    e2.setup(p, (lane >= 21 && lane < 25) ? lane + 11 : 35);
+    e2.setup(p, lane < 4 ? 32 + lane : 35);   // second entry of lanes 0..3: 32..35 (riccati_factor)
 #ifdef MQ_PROF
     const long long pt0 = clock64();
 #endif
     QpResult r = solve_node_qp(w, e1, e2);
+    if (wid != 0) continue;
+    // ---- warp 0: bookkeeping, scan of the relaxed optimum, children ----
+    const double nbound = st.bound[pb + slot];
+    const int2 nmeta = st.meta[pb + slot];
+    const unsigned long long nuid = st.uid[pb + slot];
+    const double cutoff = st.cutoff[s];
 #ifdef MQ_PROF
     if (lane == 0) {
       atomicAdd(&st.prof[r.iters > 100 ? 100 : r.iters], 1ULL);
       atomicAdd(&st.prof[128], (unsigned long long)r.c_rows); atomicAdd(&st.prof[129], (unsigned long long)r.c_factor);
       atomicAdd(&st.prof[130], (unsigned long long)r.c_sweeps); atomicAdd(&st.prof[131], (unsigned long long)(clock64() - pt0));
       if (r.status != 0) { atomicAdd(&st.prof[132], 1ULL); atomicAdd(&st.prof[133], (unsigned long long)r.iters); }
+      atomicAdd(&st.prof[134], (unsigned long long)r.c_a); atomicAdd(&st.prof[135], (unsigned long long)r.c_ared); atomicAdd(&st.prof[136], (unsigned long long)r.c_d);
+      atomicAdd(&st.prof[137], (unsigned long long)r.c_e); atomicAdd(&st.prof[138], (unsigned long long)r.c_g);
     }
 #endif
     if (lane == 0) {
@@ -678,9 +688,8 @@ int node_kernel_max_ctas(int smem_per_cta, int threads) {
 }
 
 int launch_bnb_nodes(const BnbState &st, const DevProb *probs, const double *dblob, const int *iblob,
-                     int smem_per_warp, int warps_per_cta, int ctas, int maxN, int round, cudaStream_t s) {
-  bnb_nodes_kernel<<<ctas, warps_per_cta * 32, (size_t)smem_per_warp * warps_per_cta, s>>>(st, probs, dblob, iblob,
-                                                                                             smem_per_warp, maxN, round);
+                     int smem_per_node, int warps_per_cta, int ctas, int maxN, int round, cudaStream_t s) {
+  bnb_nodes_kernel<<<ctas, warps_per_cta * 32, (size_t)smem_per_node, s>>>(st, probs, dblob, iblob, smem_per_node, maxN, round);
   return (int)cudaGetLastError();
 }
 

@@ -21,7 +21,7 @@ struct BnbState {
   int zstride;          // doubles per incumbent trajectory (max C*N*8 + 4*P*N)
   int kmax;             // row slots per stage (max over plans)
   int npad;             // stages padded to a multiple of 32 (max over plans)
-  int nwarps;           // resident warps of the node kernel
+  int nwarps;           // node relaxations in flight (resident teams of the node kernel)
   int sel_per_plan;     // stride of sel_idx: most node relaxations a plan may take in one round
   int sel_base;         // nodes per plan per round once an incumbent exists (raised when few plans are active)
   int sel_dive;         // nodes per plan per round while diving for the first incumbent
@@ -50,13 +50,13 @@ struct BnbState {
   unsigned long long *prof;   // [256] diagnostics (filled only by -DMQ_PROF builds): [it] histogram of IPM iterations per node, [128..] cycles
   // round control
   int2 *work; int *work_cnt; int *work_next; int *active; int *err; int *active_prev;
-  double2 *rows_ws;     // [nwarps][kmax+1][maxN] (s, lambda) records of the warp-per-node kernel
   int2 *work2; int *work_cnt2; int *work_next2;   // plans with NumCars > 1 (bnb_multi.cu)
 };
 
 void launch_bnb_init(const BnbState &st, const DevProb *probs, const unsigned char *warm_dec /* [count][ndec_stride] or null */,
                      const int *has_warm, cudaStream_t s);
 void launch_bnb_select(const BnbState &st, const DevProb *probs, int round, cudaStream_t s);
+constexpr int NODE_TEAM_WARPS = 4;   // warps that share one node relaxation (bnb_nodes_kernel)
 // returns 0 or a cudaError
 int launch_bnb_nodes(const BnbState &st, const DevProb *probs, const double *dblob, const int *iblob,
                      int smem_per_warp, int warps_per_cta, int ctas, int maxN, int round, cudaStream_t s);

@@ -1,4 +1,4 @@
-// node_qp.cuh -- one warp solves one node relaxation of the branch and bound.
+// node_qp.cuh -- one CTA (a team of up to four warps) solves one node relaxation of the branch and bound.
 //
 // A node fixes a subset of the disjunctions of the cplexmodel .mod files (region + low-speed
 // mode per car-step, model_region_constraints.mod:43-113 / minimum_speed_constraints.mod;
@@ -13,13 +13,17 @@
 //          G_i z_i <= h_i                          (stage-local rows)
 //
 // Solver: Mehrotra predictor-corrector interior point in STAGE space.  Every Newton step is
-// a Riccati sweep over the banded KKT system: lane = stage for everything that is local to
-// a stage (row generation, residuals, Hessian accumulation, step lengths), lanes = matrix
-// entries for the backward Riccati factorisation, and the cheap vector sweeps are done
-// redundantly by all lanes without any synchronisation.  Inequality rows are never stored:
+// a Riccati sweep over the banded KKT system.  Everything that is local to a stage (row
+// generation, residuals, Hessian accumulation, step lengths) is spread over the whole team:
+// sg = 4 / 3 / 2 / 1 adjacent lanes share one stage and take its row slots round robin, so that
+// N = 40 stages x 3 sub-lanes fill four warps; partial sums are combined with shuffles.  The
+// sequential part runs on warp 0 while the others wait at the barrier: lanes = matrix entries
+// for the backward Riccati factorisation, and the cheap vector sweeps are done redundantly by
+// all lanes without any synchronisation.  Inequality rows are never stored:
 // their coefficients are regenerated from the small per-plan tables in every pass; only the
 // slack and multiplier (s, lambda) of every row live in shared memory, laid out
-// [slot][stage] so that lanes (stages) access consecutive 16-byte pairs; residuals, the
+// [slot][stage] with the stage stride padded so that the (stage, sub-lane) pattern of a warp is
+// bank-conflict free for 16-byte records; residuals, the
 // affine step and the pending Newton step are recomputed from the stage vectors instead of
 // being stored (3 dot products per row instead of 2 more arrays).
 //
@@ -68,9 +72,31 @@ struct WarpCtx {
   int *aux;             // [3N] scan tables: best alt, region_decided, blame
   double *auxd;         // [N] scan: best non-frozen violation
   double *T;            // [T_SIZE] Riccati scratch (value function of the next stage)
-  double2 *rows;        // [kmax+1][N] (s, lambda) per inequality row
+  double2 *rows;        // [kmax+1][NP] (s, lambda) per inequality row
+  double *red;          // [8][4] team reduction scratch
   int lane, N;
+  int wid, nw;          // warp of the team, warps per team
+  int sg, g, ls, spw;   // sub-lanes per stage, my sub-lane, my stage slot in the warp (idle if >= spw), stages per warp
+  int sgmul;            // 65536 / sg + 1: slot % sg without a division
+  int NP;               // stage stride of `rows`
+  __device__ __forceinline__ bool mine(int slot) const { const int q = (slot * sgmul) >> 16; return slot - q * sg == g; }
 };
+
+// sub-lanes per stage for a team of nw warps and the padded stage stride of the row records
+__host__ __device__ inline int team_sublanes(int N, int nw) {
+  for (int s = 4; s > 1; --s) if (nw * (32 / s) >= N) return s;
+  return 1;
+}
+__host__ __device__ inline int team_row_stride(int N, int sg) {
+  const int target = (sg == 4) ? 2 : (sg == 3) ? 3 : (sg == 2) ? 4 : (N & 7);
+  return N + ((target - N) & 7);
+}
+
+// stages of this thread: i = wid * spw + ls, then in steps of nw * spw; every thread runs the same
+// number of trips (shuffles and barriers inside the body stay uniform), `act` says whether i is real
+#define MQ_FOR_STAGES(i, act)                                                                        \
+  for (int i = w.wid * w.spw + w.ls, c0_ = 0; c0_ < N; c0_ += w.nw * w.spw, i += w.nw * w.spw)       \
+    if (const bool act = (w.ls < w.spw) && (i < N); true)
 
 __device__ __forceinline__ double warp_max(double v) {
   for (int o = 16; o > 0; o >>= 1) { double t = __shfl_xor_sync(FULL, v, o); v = t > v ? t : v; }
@@ -87,6 +113,27 @@ __device__ __forceinline__ double warp_sum(double v) {
 __device__ __forceinline__ int warp_sum_i(int v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
   return v;
+}
+
+// sum / max over the sg adjacent lanes that share a stage; the result is valid in the leader (g == 0)
+__device__ __forceinline__ double sg_sum(const WarpCtx &w, double v) {
+  double t = v;
+  for (int d = 1; d < w.sg; ++d) t += __shfl_down_sync(FULL, v, d);
+  return t;
+}
+__device__ __forceinline__ double sg_max(const WarpCtx &w, double v) {
+  double t = v;
+  for (int d = 1; d < w.sg; ++d) { const double o = __shfl_down_sync(FULL, v, d); t = o > t ? o : t; }
+  return t;
+}
+// team-wide {max a, max b, sum c, sum d}; every thread receives bitwise identical results
+__device__ __forceinline__ void team_reduce(const WarpCtx &w, double &a, double &b, double &c, double &d) {
+  a = warp_max(a); b = warp_max(b); c = warp_sum(c); d = warp_sum(d);
+  if (w.lane == 0) { double *r = w.red + 4 * w.wid; r[0] = a; r[1] = b; r[2] = c; r[3] = d; }
+  __syncthreads();
+  a = w.red[0]; b = w.red[1]; c = w.red[2]; d = w.red[3];
+  for (int k = 1; k < w.nw; ++k) { a = fmax(a, w.red[4 * k]); b = fmax(b, w.red[4 * k + 1]); c += w.red[4 * k + 2]; d += w.red[4 * k + 3]; }
+  __syncthreads();
 }
 
 // bounds of a stage (model_region_constraints.mod:22-39 and the per-region boxes :73-94
@@ -147,7 +194,8 @@ __device__ __forceinline__ void mode_row(const WarpCtx &w, int j, int h, int k, 
   }
 }
 
-// Enumerates the inequality rows of stage i of the node in a fixed slot order.
+// Enumerates the inequality rows of stage i of the node in a fixed slot order; a thread only visits
+// the slots of its sub-lane (WarpCtx::mine).
 // Vis::bound<T>(slot, sgn, rhs):  sgn * y[T] <= rhs ;  Vis::general(slot, a[6], rhs):  a.x <= rhs
 template <class Vis>
 __device__ __forceinline__ void visit_rows(const WarpCtx &w, int i, Vis &v) {
@@ -161,47 +209,49 @@ __device__ __forceinline__ void visit_rows(const WarpCtx &w, int i, Vis &v) {
   int slot = 0;
 #define MQ_BND(T, act)                                                        \
   {                                                                           \
-    if ((act) && hi[T] < MQ_INF) v.template bound<T>(slot, 1.0, hi[T]);       \
+    if ((act) && hi[T] < MQ_INF && w.mine(slot)) v.template bound<T>(slot, 1.0, hi[T]);       \
     ++slot;                                                                   \
-    if ((act) && lo[T] > -MQ_INF) v.template bound<T>(slot, -1.0, -lo[T]);    \
+    if ((act) && lo[T] > -MQ_INF && w.mine(slot)) v.template bound<T>(slot, -1.0, -lo[T]);    \
     ++slot;                                                                   \
   }
   MQ_BND(Y_VX, st) MQ_BND(Y_AX, st) MQ_BND(Y_VY, st) MQ_BND(Y_AY, st) MQ_BND(Y_UX, ut) MQ_BND(Y_UY, ut)
 #undef MQ_BND
   if (i == 0) return;
+  // General rows: the sub-lanes of a stage walk every family in lockstep (item = k * sg + g), so that all
+  // lanes of a warp execute the same code on different rows; a global round robin over the slots would
+  // put the sub-lanes on different row kinds and serialise them.
   double a[6], rhs;
+  const int sg = w.sg, g = w.g;
   if (m != UNDEC && m != MODE_FROZEN) {
     const int j = m >> 2, h = m & 3;
 #pragma unroll 1
-    for (int k = 0; k < 5; ++k) { mode_row(w, j, h, k, a, rhs); v.general(slot + k, a, rhs); }
+    for (int k = g; k < 5; k += sg) { mode_row(w, j, h, k, a, rhs); v.general(slot + k, a, rhs); }
   }
   slot += 5;
   const double *ft = w.D + p.o_fronttab + 12 * (je >= 0 ? je : 0);
   if (p.E > 0) {
+    const int ME = p.maxEnvEdges;
 #pragma unroll 1
-    for (int pt = 0; pt < 5; ++pt) {
+    for (int item = g; item < 5 * ME; item += sg) {
+      const int pt = item / ME, ed = item - pt * ME;
       const int e = (p.E == 1) ? 0 : w.dec[p.off_env + i * 5 + pt];
       const bool act = (e != UNDEC) && (pt == 0 || je >= 0);
-      const int e0 = act ? w.I[p.o_env_off + e] : 0;
-      const int ne = act ? w.I[p.o_env_off + e + 1] - e0 : 0;
-#pragma unroll 1
-      for (int ed = 0; ed < p.maxEnvEdges; ++ed) {
-        if (ed < ne) { edge_row(w.D + p.o_envtab + 3 * (e0 + ed), ft, pt, -1.0, a, rhs); v.general(slot, a, rhs); }
-        ++slot;
-      }
+      if (!act) continue;
+      const int e0 = w.I[p.o_env_off + e];
+      const int ne = w.I[p.o_env_off + e + 1] - e0;
+      if (ed < ne) { edge_row(w.D + p.o_envtab + 3 * (e0 + ed), ft, pt, -1.0, a, rhs); v.general(slot + item, a, rhs); }
     }
+    slot += 5 * ME;
   }
 #pragma unroll 1
-  for (int o = 0; o < p.O; ++o)
-#pragma unroll 1
-    for (int pt = 0; pt < 5; ++pt) {
-      const unsigned char d = w.dec[p.off_obs + (o * N + i) * 5 + pt];
-      if (d != UNDEC && d != OBS_SOFT && (pt == 0 || je >= 0)) {
-        edge_row(w.D + p.o_obstab + 3 * ((o * N + i) * p.L + d), ft, pt, 1.0, a, rhs);
-        v.general(slot, a, rhs);
-      }
-      ++slot;
+  for (int item = g; item < 5 * p.O; item += sg) {
+    const int o = item / 5, pt = item - 5 * o;
+    const unsigned char d = w.dec[p.off_obs + (o * N + i) * 5 + pt];
+    if (d != UNDEC && d != OBS_SOFT && (pt == 0 || je >= 0)) {
+      edge_row(w.D + p.o_obstab + 3 * ((o * N + i) * p.L + d), ft, pt, 1.0, a, rhs);
+      v.general(slot + item, a, rhs);
     }
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -212,30 +262,15 @@ struct StepCtx {  // quantities of the last Newton step, needed to recompute it 
   bool pending;
 };
 
-// (s, lambda) of the inequality rows of one stage, [slot][stage] in the warp's shared memory.
-// Measured alternative (-DMQ_ROWS_L2): the records in a per-warp slice of HBM that stays L2
-// resident, with the record of slot+1 requested while slot is processed; it halves the shared
-// memory of a node (8 instead of 4 warps per SM at N=40) but runs 1.6x SLOWER (2048 config-2
-// plans: 652 ms vs 405 ms) -- the L2 round trip per row is not hidden by one more warp per
-// scheduler.  profiles/r1_ab_rows_l2_vs_smem.md
+// (s, lambda) of the inequality rows of one stage, [slot][stage] in the team's shared memory.
+// (A variant with the records in an L2-resident slice of HBM halves the shared memory of a node but ran
+// 1.6x slower: profiles/r1_ab_rows_l2_vs_smem.md.)
 struct RowIO {
   double2 *base;   // rows + i
-  int N, pslot;
-  double2 pref;
-  __device__ __forceinline__ void init(double2 *rows, int N_, int i) { base = rows + i; N = N_; pslot = -1; pref = make_double2(1.0, 1.0); }
-#ifndef MQ_ROWS_L2   // default: records in shared memory
-  __device__ __forceinline__ double2 ld(int slot) { return base[slot * N]; }
-  __device__ __forceinline__ void st(int slot, double2 v) { base[slot * N] = v; }
-#else
-  __device__ __forceinline__ double2 ld(int slot) {
-    double2 v;
-    if (slot == pslot) v = pref; else v = __ldcg(base + slot * N);
-    pslot = slot + 1;
-    pref = __ldcg(base + (slot + 1) * N);   // one spare slot row is allocated behind the last one
-    return v;
-  }
-  __device__ __forceinline__ void st(int slot, double2 v) { __stcg(base + slot * N, v); }
-#endif
+  int NP;
+  __device__ __forceinline__ void init(double2 *rows, int NP_, int i) { base = rows + i; NP = NP_; }
+  __device__ __forceinline__ double2 ld(int slot) { return base[slot * NP]; }
+  __device__ __forceinline__ void st(int slot, double2 v) { base[slot * NP] = v; }
 };
 
 __device__ __forceinline__ double dot6(const double a[6], const double y[8]) {
@@ -245,23 +280,27 @@ __device__ __forceinline__ double dot6(const double a[6], const double y[8]) {
   return v;
 }
 
-struct PassInit {  // s = max(h - g.z, 1), lambda = 1
-  RowIO io; double y[8];
+struct PassInit {  // s = max(h - g.z, 1), lambda = 1; gl = G' lambda for the initial dual residual
+  RowIO io; double y[8]; double gl[8];
   __device__ __forceinline__ void put(int slot, double gz, double rhs) {
     const double sl = rhs - gz;
     io.st(slot, make_double2(sl > 1.0 ? sl : 1.0, 1.0));
   }
-  template <int T> __device__ __forceinline__ void bound(int slot, double sgn, double rhs) { put(slot, sgn * y[T], rhs); }
-  __device__ __forceinline__ void general(int slot, const double a[6], double rhs) { put(slot, dot6(a, y), rhs); }
+  template <int T> __device__ __forceinline__ void bound(int slot, double sgn, double rhs) { put(slot, sgn * y[T], rhs); gl[T] += sgn; }
+  __device__ __forceinline__ void general(int slot, const double a[6], double rhs) {
+    put(slot, dot6(a, y), rhs);
+#pragma unroll
+    for (int t = 0; t < 6; ++t) gl[t] += a[t];
+  }
 };
 
 struct PassA {  // apply the pending step, residuals, Hessian and predictor gradient
   RowIO io; StepCtx sc;
   double y[8], d[8], da[8];
-  double H[21], Huu[2], gx[8], gl[8];
+  double H[21], Huu[2], gx[8];
   double rpn, musum, lmax; int m;
-  // returns (weight, weight*rp, lambda) of the row after the update
-  __device__ __forceinline__ void core(int slot, double gz, double gdz, double gda, double rhs, double &wgt, double &wr, double &lam_out) {
+  // returns (weight, weight*rp) of the row after the update
+  __device__ __forceinline__ void core(int slot, double gz, double gdz, double gda, double rhs, double &wgt, double &wr) {
     double2 v = io.ld(slot);
     double s = v.x, lam = v.y;
     if (sc.pending) {
@@ -276,18 +315,18 @@ struct PassA {  // apply the pending step, residuals, Hessian and predictor grad
       io.st(slot, make_double2(s, lam));
     }
     const double rp = gz + s - rhs;
-    wgt = lam * fast_rcp(s); wr = wgt * rp; lam_out = lam;
+    wgt = lam * fast_rcp(s); wr = wgt * rp;
     rpn = fmax(rpn, fabs(rp)); musum += s * lam; lmax = fmax(lmax, lam); ++m;
   }
   template <int T> __device__ __forceinline__ void bound(int slot, double sgn, double rhs) {
-    double wgt, wr, lam;
-    core(slot, sgn * y[T], sgn * d[T], sgn * da[T], rhs, wgt, wr, lam);
+    double wgt, wr;
+    core(slot, sgn * y[T], sgn * d[T], sgn * da[T], rhs, wgt, wr);
     if (T < 6) H[T * (T + 1) / 2 + T] += wgt; else Huu[T - 6] += wgt;
-    gx[T] += sgn * wr; gl[T] += sgn * lam;
+    gx[T] += sgn * wr;
   }
   __device__ __forceinline__ void general(int slot, const double a[6], double rhs) {
-    double wgt, wr, lam;
-    core(slot, dot6(a, y), dot6(a, d), dot6(a, da), rhs, wgt, wr, lam);
+    double wgt, wr;
+    core(slot, dot6(a, y), dot6(a, d), dot6(a, da), rhs, wgt, wr);
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
       const double wa = wgt * a[r];
@@ -295,7 +334,7 @@ struct PassA {  // apply the pending step, residuals, Hessian and predictor grad
       for (int c = 0; c <= r; ++c) H[r * (r + 1) / 2 + c] += wa * a[c];
     }
 #pragma unroll
-    for (int t = 0; t < 6; ++t) { gx[t] += a[t] * wr; gl[t] += a[t] * lam; }
+    for (int t = 0; t < 6; ++t) gx[t] += a[t] * wr;
   }
 };
 
@@ -379,35 +418,36 @@ __device__ __forceinline__ void ab_column(const DevProb &p, int a, int &row0, in
   }
 }
 
-struct PhiEntry {  // one entry (a,b) of Phi = M + [A B]' P [A B]
+struct PhiEntry {  // one entry (a,b) of Phi = M + [A B]' P [A B]: sum_k fa[k] sum_l fb[l] P[pi[3k+l]]
   int a, b;
-  int pi[9]; double cf[9];
+  int pi[9]; double fa[3], fb[3];
   __device__ __forceinline__ void setup(const DevProb &p, int e) {
     if (e < 21) { a = 0; while ((a + 1) * (a + 2) / 2 <= e) ++a; b = e - a * (a + 1) / 2; }
     else if (e < 33) { a = 6 + (e - 21) / 6; b = (e - 21) % 6; }
     else { a = (e == 33) ? 6 : 7; b = (e == 35) ? 7 : 6; }
-    int ra, ca, rb, cb; double fa[3], fb[3];
+    int ra, ca, rb, cb;
     ab_column(p, a, ra, ca, fa); ab_column(p, b, rb, cb, fb);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { if (k >= ca) fa[k] = 0.0; if (k >= cb) fb[k] = 0.0; }
 #pragma unroll
     for (int k = 0; k < 3; ++k)
 #pragma unroll
-      for (int l = 0; l < 3; ++l) {
-        const bool on = (k < ca && l < cb);
-        pi[k * 3 + l] = on ? pidx(ra + k, rb + l) : 0;
-        cf[k * 3 + l] = on ? fa[k] * fb[l] : 0.0;
-      }
+      for (int l = 0; l < 3; ++l) pi[k * 3 + l] = (k < ca && l < cb) ? pidx(ra + k, rb + l) : 0;
   }
+  // three independent inner chains of three, then one outer chain of three (6 dependent DFMA instead of 9)
   __device__ __forceinline__ double eval(const double *P) const {
-    double v = 0.0;
+    double r[3];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) v += cf[k] * P[pi[k]];
-    return v;
+    for (int k = 0; k < 3; ++k) r[k] = fma(fb[2], P[pi[3 * k + 2]], fma(fb[1], P[pi[3 * k + 1]], fb[0] * P[pi[3 * k]]));
+    return fma(fa[2], r[2], fma(fa[1], r[1], fa[0] * r[0]));
   }
 };
 
 // Backward factorisation + predictor vector.  On return S_i holds G_i, Finv_i and V_i holds
 // k_i for every stage; the value function (P, p) of the next stage only lives in the warp
-// scratch (double buffered).
+// scratch (double buffered).  Straight-line code per stage: every lane evaluates its entry lane of
+// Phi (0..31) AND, interleaved, a second entry (32 + lane for lanes 0..3, a zero dummy elsewhere) and
+// one component of phi = g + [A B]' p (lanes 0..7); only the stores are predicated.
 __device__ __forceinline__ void riccati_factor(const WarpCtx &w, const PhiEntry &e1, const PhiEntry &e2) {
   const DevProb &p = *w.p;
   const int lane = w.lane, N = w.N;
@@ -421,44 +461,51 @@ __device__ __forceinline__ void riccati_factor(const WarpCtx &w, const PhiEntry 
   __syncwarp();
   int prow0 = 0, pcnt = 0; double pcf[3] = {0, 0, 0};
   if (lane < 8) ab_column(p, lane, prow0, pcnt, pcf);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) if (k >= pcnt) pcf[k] = 0.0;
+  const int la = (lane < 21) ? e1.a : 0, lb = (lane < 21) ? e1.b : 0, l6 = (lane < 6) ? lane : 0;
   for (int i = N - 2; i >= 0; --i) {
     double *Si = w.S + i * S_STRIDE, *Vi = w.V + i * V_STRIDE;
     const double *Pn = T + T_P + 24 * ((i + 1) & 1), *pn = T + T_PV + 6 * ((i + 1) & 1);
     double *Pc = T + T_P + 24 * (i & 1), *pc = T + T_PV + 6 * (i & 1);
-    // phase 1: Phi entries
-    double phi1 = e1.eval(Pn);
-    if (lane < 21) phi1 += Si[lane];                       // + Mxx
-    else Si[lane] = phi1;                                  // lanes 21..31: G entries 21..31 (M_ux = 0)
-    double phix = 0.0;
-    if (lane < 8) {                                        // phi = g + [A B]' p_next
-      double v = Vi[V_G + lane];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) if (k < pcnt) v += pcf[k] * pn[prow0 + k];
-      if (lane < 6) phix = v; else T[T_PHIU + lane - 6] = v;
-    }
-    if (lane >= 21 && lane < 25) {                         // entries 32..35
-      double phi2 = e2.eval(Pn);
-      const int e = lane + 11;
-      if (e == 32) Si[32] = phi2;
-      else { if (e == 33) phi2 += Si[S_MUU]; else if (e == 35) phi2 += Si[S_MUU + 1]; T[T_PUU + e - 33] = phi2; }
-    }
+    // phase 1: Phi entries and phi
+    const double m1 = (lane < 21) ? Si[lane] : 0.0;                                            // + Mxx (M_ux = 0)
+    const double m2 = (lane == 1) ? Si[S_MUU] : (lane == 3) ? Si[S_MUU + 1] : 0.0;             // + Muu on entries 33, 35
+    const double gv = (lane < 8) ? Vi[V_G + lane] : 0.0;
+    const double phi1 = m1 + e1.eval(Pn);
+    const double phi2 = m2 + e2.eval(Pn);
+    const double phiv = fma(pcf[2], pn[prow0 + 2 < 6 ? prow0 + 2 : 5], fma(pcf[1], pn[prow0 + 1 < 6 ? prow0 + 1 : 5], fma(pcf[0], pn[prow0], gv)));
+    if (lane >= 21) Si[lane] = phi1;                       // G entries 21..31
+    if (lane == 0) Si[32] = phi2;                          // G entry 32
+    if (lane >= 1 && lane < 4) T[T_PUU + lane - 1] = phi2; // Phi_uu
+    if (lane == 6 || lane == 7) T[T_PHIU + lane - 6] = phiv;
     __syncwarp();
     // phase 2: Finv, P_i, p_i, k_i
     const double f00 = T[T_PUU], f10 = T[T_PUU + 1], f11 = T[T_PUU + 2];
+    const double pu0 = T[T_PHIU], pu1 = T[T_PHIU + 1];
+    const double g0a = Si[S_G + la], g1a = Si[S_G + 6 + la], g0b = Si[S_G + lb], g1b = Si[S_G + 6 + lb];
+    const double h0 = Si[S_G + l6], h1 = Si[S_G + 6 + l6];
     const double idet = fast_rcp(f00 * f11 - f10 * f10);
     const double i00 = f11 * idet, i10 = -f10 * idet, i11 = f00 * idet;
-    const double pu0 = T[T_PHIU], pu1 = T[T_PHIU + 1];
     const double k0 = -(i00 * pu0 + i10 * pu1), k1 = -(i10 * pu0 + i11 * pu1);
-    if (lane < 21) {
-      const double g0a = Si[S_G + e1.a], g1a = Si[S_G + 6 + e1.a], g0b = Si[S_G + e1.b], g1b = Si[S_G + 6 + e1.b];
-      const double w0 = i00 * g0b + i10 * g1b, w1 = i10 * g0b + i11 * g1b;
-      Pc[lane] = phi1 - (g0a * w0 + g1a * w1);
-    }
-    if (lane < 6) pc[lane] = phix + Si[S_G + lane] * k0 + Si[S_G + 6 + lane] * k1;
+    const double w0 = i00 * g0b + i10 * g1b, w1 = i10 * g0b + i11 * g1b;
+    if (lane < 21) Pc[lane] = phi1 - (g0a * w0 + g1a * w1);
+    if (lane < 6) pc[lane] = phiv + h0 * k0 + h1 * k1;
     if (lane == 31) { Si[S_FINV] = i00; Si[S_FINV + 1] = i10; Si[S_FINV + 2] = i11; Vi[V_K] = k0; Vi[V_K + 1] = k1; }
     __syncwarp();
   }
 }
+
+// stage record of the sweeps, fetched one stage ahead of its use (the compiler may not move the
+// shared-memory loads of stage i+1 above the stores of stage i by itself)
+struct SweepRec {
+  double G[12], F[3];
+  __device__ __forceinline__ void load(const double *Si) {
+#pragma unroll
+    for (int t = 0; t < 12; ++t) G[t] = Si[S_G + t];
+    F[0] = Si[S_FINV]; F[1] = Si[S_FINV + 1]; F[2] = Si[S_FINV + 2];
+  }
+};
 
 // vector-only backward sweep with a new gradient (V_G), all lanes redundantly
 __device__ __forceinline__ void riccati_vector(const WarpCtx &w) {
@@ -468,23 +515,32 @@ __device__ __forceinline__ void riccati_vector(const WarpCtx &w) {
   double pn[6];
 #pragma unroll
   for (int t = 0; t < 6; ++t) pn[t] = w.V[(N - 1) * V_STRIDE + V_G + t];
+  SweepRec cur, nxt;
+  double gcur[8], gnxt[8];
+  cur.load(w.S + (N - 2) * S_STRIDE);
+#pragma unroll
+  for (int t = 0; t < 8; ++t) gcur[t] = w.V[(N - 2) * V_STRIDE + V_G + t];
   for (int i = N - 2; i >= 0; --i) {
-    const double *Si = w.S + i * S_STRIDE;
-    double *Vi = w.V + i * V_STRIDE;
+    const int ip = (i > 0) ? i - 1 : 0;
+    nxt.load(w.S + ip * S_STRIDE);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) gnxt[t] = w.V[ip * V_STRIDE + V_G + t];
     double phi[8];
 #pragma unroll
     for (int ax = 0; ax < 2; ++ax) {
       const double pp = pn[3 * ax], pv = pn[3 * ax + 1], pa = pn[3 * ax + 2];
-      phi[3 * ax] = Vi[V_G + 3 * ax] + pp;
-      phi[3 * ax + 1] = Vi[V_G + 3 * ax + 1] + ts * pp + pv;
-      phi[3 * ax + 2] = Vi[V_G + 3 * ax + 2] + c2 * pp + ts * pv + pa;
-      phi[6 + ax] = Vi[V_G + 6 + ax] + c3 * pp + c2 * pv + ts * pa;
+      phi[3 * ax] = gcur[3 * ax] + pp;
+      phi[3 * ax + 1] = gcur[3 * ax + 1] + ts * pp + pv;
+      phi[3 * ax + 2] = gcur[3 * ax + 2] + c2 * pp + ts * pv + pa;
+      phi[6 + ax] = gcur[6 + ax] + c3 * pp + c2 * pv + ts * pa;
     }
-    const double i00 = Si[S_FINV], i10 = Si[S_FINV + 1], i11 = Si[S_FINV + 2];
-    const double k0 = -(i00 * phi[6] + i10 * phi[7]), k1 = -(i10 * phi[6] + i11 * phi[7]);
+    const double k0 = -(cur.F[0] * phi[6] + cur.F[1] * phi[7]), k1 = -(cur.F[1] * phi[6] + cur.F[2] * phi[7]);
 #pragma unroll
-    for (int t = 0; t < 6; ++t) pn[t] = phi[t] + Si[S_G + t] * k0 + Si[S_G + 6 + t] * k1;
-    if (w.lane == 6) { Vi[V_K] = k0; Vi[V_K + 1] = k1; }
+    for (int t = 0; t < 6; ++t) pn[t] = phi[t] + cur.G[t] * k0 + cur.G[6 + t] * k1;
+    if (w.lane == 6) { double *Vi = w.V + i * V_STRIDE; Vi[V_K] = k0; Vi[V_K + 1] = k1; }
+    cur = nxt;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) gcur[t] = gnxt[t];
   }
   __syncwarp();
 }
@@ -495,17 +551,22 @@ __device__ __forceinline__ void riccati_forward(const WarpCtx &w, int dst) {
   const int N = w.N;
   const double ts = p.ts, c2 = p.c2, c3 = p.c3;
   double dx[6] = {0, 0, 0, 0, 0, 0};
+  SweepRec cur, nxt;
+  double kc0, kc1, kn0, kn1;
+  cur.load(w.S);
+  kc0 = w.V[V_K]; kc1 = w.V[V_K + 1];
   for (int i = 0; i < N; ++i) {
     double *Vi = w.V + i * V_STRIDE;
+    const int in = (i + 1 < N - 1) ? i + 1 : 0;        // stage N-1 has no input: its record is never used
+    nxt.load(w.S + in * S_STRIDE);
+    kn0 = w.V[in * V_STRIDE + V_K]; kn1 = w.V[in * V_STRIDE + V_K + 1];
     double du0 = 0.0, du1 = 0.0;
     if (i < N - 1) {
-      const double *Si = w.S + i * S_STRIDE;
-      double t0 = 0.0, t1 = 0.0;
-#pragma unroll
-      for (int t = 0; t < 6; ++t) { t0 += Si[S_G + t] * dx[t]; t1 += Si[S_G + 6 + t] * dx[t]; }
-      const double i00 = Si[S_FINV], i10 = Si[S_FINV + 1], i11 = Si[S_FINV + 2];
-      du0 = Vi[V_K] - (i00 * t0 + i10 * t1);
-      du1 = Vi[V_K + 1] - (i10 * t0 + i11 * t1);
+      // two partial chains per row of G dx
+      const double t0 = (cur.G[0] * dx[0] + cur.G[1] * dx[1] + cur.G[2] * dx[2]) + (cur.G[3] * dx[3] + cur.G[4] * dx[4] + cur.G[5] * dx[5]);
+      const double t1 = (cur.G[6] * dx[0] + cur.G[7] * dx[1] + cur.G[8] * dx[2]) + (cur.G[9] * dx[3] + cur.G[10] * dx[4] + cur.G[11] * dx[5]);
+      du0 = kc0 - (cur.F[0] * t0 + cur.F[1] * t1);
+      du1 = kc1 - (cur.F[1] * t0 + cur.F[2] * t1);
     }
     {  // lane t < 8 stores component t (one predicated store instead of eight branches)
       double val = dx[0];
@@ -521,6 +582,7 @@ __device__ __forceinline__ void riccati_forward(const WarpCtx &w, int dst) {
       dx[3 * ax + 1] = Vv + ts * A + c2 * U;
       dx[3 * ax + 2] = A + ts * U;
     }
+    cur = nxt; kc0 = kn0; kc1 = kn1;
   }
   __syncwarp();
 }
@@ -532,26 +594,36 @@ struct QpResult {
   long rows;      // active rows x iterations (work counter)
 #ifdef MQ_PROF
   long long c_rows, c_factor, c_sweeps;   // clock64 cycles: row passes / Riccati factorisation / vector + forward sweeps
+  long long c_a, c_ared, c_d, c_e, c_g;   // split of c_rows: pass A visit, pass A reduce + epilogue + team reduce, D, E, G
 #endif
 };
 
-// Solves the node QP of w.dec.  On success V_Z holds the optimal stage vectors.
+// Solves the node QP of w.dec; called by every thread of the team with identical arguments.  On
+// success V_Z holds the optimal stage vectors.  All control decisions derive from team_reduce results,
+// which are bitwise identical in every thread, so the barriers inside stay uniform.
 __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEntry &e1, const PhiEntry &e2) {
   const DevProb &p = *w.p;
   const double *D = w.D;
-  const int lane = w.lane, N = w.N;
+  const int N = w.N;
+  const bool lead = (w.g == 0);
   QpResult res; res.status = 1; res.iters = 0; res.obj = 0.0; res.rows = 0;
 #ifdef MQ_PROF
-  res.c_rows = res.c_factor = res.c_sweeps = 0;
+  res.c_rows = res.c_factor = res.c_sweeps = 0; res.c_a = res.c_ared = res.c_d = res.c_e = res.c_g = 0;
+  long long qc0 = 0;
+#define MQ_T0 qc0 = clock64();
+#define MQ_T1(field) res.field += clock64() - qc0;
   long long pc0 = clock64(), pc1;
 #define MQ_TICK(field) { pc1 = clock64(); res.field += pc1 - pc0; pc0 = pc1; }
 #else
 #define MQ_TICK(field)
+#define MQ_T0
+#define MQ_T1(field)
 #endif
 
-  // trivially infeasible boxes (build_node_qp of the oracle)
-  int bad = 0;
-  for (int i = lane; i < N; i += 32) {
+  // trivially infeasible boxes (build_node_qp of the oracle); cn = largest linear cost coefficient
+  double bad = 0.0, cn = 0.0, z0 = 0.0, z1 = 0.0;
+  MQ_FOR_STAGES(i, act) {
+    if (!act || !lead) continue;
     const unsigned char m = (i > 0) ? w.dec[p.off_mode + i] : (unsigned char)0;
     double lo[8], hi[8];
     stage_bounds(w, i, w.jeff[i], i > 0 && m == MODE_FROZEN, lo, hi);
@@ -559,93 +631,119 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
     for (int t = 1; t < 8; ++t) {
       if (t == Y_PY) continue;
       if (i == 0 && t < 6) continue;
-      if (lo[t] > hi[t] + 1e-12) bad = 1;
-      if (i == N - 1 && t >= 6 && (lo[t] > 1e-9 || hi[t] < -1e-9)) bad = 1;
+      if (lo[t] > hi[t] + 1e-12) bad = 1.0;
+      if (i == N - 1 && t >= 6 && (lo[t] > 1e-9 || hi[t] < -1e-9)) bad = 1.0;
     }
-  }
-  if (__any_sync(FULL, bad)) return res;
-
-  // start: zero jerk (free response), s = max(h - g.z, 1), lambda = 1
-  const double x0[6] = {D[p.o_x0], D[p.o_x0 + 1], D[p.o_x0 + 2], D[p.o_x0 + 3], D[p.o_x0 + 4], D[p.o_x0 + 5]};
-  double cn = 0.0;
-  for (int i = lane; i < N; i += 32) {
-    double *Vi = w.V + i * V_STRIDE;
-    const double t = i * p.ts;
-    PassInit v; v.io.init(w.rows, N, i);
-#pragma unroll
-    for (int ax = 0; ax < 2; ++ax) {
-      const double P = x0[3 * ax], Vv = x0[3 * ax + 1], A = x0[3 * ax + 2];
-      v.y[3 * ax] = P + t * Vv + 0.5 * t * t * A;
-      v.y[3 * ax + 1] = Vv + t * A;
-      v.y[3 * ax + 2] = A;
-    }
-    v.y[6] = 0.0; v.y[7] = 0.0;
-#pragma unroll
-    for (int t8 = 0; t8 < 8; ++t8) { Vi[V_Z + t8] = v.y[t8]; Vi[V_DZ + t8] = 0.0; Vi[V_DZA + t8] = 0.0; }
     const double *cst = D + p.o_cost + 16 * i;
 #pragma unroll
     for (int t8 = 0; t8 < 8; ++t8) cn = fmax(cn, fabs(cst[8 + t8]));
-    visit_rows(w, i, v);
   }
-  cn = warp_max(cn);
-  __syncwarp();
+  team_reduce(w, bad, cn, z0, z1);
+  if (bad > 0.0) return res;
+
+  // start: zero jerk (free response), s = max(h - g.z, 1), lambda = 1
+  const double x0[6] = {D[p.o_x0], D[p.o_x0 + 1], D[p.o_x0 + 2], D[p.o_x0 + 3], D[p.o_x0 + 4], D[p.o_x0 + 5]};
+  double rdn = 0.0;
+  MQ_FOR_STAGES(i, act) {
+    PassInit v; v.io.init(w.rows, w.NP, act ? i : 0);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) v.gl[t] = 0.0;
+    if (act) {
+      const double t = i * p.ts;
+#pragma unroll
+      for (int ax = 0; ax < 2; ++ax) {
+        const double P = x0[3 * ax], Vv = x0[3 * ax + 1], A = x0[3 * ax + 2];
+        v.y[3 * ax] = P + t * Vv + 0.5 * t * t * A;
+        v.y[3 * ax + 1] = Vv + t * A;
+        v.y[3 * ax + 2] = A;
+      }
+      v.y[6] = 0.0; v.y[7] = 0.0;
+      visit_rows(w, i, v);
+    }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) v.gl[t] = sg_sum(w, v.gl[t]);
+    if (act && lead) {
+      double *Vi = w.V + i * V_STRIDE;
+      const double *cst = D + p.o_cost + 16 * i;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        Vi[V_Z + t] = v.y[t]; Vi[V_DZ + t] = 0.0; Vi[V_DZA + t] = 0.0;
+        // dual residual at the start (all dynamics multipliers zero); it contracts by (1 - alpha)
+        // with every Newton step afterwards
+        if ((t < 6 && i > 0) || (t >= 6 && i < N - 1)) rdn = fmax(rdn, fabs(cst[t] * v.y[t] + cst[8 + t] + v.gl[t]));
+      }
+    }
+  }
+  { double q0 = 0.0, q1 = 0.0, q2 = 0.0; team_reduce(w, rdn, q0, q1, q2); }
 
   StepCtx sc; sc.alpha = 0.0; sc.sigmu = 0.0; sc.pending = false;
   int status = 2, stall = 0, it = 0;
-  double rdn = 0.0;
   for (it = 0; it < 100; ++it) {
     // ---- pass A ----
-    double rpn = 0.0, musum = 0.0, lmax = 0.0, rd0 = 0.0; int m = 0;
-    for (int i = lane; i < N; i += 32) {
-      double *Vi = w.V + i * V_STRIDE, *Si = w.S + i * S_STRIDE;
-      PassA v; v.io.init(w.rows, N, i); v.sc = sc;
+    double rpn = 0.0, musum = 0.0, lmax = 0.0, mcount = 0.0;
+    MQ_FOR_STAGES(i, act) {
+      PassA v; v.io.init(w.rows, w.NP, act ? i : 0); v.sc = sc;
       v.rpn = 0.0; v.musum = 0.0; v.lmax = 0.0; v.m = 0;
 #pragma unroll
       for (int t = 0; t < 21; ++t) v.H[t] = 0.0;
       v.Huu[0] = v.Huu[1] = 0.0;
 #pragma unroll
-      for (int t = 0; t < 8; ++t) { v.y[t] = Vi[V_Z + t]; v.d[t] = Vi[V_DZ + t]; v.da[t] = Vi[V_DZA + t]; v.gx[t] = 0.0; v.gl[t] = 0.0; }
-      visit_rows(w, i, v);
-      const double *cst = D + p.o_cost + 16 * i;
+      for (int t = 0; t < 8; ++t) v.gx[t] = 0.0;
+      if (act) {
+        const double *Vi = w.V + i * V_STRIDE;
 #pragma unroll
-      for (int t = 0; t < 6; ++t) v.H[t * (t + 1) / 2 + t] += cst[t];
-#pragma unroll
-      for (int t = 0; t < 21; ++t) Si[t] = v.H[t];
-      Si[S_MUU] = v.Huu[0] + cst[6] + 1e-10; Si[S_MUU + 1] = v.Huu[1] + cst[7] + 1e-10;
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const double q = cst[t] * v.y[t] + cst[8 + t];
-        Vi[V_G + t] = q + v.gx[t];
-        // dual residual at the start (all dynamics multipliers zero); it contracts by
-        // (1 - alpha) with every Newton step afterwards
-        if (it == 0 && ((t < 6 && i > 0) || (t >= 6 && i < N - 1))) rd0 = fmax(rd0, fabs(q + v.gl[t]));
+        for (int t = 0; t < 8; ++t) { v.y[t] = Vi[V_Z + t]; v.d[t] = Vi[V_DZ + t]; v.da[t] = Vi[V_DZA + t]; }
+        MQ_T0
+        visit_rows(w, i, v);
+        MQ_T1(c_a)
       }
-      rpn = fmax(rpn, v.rpn); musum += v.musum; lmax = fmax(lmax, v.lmax); m += v.m;
+      MQ_T0
+#pragma unroll
+      for (int t = 0; t < 21; ++t) v.H[t] = sg_sum(w, v.H[t]);
+      v.Huu[0] = sg_sum(w, v.Huu[0]); v.Huu[1] = sg_sum(w, v.Huu[1]);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) v.gx[t] = sg_sum(w, v.gx[t]);
+      if (act && lead) {
+        double *Vi = w.V + i * V_STRIDE, *Si = w.S + i * S_STRIDE;
+        const double *cst = D + p.o_cost + 16 * i;
+#pragma unroll
+        for (int t = 0; t < 6; ++t) v.H[t * (t + 1) / 2 + t] += cst[t];
+#pragma unroll
+        for (int t = 0; t < 21; ++t) Si[t] = v.H[t];
+        Si[S_MUU] = v.Huu[0] + cst[6] + 1e-10; Si[S_MUU + 1] = v.Huu[1] + cst[7] + 1e-10;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) Vi[V_G + t] = cst[t] * v.y[t] + cst[8 + t] + v.gx[t];
+      }
+      rpn = fmax(rpn, v.rpn); musum += v.musum; lmax = fmax(lmax, v.lmax); mcount += (double)v.m;
     }
     sc.pending = false;
-    rpn = warp_max(rpn); lmax = warp_max(lmax); musum = warp_sum(musum); m = warp_sum_i(m);
-    if (it == 0) rdn = warp_max(rd0);
+    team_reduce(w, rpn, lmax, musum, mcount);
+    MQ_T1(c_ared)
+    const long m = (long)mcount;
     res.rows += m;
     const double mu = (m > 0) ? musum / m : 0.0;
-    __syncwarp();
     if (rpn <= 1e-9 && rdn <= 1e-8 * (1.0 + cn) && mu <= 1e-10) { status = 0; break; }
     if (lmax > 1e13) { status = 1; break; }
     // ---- predictor ----
     MQ_TICK(c_rows)
-    riccati_factor(w, e1, e2);
+    if (w.wid == 0) riccati_factor(w, e1, e2);
     MQ_TICK(c_factor)
-    riccati_forward(w, V_DZA);
+    if (w.wid == 0) riccati_forward(w, V_DZA);
+    __syncthreads();
     MQ_TICK(c_sweeps)
-    double rmax = 1.0, s1 = 0.0, s2 = 0.0;
-    for (int i = lane; i < N; i += 32) {
+    double rmax = 1.0, s1 = 0.0, s2 = 0.0, dummy = 0.0;
+    MQ_T0
+    MQ_FOR_STAGES(i, act) {
+      if (!act) continue;
       const double *Vi = w.V + i * V_STRIDE;
-      PassD v; v.io.init(w.rows, N, i); v.rmax = 1.0; v.s1 = 0.0; v.s2 = 0.0;
+      PassD v; v.io.init(w.rows, w.NP, i); v.rmax = 1.0; v.s1 = 0.0; v.s2 = 0.0;
 #pragma unroll
       for (int t = 0; t < 8; ++t) { v.y[t] = Vi[V_Z + t]; v.da[t] = Vi[V_DZA + t]; }
       visit_rows(w, i, v);
       rmax = fmax(rmax, v.rmax); s1 += v.s1; s2 += v.s2;
     }
-    rmax = warp_max(rmax); s1 = warp_sum(s1); s2 = warp_sum(s2);
+    team_reduce(w, rmax, dummy, s1, s2);
+    MQ_T1(c_d)
     double amin = 1.0 / rmax;
     double sigma = 0.0;
     if (m > 0 && mu > 0.0) {
@@ -657,70 +755,88 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
     }
     const double sigmu = sigma * mu;
     // ---- corrector ----
-    for (int i = lane; i < N; i += 32) {
-      double *Vi = w.V + i * V_STRIDE;
-      PassE v; v.io.init(w.rows, N, i); v.sigmu = sigmu;
+    MQ_T0
+    MQ_FOR_STAGES(i, act) {
+      PassE v; v.io.init(w.rows, w.NP, act ? i : 0); v.sigmu = sigmu;
 #pragma unroll
-      for (int t = 0; t < 8; ++t) { v.y[t] = Vi[V_Z + t]; v.da[t] = Vi[V_DZA + t]; v.gx[t] = 0.0; }
-      visit_rows(w, i, v);
-      const double *cst = D + p.o_cost + 16 * i;
+      for (int t = 0; t < 8; ++t) v.gx[t] = 0.0;
+      if (act) {
+        const double *Vi = w.V + i * V_STRIDE;
 #pragma unroll
-      for (int t = 0; t < 8; ++t) Vi[V_G + t] = cst[t] * v.y[t] + cst[8 + t] + v.gx[t];
+        for (int t = 0; t < 8; ++t) { v.y[t] = Vi[V_Z + t]; v.da[t] = Vi[V_DZA + t]; }
+        visit_rows(w, i, v);
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) v.gx[t] = sg_sum(w, v.gx[t]);
+      if (act && lead) {
+        double *Vi = w.V + i * V_STRIDE;
+        const double *cst = D + p.o_cost + 16 * i;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) Vi[V_G + t] = cst[t] * v.y[t] + cst[8 + t] + v.gx[t];
+      }
     }
-    __syncwarp();
+    __syncthreads();
+    MQ_T1(c_e)
     MQ_TICK(c_rows)
-    riccati_vector(w);
-    riccati_forward(w, V_DZ);
+    if (w.wid == 0) { riccati_vector(w); riccati_forward(w, V_DZ); }
+    __syncthreads();
     MQ_TICK(c_sweeps)
     rmax = 0.0;
-    bool bad_step = false;
-    for (int i = lane; i < N; i += 32) {
+    double bad_step = 0.0; s1 = 0.0; s2 = 0.0;
+    MQ_T0
+    MQ_FOR_STAGES(i, act) {
+      if (!act) continue;
       const double *Vi = w.V + i * V_STRIDE;
-      PassG v; v.io.init(w.rows, N, i); v.sigmu = sigmu; v.rmax = 0.0;
+      PassG v; v.io.init(w.rows, w.NP, i); v.sigmu = sigmu; v.rmax = 0.0;
 #pragma unroll
       for (int t = 0; t < 8; ++t) { v.y[t] = Vi[V_Z + t]; v.d[t] = Vi[V_DZ + t]; v.da[t] = Vi[V_DZA + t]; }
-      bad_step |= !(fabs(v.d[Y_UX]) + fabs(v.d[Y_UY]) + fabs(v.d[Y_PX]) + fabs(v.d[Y_PY]) < 1e300);  // NaN / inf step
+      if (!(fabs(v.d[Y_UX]) + fabs(v.d[Y_UY]) + fabs(v.d[Y_PX]) + fabs(v.d[Y_PY]) < 1e300)) bad_step = 1.0;  // NaN / inf step
       visit_rows(w, i, v);
       rmax = fmax(rmax, v.rmax);
     }
-    rmax = warp_max(rmax);
-    if (__any_sync(FULL, bad_step)) { status = 2; break; }  // singular stage system
+    team_reduce(w, rmax, bad_step, s1, s2);
+    MQ_T1(c_g)
+    if (bad_step > 0.0) { status = 2; break; }  // singular stage system
     double alpha = (rmax > 0.995) ? 0.995 / rmax : 1.0;
     sc.alpha = alpha; sc.sigmu = sigmu; sc.pending = true;
     rdn *= (1.0 - alpha);
-    for (int i = lane; i < N; i += 32) {   // z += alpha dz (rows are updated lazily by the next pass A)
+    MQ_FOR_STAGES(i, act) {   // z += alpha dz (rows are updated lazily by the next pass A)
+      if (!act || !lead) continue;
       double *Vi = w.V + i * V_STRIDE;
 #pragma unroll
       for (int t = 0; t < 8; ++t) Vi[V_Z + t] += alpha * Vi[V_DZ + t];
     }
-    __syncwarp();
+    __syncthreads();
     if (alpha < 1e-6) { if (++stall >= 5) { status = 2; break; } } else stall = 0;
   }
   res.iters = it;
   MQ_TICK(c_rows)
   if (status != 0) {
     // not converged: infeasible only if the primal point violates its rows
-    double worst = 0.0;
-    for (int i = lane; i < N; i += 32) {
+    double worst = 0.0, nanflag = 0.0, q0 = 0.0, q1 = 0.0;
+    MQ_FOR_STAGES(i, act) {
+      if (!act) continue;
       PassViol v; v.worst = 0.0;
 #pragma unroll
       for (int t = 0; t < 8; ++t) v.y[t] = w.V[i * V_STRIDE + V_Z + t];
       visit_rows(w, i, v);
+      if (!(v.worst == v.worst)) nanflag = 1.0;
       worst = fmax(worst, v.worst);
     }
-    worst = warp_max(worst);
-    status = (worst > 1e-7 || !(worst == worst)) ? 1 : 0;
+    team_reduce(w, worst, nanflag, q0, q1);
+    status = (worst > 1e-7 || nanflag > 0.0) ? 1 : 0;
   }
   res.status = status;
   if (status == 0) {
-    double o = 0.0;
-    for (int i = lane; i < N; i += 32) {
+    double o = 0.0, q0 = 0.0, q1 = 0.0, q2 = 0.0;
+    MQ_FOR_STAGES(i, act) {
+      if (!act || !lead) continue;
       const double *cst = D + p.o_cost + 16 * i;
       const double *z = w.V + i * V_STRIDE + V_Z;
 #pragma unroll
       for (int t = 0; t < 8; ++t) o += (0.5 * cst[t] * z[t] + cst[8 + t]) * z[t];
     }
-    o = warp_sum(o);
+    team_reduce(w, q0, q1, o, q2);
     res.obj = o + p.cost_const;
   }
   return res;

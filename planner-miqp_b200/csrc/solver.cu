@@ -87,7 +87,6 @@ struct MiqpB200Solver {
   long multi_ws_bytes = 0;
   DevBuf<double> b_multi_ws;
   DevBuf<int2> b_work2;
-  DevBuf<double2> b_rows_ws;
   bool uploaded = false, ran = false;
   double last_seconds = 0.0;
   bool timed_out = false;
@@ -158,14 +157,14 @@ void setup_bnb(MiqpB200Solver *s) {
   s->single_maxN = std::max(maxN1, 2);
   st.nwarps = 0; s->ctas = 0; s->multi_ctas = 0;
   if (s->n_single > 0) {
-    s->smem_per_warp = node_kernel_smem_per_warp(s->single_maxN, st.kmax, st.ndec_stride);
-    s->warps_per_cta = 1;
-    const int per_sm = node_kernel_max_ctas(s->smem_per_warp * s->warps_per_cta, s->warps_per_cta * 32);
+    s->smem_per_warp = node_kernel_smem_per_warp(s->single_maxN, st.kmax, st.ndec_stride);   // per node (one team)
+    s->warps_per_cta = NODE_TEAM_WARPS;
+    const int per_sm = node_kernel_max_ctas(s->smem_per_warp, s->warps_per_cta * 32);
     if (per_sm <= 0) throw std::runtime_error("node kernel does not fit in shared memory for this horizon");
     s->ctas = per_sm * s->num_sms;
-    st.nwarps += s->ctas * s->warps_per_cta;
-    s->b_rows_ws.ensure((size_t)s->ctas * s->warps_per_cta * (size_t)(st.kmax + 1) * s->single_maxN);
-    st.rows_ws = s->b_rows_ws.p;
+    int fm = 1;
+    if (const char *e = getenv("MIQP_FILL_MULT")) fm = std::max(1, atoi(e));
+    st.nwarps += s->ctas * fm;
   }
   if (s->n_multi > 0) {
     s->multi_threads = (maxCm <= 2) ? 64 : 128;
@@ -186,7 +185,7 @@ void setup_bnb(MiqpB200Solver *s) {
   if (K <= 0) { K = (st.nwarps + count - 1) / count; if (K < 1) K = 1; if (K > 64) K = 64; }
   st.sel_base = K;
   st.sel_dive = std::max(1, std::min(8, st.nwarps / std::max(count, 1)));   // several dive heads only when warps would idle
-  st.dive_fill = 4;   // A/B on 2048 config-2 plans: 0 -> 347 ms (120 rounds), 2 -> 234 ms, 4 -> 224 ms (62 rounds)
+  st.dive_fill = 2;   // A/B on 2048 config-2 plans (profiles/r1i, r1k): one dive head 347 ms / 120 rounds; widened dive 143 ms / 53 rounds
   if (const char *e = getenv("MIQP_DIVE_FILL")) st.dive_fill = atoi(e);
   int KS = std::max(K, std::min(64, std::max(1, st.nwarps)));
   st.sel_per_plan = KS;
@@ -194,7 +193,10 @@ void setup_bnb(MiqpB200Solver *s) {
   int cap = s->opt.pool_capacity;
   if (cap <= 0) {
     const size_t node_bytes = (size_t)st.ndec_stride + 48;
-    size_t budget = (size_t)8 << 30;  // 8 GiB of pool by default
+    // pool budget: a third of the free HBM, at most 48 GiB (B200: 180 GB per GPU)
+    size_t free_b = 0, total_b = 0;
+    size_t budget = (size_t)8 << 30;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) budget = std::min<size_t>(free_b / 3, (size_t)48 << 30);
     size_t c = budget / (node_bytes * (size_t)count);
     if (c > (1u << 20)) c = 1u << 20;
     if (c < 256) c = 256;
@@ -286,7 +288,7 @@ void miqp_b200_destroy(MiqpB200Solver *s) {
   s->b_pruned.release(); s->b_incz.release(); s->b_meta.release(); s->b_work.release();
   s->b_uid.release(); s->b_keybuf.release(); s->b_incuid.release(); s->b_stats.release(); s->b_open.release();
   s->b_opencnt.release(); s->b_free.release(); s->b_freecnt.release(); s->b_sel.release(); s->b_selcnt.release();
-  s->b_done.release(); s->b_lock.release(); s->b_ctrl.release(); s->b_multi_ws.release(); s->b_work2.release(); s->b_rows_ws.release();
+  s->b_done.release(); s->b_lock.release(); s->b_ctrl.release(); s->b_multi_ws.release(); s->b_work2.release();
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   if (s->evr0) cudaEventDestroy(s->evr0);

@@ -106,7 +106,10 @@ static void gpu_part() {
   SolutionProperties sp = planner.GetSolutionProperties();
   CHECK(sp.status == 101 || sp.status == 102);
   CHECK(sp.gap <= 1e-4 && sp.max_violation <= 1e-6 && sp.NrSolutionPool == 1);
-  CHECK(sp.NrBinaryVariables == 5 * 20 + 16 * 20 + 5 * 20 && sp.NrFloatVariables == 240 && sp.NrConstraints > 8944);
+  CHECK(sp.NrBinaryVariables == 5 * 20 + 16 * 20 + 5 * 20);
+  CHECK(sp.NrFloatVariables == 240);
+  if (!(sp.NrConstraints > 8944)) std::printf("NrConstraints %d nnz %d\n", sp.NrConstraints, sp.NonZeroCoefficients);
+  CHECK(sp.NrConstraints > 8944);
   auto rr = planner.GetSolution();
   CHECK(rr->N == 20 && rr->NrCars == 1 && rr->pos_x(0, 0) == 0.0 && rr->active_region(0, 0, 0) == 1);
   for (int i = 0; i < 20; ++i) { int sum = 0; for (int j = 0; j < 16; ++j) sum += rr->active_region(0, i, j); CHECK(sum == 1); }
