@@ -128,9 +128,10 @@ __global__ void __launch_bounds__(SEL_THREADS) bnb_select_kernel(BnbState st, co
     K = st.sel_base;
     if (fill > K) K = fill;
     if (K > KS) K = KS;
-  } else if (st.dive_fill > 0) {
-    const int kd = fill / st.dive_fill;
-    if (kd > K) K = kd;
+  } else {
+    if (st.dive_fill > 0) { const int kd = fill / st.dive_fill; if (kd > K) K = kd; }
+    // still no incumbent long after the typical plan has finished its dive: a hard plan, widen its beam
+    if (st.dive_patience > 0 && round > st.dive_patience) { const int kp = (round - st.dive_patience) * st.dive_growth; if (kp > K) K = kp; }
     if (K > KS) K = KS;
   }
   __syncthreads();
@@ -163,6 +164,9 @@ __global__ void __launch_bounds__(SEL_THREADS) bnb_select_kernel(BnbState st, co
     for (int k = 0; k < SEL_THREADS / 32; ++k) pm = fmin(pm, s_pruned[k]);
     st.pruned_lb[s] = pm;
   }
+  // a plan whose frontier stays large after pruning is a hard one: let it run wide even while the easy
+  // plans still fill the machine (its sequential depth, not the node count, is what ends the batch)
+  if (have_inc && st.wide_div > 0) { int kw = n1 / st.wide_div; if (kw > KS) kw = KS; if (kw > K) K = kw; }
   // 4. threshold key of the K best
   unsigned long long T = ~0ULL; int remaining = n1;  // take everything
   if (n1 > K) {

@@ -26,6 +26,8 @@ struct BnbState {
   int sel_base;         // nodes per plan per round once an incumbent exists (raised when few plans are active)
   int sel_dive;         // nodes per plan per round while diving for the first incumbent
   int dive_fill;        // >0: while diving, widen to (resident warps / active plans) / dive_fill heads when few plans are active
+  int wide_div;         // >0: a plan with an incumbent takes at least (open nodes below the cutoff) / wide_div nodes per round
+  int dive_patience, dive_growth;   // a plan without incumbent after dive_patience rounds widens its dive by dive_growth heads per round
   int work_cap;
   int force_multi;      // route every plan to the CTA-per-node kernel (test hook)
   // node pools [count][cap]

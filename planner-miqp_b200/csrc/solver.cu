@@ -187,7 +187,14 @@ void setup_bnb(MiqpB200Solver *s) {
   st.sel_dive = std::max(1, std::min(8, st.nwarps / std::max(count, 1)));   // several dive heads only when warps would idle
   st.dive_fill = 2;   // A/B on 2048 config-2 plans (profiles/r1i, r1k): one dive head 347 ms / 120 rounds; widened dive 143 ms / 53 rounds
   if (const char *e = getenv("MIQP_DIVE_FILL")) st.dive_fill = atoi(e);
-  int KS = std::max(K, std::min(64, std::max(1, st.nwarps)));
+  st.wide_div = 0;
+  if (const char *e = getenv("MIQP_WIDE_DIV")) st.wide_div = atoi(e);
+  st.dive_patience = 14; st.dive_growth = 8;   // profiles/r1k: batch 1024 139 -> 80 ms, batch 2048 unchanged (144 ms, 53 -> 38 rounds)
+  if (const char *e = getenv("MIQP_DIVE_PATIENCE")) st.dive_patience = atoi(e);
+  if (const char *e = getenv("MIQP_DIVE_GROWTH")) st.dive_growth = atoi(e);
+  int kscap = 64;
+  if (const char *e = getenv("MIQP_KS")) kscap = std::max(1, atoi(e));
+  int KS = std::max(K, std::min(kscap, std::max(1, st.nwarps)));
   st.sel_per_plan = KS;
   // pool capacity per plan
   int cap = s->opt.pool_capacity;
