@@ -270,7 +270,7 @@ def main():
         "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": traffic,
         "peak_source": "DFMA micro-benchmark in this run (MEASURED_PEAKS.json has no FP64 figure)",
         "kernel_share_of_step": node_ms / total_ms if total_ms else None,
-        "note": "latency-bound FP64 kernel (one warp per node relaxation, serial Riccati sweeps); see DESIGN.md",
+        "note": "latency-bound FP64 kernel (one CTA of four warps per node relaxation, sequential Riccati recursion on one warp); see DESIGN.md section 4",
         "hbm": {"achieved": hbm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": hbm_gbs / peaks["hbm_gbs"] if peaks["hbm_gbs"] else None, "peak_source": peaks["source"]},
         "nodes_per_s": st["nodes"] / (node_ms_last * 1e-3) if node_ms_last > 0 else None,
