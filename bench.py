@@ -172,6 +172,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the MIQP backend has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL_DEBUG=VERSION prints there)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     import planner_miqp_b200 as P

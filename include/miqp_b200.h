@@ -163,6 +163,8 @@ int miqp_b200_run_stats(const MiqpB200Solver *s, MiqpB200RunStats *out);
  * clock64 cycles in row passes / Riccati factorisation / vector sweeps / whole node solves,
  * out256[132..133] infeasible node relaxations and their iterations. */
 int miqp_b200_debug_profile(MiqpB200Solver *s, unsigned long long *out256);
+/* -DMQ_PROF builds: per-iteration (alpha, mu, primal residual, sigma, lambda max) of up to 8 slow node relaxations, [8][512] */
+int miqp_b200_debug_traces(MiqpB200Solver *s, double *out4096);
 
 /* FP64 FMA throughput of the device in TFLOP/s (DFMA micro-benchmark, best of 5): the
  * roofline denominator of the node kernel, which MEASURED_PEAKS.json does not provide. */

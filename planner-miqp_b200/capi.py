@@ -22,7 +22,7 @@ DECLARED_SYMBOLS = [
     "miqp_b200_last_error", "miqp_b200_layout", "miqp_b200_sizes", "miqp_b200_assemble",
     "miqp_b200_evaluate", "miqp_b200_solve_batch", "miqp_b200_batch_upload", "miqp_b200_batch_run",
     "miqp_b200_batch_fetch", "miqp_b200_run_stats", "miqp_b200_measure_fp64_peak",
-    "miqp_b200_debug_profile",
+    "miqp_b200_debug_profile", "miqp_b200_debug_traces",
 ]
 
 
@@ -128,6 +128,7 @@ def load_library():
     lib.miqp_b200_run_stats.argtypes = [C.c_void_p, C.POINTER(CRunStats)]
     lib.miqp_b200_measure_fp64_peak.argtypes = [C.c_void_p, _dp]
     lib.miqp_b200_debug_profile.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong)]
+    lib.miqp_b200_debug_traces.argtypes = [C.c_void_p, _dp]
     _lib = lib
     return lib
 
@@ -354,6 +355,12 @@ class Solver:
         st = CRunStats()
         self._check(self._lib.miqp_b200_run_stats(self._h, C.byref(st)), "miqp_b200_run_stats")
         return {n: getattr(st, n) for n, _ in CRunStats._fields_}
+
+    def debug_traces(self):
+        import numpy as _np
+        out = _np.zeros(4096)
+        self._check(self._lib.miqp_b200_debug_traces(self._h, out.ctypes.data_as(_dp)), "miqp_b200_debug_traces")
+        return out.reshape(8, 512)
 
     def debug_profile(self):
         out = (C.c_ulonglong * 256)()

@@ -67,6 +67,7 @@ __global__ void bnb_init_kernel(BnbState st, const DevProb *probs, const unsigne
       st.bound[pb + 1] = -MQ_INF; st.meta[pb + 1] = make_int2(1 << 20, 0); st.uid[pb + 1] = 2ULL;   // rank -1: before the root
       st.open_idx[pb + 1] = 1;
     }
+    if (st.zpool) for (int r = 0; r < nroot; ++r) st.zpool[(pb + r) * (long)st.zp_stride] = __longlong_as_double(0x7ff8000000000000LL);   // no parent: cold start
     st.open_cnt[s] = nroot;
     st.sel_cnt[s] = 0;
     st.ub[s] = MQ_INF; st.cutoff[s] = MQ_INF; st.pruned_lb[s] = MQ_INF;
@@ -515,8 +516,11 @@ int node_kernel_smem_per_warp(int maxN, int kmax, int ndec_stride) { return node
 // One CTA = one team of NODE_TEAM_WARPS warps = one node relaxation at a time (persistent: teams pull
 // (plan, node) items from the round's work list).  255 registers x 128 threads x 2 CTAs fill the
 // register file of an SM; the third CTA that shared memory would allow (57 kB per node at N = 40) does not fit.
-__global__ void __launch_bounds__(NODE_TEAM_WARPS * 32, 2) bnb_nodes_kernel(BnbState st, const DevProb *probs, const double *dblob,
-                                                                             const int *iblob, int smem_per_node, int maxN, int round) {
+// NW = 8 (one CTA per SM, 6 sub-lanes per stage at N = 40) is launched for rounds that hold fewer nodes than SMs: the
+// round time is then the latency of its slowest node, and the wider team shortens the row passes.
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, NW == NODE_TEAM_WARPS ? 2 : 1) bnb_nodes_kernel(BnbState st, const DevProb *probs, const double *dblob,
+                                                                                            const int *iblob, int smem_per_node, int maxN, int round) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double s_red[32];
   __shared__ int s_wi;
@@ -525,6 +529,10 @@ __global__ void __launch_bounds__(NODE_TEAM_WARPS * 32, 2) bnb_nodes_kernel(BnbS
   const NodeSmem L = node_smem_layout(maxN, st.kmax, st.ndec_stride);
   WarpCtx w;
   w.D = dblob; w.I = iblob; w.lane = lane; w.wid = wid; w.nw = nw; w.red = s_red;
+  w.dbgrow = nullptr;
+#ifdef MQ_PROF
+  if (st.dbg && blockIdx.x < 1024) w.dbgrow = st.dbg + (size_t)blockIdx.x * 512;
+#endif
   w.S = reinterpret_cast<double *>(base);
   w.V = w.S + maxN * S_STRIDE;
   w.T = w.V + maxN * V_STRIDE;
@@ -569,7 +577,9 @@ __global__ void __launch_bounds__(NODE_TEAM_WARPS * 32, 2) bnb_nodes_kernel(BnbS
 #ifdef MQ_PROF
     const long long pt0 = clock64();
 #endif
-    QpResult r = solve_node_qp(w, e1, e2);
+    const double *zw = st.zpool ? st.zpool + (pb + slot) * (long)st.zp_stride : nullptr;
+    if (zw && !(zw[0] == zw[0])) zw = nullptr;   // NaN marks a node without parent optimum
+    QpResult r = solve_node_qp(w, e1, e2, zw, st.warm_mu);
     if (wid != 0) continue;
     // ---- warp 0: bookkeeping, scan of the relaxed optimum, children ----
     const double nbound = st.bound[pb + slot];
@@ -582,6 +592,10 @@ __global__ void __launch_bounds__(NODE_TEAM_WARPS * 32, 2) bnb_nodes_kernel(BnbS
       atomicAdd(&st.prof[128], (unsigned long long)r.c_rows); atomicAdd(&st.prof[129], (unsigned long long)r.c_factor);
       atomicAdd(&st.prof[130], (unsigned long long)r.c_sweeps); atomicAdd(&st.prof[131], (unsigned long long)(clock64() - pt0));
       if (r.status != 0) { atomicAdd(&st.prof[132], 1ULL); atomicAdd(&st.prof[133], (unsigned long long)r.iters); atomicAdd(&st.prof[150 + (r.iters > 100 ? 100 : r.iters)], 1ULL); }
+      if (w.dbgrow && r.iters >= 30 && r.status == 0) {   // keep the traces of the first eight slow feasible relaxations
+        const unsigned long long k = atomicAdd(&st.prof[140], 1ULL);
+        if (k < 8) { double *dst = st.dbg + (size_t)(1024 + k) * 512; dst[0] = r.iters; dst[1] = r.obj; dst[2] = nmeta.x; for (int q = 8; q < 8 + 5 * 100; ++q) dst[q] = w.dbgrow[q]; }
+      }
       atomicAdd(&st.prof[134], (unsigned long long)r.c_a); atomicAdd(&st.prof[135], (unsigned long long)r.c_ared); atomicAdd(&st.prof[136], (unsigned long long)r.c_d);
       atomicAdd(&st.prof[137], (unsigned long long)r.c_e); atomicAdd(&st.prof[138], (unsigned long long)r.c_g);
     }
@@ -670,6 +684,10 @@ __global__ void __launch_bounds__(NODE_TEAM_WARPS * 32, 2) bnb_nodes_kernel(BnbS
       const int cs = st.free_stack[pb + fbase + a];
       unsigned char *dst = st.dec + (pb + cs) * st.ndec_stride;
       copy_bytes16(dst, src, st.ndec_stride, lane);
+      if (st.zpool) {   // the child starts its interior-point solve from this node's relaxed optimum
+        double *zc = st.zpool + (pb + cs) * (long)st.zp_stride;
+        for (int k = lane; k < p.N * 8; k += 32) zc[k] = w.V[(k >> 3) * V_STRIDE + V_Z + (k & 7)];
+      }
       __syncwarp();
       if (lane == 0) {
         int rank = 0;
@@ -686,14 +704,22 @@ __global__ void __launch_bounds__(NODE_TEAM_WARPS * 32, 2) bnb_nodes_kernel(BnbS
 
 int node_kernel_max_ctas(int smem_per_cta, int threads) {
   int nb = 0;
-  cudaFuncSetAttribute(bnb_nodes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_per_cta);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bnb_nodes_kernel, threads, smem_per_cta) != cudaSuccess) return 0;
+  if (threads == NODE_TEAM_WARPS_WIDE * 32) {
+    cudaFuncSetAttribute(bnb_nodes_kernel<NODE_TEAM_WARPS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_per_cta);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bnb_nodes_kernel<NODE_TEAM_WARPS_WIDE>, threads, smem_per_cta) != cudaSuccess) return 0;
+    return nb;
+  }
+  cudaFuncSetAttribute(bnb_nodes_kernel<NODE_TEAM_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_per_cta);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bnb_nodes_kernel<NODE_TEAM_WARPS>, threads, smem_per_cta) != cudaSuccess) return 0;
   return nb;
 }
 
 int launch_bnb_nodes(const BnbState &st, const DevProb *probs, const double *dblob, const int *iblob,
                      int smem_per_node, int warps_per_cta, int ctas, int maxN, int round, cudaStream_t s) {
-  bnb_nodes_kernel<<<ctas, warps_per_cta * 32, (size_t)smem_per_node, s>>>(st, probs, dblob, iblob, smem_per_node, maxN, round);
+  if (warps_per_cta == NODE_TEAM_WARPS_WIDE)
+    bnb_nodes_kernel<NODE_TEAM_WARPS_WIDE><<<ctas, warps_per_cta * 32, (size_t)smem_per_node, s>>>(st, probs, dblob, iblob, smem_per_node, maxN, round);
+  else
+    bnb_nodes_kernel<NODE_TEAM_WARPS><<<ctas, warps_per_cta * 32, (size_t)smem_per_node, s>>>(st, probs, dblob, iblob, smem_per_node, maxN, round);
   return (int)cudaGetLastError();
 }
 

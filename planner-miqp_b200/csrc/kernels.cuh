@@ -39,6 +39,9 @@ struct BnbState {
   int *free_stack; int *free_cnt;
   int *sel_idx; int *sel_cnt;      // slots handed to the node kernel in the last round [count][sel_per_plan]
   unsigned long long *keybuf;      // [count][cap]
+  double *zpool;        // [count][cap][zp_stride] relaxed optimum of the parent (warm start of the child's interior-point solve); null = off
+  int zp_stride;
+  double warm_mu;       // complementarity target of the warm start
   // per plan
   double *ub;           // incumbent objective (inf if none)
   double *cutoff;       // snapshot used by the node kernel in the current round
@@ -49,6 +52,7 @@ struct BnbState {
   unsigned char *inc_dec;  // [count][ndec_stride]
   unsigned long long *inc_uid;  // tie break between equal incumbents (deterministic result)
   unsigned long long *stat_nodes, *stat_iters, *stat_rows;
+  double *dbg;                // [-DMQ_PROF] per-CTA iteration traces [ctas + 8][512]; slots ctas.. hold the claimed slow relaxations
   unsigned long long *prof;   // [256] diagnostics (filled only by -DMQ_PROF builds): [it] histogram of IPM iterations per node, [128..] cycles
   // round control
   int2 *work; int *work_cnt; int *work_next; int *active; int *err; int *active_prev;
@@ -58,7 +62,8 @@ struct BnbState {
 void launch_bnb_init(const BnbState &st, const DevProb *probs, const unsigned char *warm_dec /* [count][ndec_stride] or null */,
                      const int *has_warm, cudaStream_t s);
 void launch_bnb_select(const BnbState &st, const DevProb *probs, int round, cudaStream_t s);
-constexpr int NODE_TEAM_WARPS = 4;   // warps that share one node relaxation (bnb_nodes_kernel)
+constexpr int NODE_TEAM_WARPS = 4;        // warps that share one node relaxation (bnb_nodes_kernel), 2 teams per SM
+constexpr int NODE_TEAM_WARPS_WIDE = 8;   // the same for rounds with fewer nodes than SMs, 1 team per SM
 // returns 0 or a cudaError
 int launch_bnb_nodes(const BnbState &st, const DevProb *probs, const double *dblob, const int *iblob,
                      int smem_per_warp, int warps_per_cta, int ctas, int maxN, int round, cudaStream_t s);

@@ -15,7 +15,7 @@
 // Solver: Mehrotra predictor-corrector interior point in STAGE space.  Every Newton step is
 // a Riccati sweep over the banded KKT system.  Everything that is local to a stage (row
 // generation, residuals, Hessian accumulation, step lengths) is spread over the whole team:
-// sg = 4 / 3 / 2 / 1 adjacent lanes share one stage and take its row slots round robin, so that
+// sg = 6 .. 1 adjacent lanes share one stage and take its row slots round robin, so that
 // N = 40 stages x 3 sub-lanes fill four warps; partial sums are combined with shuffles.  The
 // sequential part runs on warp 0 while the others wait at the barrier: lanes = matrix entries
 // for the backward Riccati factorisation, and the cheap vector sweeps are done redundantly by
@@ -74,6 +74,7 @@ struct WarpCtx {
   double *T;            // [T_SIZE] Riccati scratch (value function of the next stage)
   double2 *rows;        // [kmax+1][NP] (s, lambda) per inequality row
   double *red;          // [8][4] team reduction scratch
+  double *dbgrow;       // [-DMQ_PROF] iteration trace of this CTA
   int lane, N;
   int wid, nw;          // warp of the team, warps per team
   int sg, g, ls, spw;   // sub-lanes per stage, my sub-lane, my stage slot in the warp (idle if >= spw), stages per warp
@@ -84,11 +85,11 @@ struct WarpCtx {
 
 // sub-lanes per stage for a team of nw warps and the padded stage stride of the row records
 __host__ __device__ inline int team_sublanes(int N, int nw) {
-  for (int s = 4; s > 1; --s) if (nw * (32 / s) >= N) return s;
+  for (int s = 6; s > 1; --s) if (nw * (32 / s) >= N) return s;
   return 1;
 }
 __host__ __device__ inline int team_row_stride(int N, int sg) {
-  const int target = (sg == 4) ? 2 : (sg == 3) ? 3 : (sg == 2) ? 4 : (N & 7);
+  const int target = (sg == 4) ? 2 : (sg == 2) ? 4 : (sg == 1) ? (N & 7) : 3;   // sg = 5, 6: two-way conflicts at most
   return N + ((target - N) & 7);
 }
 
@@ -280,17 +281,22 @@ __device__ __forceinline__ double dot6(const double a[6], const double y[8]) {
   return v;
 }
 
-struct PassInit {  // s = max(h - g.z, 1), lambda = 1; gl = G' lambda for the initial dual residual
+struct PassInit {  // cold: s = max(h - g.z, 1), lambda = 1; warm: s = max(h - g.z, smin), lambda = mu0 / s; gl = G' lambda
   RowIO io; double y[8]; double gl[8];
-  __device__ __forceinline__ void put(int slot, double gz, double rhs) {
+  double mu0, smin;   // mu0 <= 0: cold start
+  __device__ __forceinline__ double put(int slot, double gz, double rhs) {
     const double sl = rhs - gz;
-    io.st(slot, make_double2(sl > 1.0 ? sl : 1.0, 1.0));
+    double s, lam;
+    if (mu0 > 0.0) { s = sl > smin ? sl : smin; lam = mu0 * fast_rcp(s); }
+    else { s = sl > 1.0 ? sl : 1.0; lam = 1.0; }
+    io.st(slot, make_double2(s, lam));
+    return lam;
   }
-  template <int T> __device__ __forceinline__ void bound(int slot, double sgn, double rhs) { put(slot, sgn * y[T], rhs); gl[T] += sgn; }
+  template <int T> __device__ __forceinline__ void bound(int slot, double sgn, double rhs) { gl[T] += sgn * put(slot, sgn * y[T], rhs); }
   __device__ __forceinline__ void general(int slot, const double a[6], double rhs) {
-    put(slot, dot6(a, y), rhs);
+    const double lam = put(slot, dot6(a, y), rhs);
 #pragma unroll
-    for (int t = 0; t < 6; ++t) gl[t] += a[t];
+    for (int t = 0; t < 6; ++t) gl[t] += a[t] * lam;
   }
 };
 
@@ -598,10 +604,11 @@ struct QpResult {
 #endif
 };
 
-// Solves the node QP of w.dec; called by every thread of the team with identical arguments.  On
+// Solves the node QP of w.dec; called by every thread of the team with identical arguments.  zwarm (may be
+// null) = relaxed optimum of the parent node, [N][8].  On
 // success V_Z holds the optimal stage vectors.  All control decisions derive from team_reduce results,
 // which are bitwise identical in every thread, so the barriers inside stay uniform.
-__device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEntry &e1, const PhiEntry &e2) {
+__device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEntry &e1, const PhiEntry &e2, const double *zwarm, double warm_mu) {
   const DevProb &p = *w.p;
   const double *D = w.D;
   const int N = w.N;
@@ -648,16 +655,22 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
     PassInit v; v.io.init(w.rows, w.NP, act ? i : 0);
 #pragma unroll
     for (int t = 0; t < 8; ++t) v.gl[t] = 0.0;
+    v.mu0 = zwarm ? warm_mu : 0.0; v.smin = zwarm ? sqrt(warm_mu) : 1.0;
     if (act) {
-      const double t = i * p.ts;
+      if (zwarm) {   // the parent's relaxed optimum (satisfies the dynamics, violates the rows this node adds)
 #pragma unroll
-      for (int ax = 0; ax < 2; ++ax) {
-        const double P = x0[3 * ax], Vv = x0[3 * ax + 1], A = x0[3 * ax + 2];
-        v.y[3 * ax] = P + t * Vv + 0.5 * t * t * A;
-        v.y[3 * ax + 1] = Vv + t * A;
-        v.y[3 * ax + 2] = A;
+        for (int t = 0; t < 8; ++t) v.y[t] = zwarm[i * 8 + t];
+      } else {
+        const double t = i * p.ts;
+#pragma unroll
+        for (int ax = 0; ax < 2; ++ax) {
+          const double P = x0[3 * ax], Vv = x0[3 * ax + 1], A = x0[3 * ax + 2];
+          v.y[3 * ax] = P + t * Vv + 0.5 * t * t * A;
+          v.y[3 * ax + 1] = Vv + t * A;
+          v.y[3 * ax + 2] = A;
+        }
+        v.y[6] = 0.0; v.y[7] = 0.0;
       }
-      v.y[6] = 0.0; v.y[7] = 0.0;
       visit_rows(w, i, v);
     }
 #pragma unroll
@@ -799,6 +812,9 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
     if (bad_step > 0.0) { status = 2; break; }  // singular stage system
     double alpha = (rmax > 0.995) ? 0.995 / rmax : 1.0;
     sc.alpha = alpha; sc.sigmu = sigmu; sc.pending = true;
+#ifdef MQ_PROF
+    if (w.dbgrow && threadIdx.x == 0 && it < 100) { double *q = w.dbgrow + 8 + 5 * it; q[0] = alpha; q[1] = mu; q[2] = rpn; q[3] = sigma; q[4] = lmax; }
+#endif
     rdn *= (1.0 - alpha);
     MQ_FOR_STAGES(i, act) {   // z += alpha dz (rows are updated lazily by the next pass A)
       if (!act || !lead) continue;

@@ -77,11 +77,11 @@ struct MiqpB200Solver {
   // bnb state buffers
   BnbState st;
   DevBuf<unsigned char> b_dec, b_incdec;
-  DevBuf<double> b_bound, b_ub, b_cutoff, b_pruned, b_incz;
+  DevBuf<double> b_bound, b_ub, b_cutoff, b_pruned, b_incz, b_zpool, b_dbg;
   DevBuf<int2> b_meta, b_work;
   DevBuf<unsigned long long> b_uid, b_keybuf, b_incuid, b_stats, b_prof;
   DevBuf<int> b_open, b_opencnt, b_free, b_freecnt, b_sel, b_selcnt, b_done, b_lock, b_ctrl;
-  int smem_per_warp = 0, warps_per_cta = 4, ctas = 0;
+  int smem_per_warp = 0, warps_per_cta = 4, ctas = 0, wide_ctas = 0;
   // CTA-per-node kernel for plans with several cars
   int n_single = 0, n_multi = 0, multi_threads = 64, multi_ctas = 0, multi_use_smem = 1;
   long multi_ws_bytes = 0;
@@ -162,6 +162,11 @@ void setup_bnb(MiqpB200Solver *s) {
     const int per_sm = node_kernel_max_ctas(s->smem_per_warp, s->warps_per_cta * 32);
     if (per_sm <= 0) throw std::runtime_error("node kernel does not fit in shared memory for this horizon");
     s->ctas = per_sm * s->num_sms;
+    s->wide_ctas = 0;
+    if (!getenv("MIQP_NO_WIDE_TEAM")) {
+      const int wide_per_sm = node_kernel_max_ctas(s->smem_per_warp, NODE_TEAM_WARPS_WIDE * 32);
+      if (wide_per_sm > 0) s->wide_ctas = wide_per_sm * s->num_sms;
+    }
     int fm = 1;
     if (const char *e = getenv("MIQP_FILL_MULT")) fm = std::max(1, atoi(e));
     st.nwarps += s->ctas * fm;
@@ -199,7 +204,11 @@ void setup_bnb(MiqpB200Solver *s) {
   // pool capacity per plan
   int cap = s->opt.pool_capacity;
   if (cap <= 0) {
-    const size_t node_bytes = (size_t)st.ndec_stride + 48;
+    // warm start of the children from the parent's relaxed optimum (single-car nodes): N x 8 doubles per node
+    st.warm_mu = 0.0; st.zp_stride = 0;
+    if (const char *e = getenv("MIQP_WARM_MU")) st.warm_mu = atof(e);
+    if (st.warm_mu > 0.0 && s->n_single > 0) st.zp_stride = s->single_maxN * 8;
+    const size_t node_bytes = (size_t)st.ndec_stride + 48 + (size_t)8 * st.zp_stride;
     // pool budget: a third of the free HBM, at most 48 GiB (B200: 180 GB per GPU)
     size_t free_b = 0, total_b = 0;
     size_t budget = (size_t)8 << 30;
@@ -215,6 +224,8 @@ void setup_bnb(MiqpB200Solver *s) {
   const size_t nodes = (size_t)count * cap;
   s->b_dec.ensure(nodes * st.ndec_stride); st.dec = s->b_dec.p;
   s->b_bound.ensure(nodes); st.bound = s->b_bound.p;
+  st.zpool = nullptr;
+  if (st.zp_stride > 0) { s->b_zpool.ensure(nodes * (size_t)st.zp_stride); st.zpool = s->b_zpool.p; }
   s->b_meta.ensure(nodes); st.meta = s->b_meta.p;
   s->b_uid.ensure(nodes); st.uid = s->b_uid.p;
   s->b_open.ensure(nodes); st.open_idx = s->b_open.p;
@@ -238,6 +249,7 @@ void setup_bnb(MiqpB200Solver *s) {
   s->b_work2.ensure(st.work_cap); st.work2 = s->b_work2.p;
   s->b_ctrl.ensure(8);
   s->b_prof.ensure(256); st.prof = s->b_prof.p;
+  s->b_dbg.ensure((size_t)(1024 + 8) * 512); st.dbg = s->b_dbg.p;
   st.work_cnt = s->b_ctrl.p; st.work_next = s->b_ctrl.p + 1; st.active = s->b_ctrl.p + 2; st.err = s->b_ctrl.p + 3;
   st.work_cnt2 = s->b_ctrl.p + 4; st.work_next2 = s->b_ctrl.p + 5; st.active_prev = s->b_ctrl.p + 6;
   s->d_x.ensure(std::max<long>(pk.total_cols, 1));
@@ -295,7 +307,7 @@ void miqp_b200_destroy(MiqpB200Solver *s) {
   s->b_pruned.release(); s->b_incz.release(); s->b_meta.release(); s->b_work.release();
   s->b_uid.release(); s->b_keybuf.release(); s->b_incuid.release(); s->b_stats.release(); s->b_open.release();
   s->b_opencnt.release(); s->b_free.release(); s->b_freecnt.release(); s->b_sel.release(); s->b_selcnt.release();
-  s->b_done.release(); s->b_lock.release(); s->b_ctrl.release(); s->b_multi_ws.release(); s->b_work2.release();
+  s->b_zpool.release(); s->b_done.release(); s->b_lock.release(); s->b_ctrl.release(); s->b_multi_ws.release(); s->b_work2.release();
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   if (s->evr0) cudaEventDestroy(s->evr0);
@@ -447,8 +459,11 @@ int miqp_b200_batch_run(MiqpB200Solver *s, float *device_ms) {
       launches += 2;
       CK(cudaEventRecord(s->evr0, s->stream));
       if (s->n_single > 0) {
-        int rc = launch_bnb_nodes(s->st, s->d_probs.p, s->d_dblob.p, s->d_iblob.p, s->smem_per_warp, s->warps_per_cta,
-                                  s->ctas, s->single_maxN, (int)rounds + 1, s->stream);
+        // fewer single-car nodes than wide teams fit (work count of the last round as the estimate): latency matters, not throughput
+        const bool wide = s->wide_ctas > 0 && rounds > 0 && ctrl[0] > 0 && ctrl[0] <= s->wide_ctas;
+        int rc = launch_bnb_nodes(s->st, s->d_probs.p, s->d_dblob.p, s->d_iblob.p, s->smem_per_warp,
+                                  wide ? NODE_TEAM_WARPS_WIDE : s->warps_per_cta, wide ? s->wide_ctas : s->ctas, s->single_maxN,
+                                  (int)rounds + 1, s->stream);
         if (rc != 0) throw std::runtime_error(std::string("node kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
         ++launches; ++node_launches;
       }
@@ -557,6 +572,13 @@ int miqp_b200_measure_fp64_peak(MiqpB200Solver *s, double *tflops) {
   const double tf = miqp::measure_fp64_tflops(s->num_sms, s->stream, 5);
   if (tf <= 0.0) return fail(s, MIQP_B200_ERR_CUDA, "fp64 micro-benchmark failed");
   *tflops = tf;
+  return MIQP_B200_OK;
+}
+
+int miqp_b200_debug_traces(MiqpB200Solver *s, double *out4096) {
+  if (!s || !out4096 || !s->b_dbg.p) return MIQP_B200_ERR_ARG;
+  if (cudaMemcpy(out4096, s->b_dbg.p + (size_t)1024 * 512, 8 * 512 * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return fail(s, MIQP_B200_ERR_CUDA, "trace copy failed");
   return MIQP_B200_OK;
 }
 

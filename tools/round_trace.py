@@ -36,3 +36,12 @@ if sum(prof):
     hi = prof[150:251]
     print("iterations of infeasible relaxations (iters: count):", {k: v for k, v in enumerate(hi) if v})
     print("iterations of feasible relaxations >= 18:", {k: h[k] - hi[k] for k in range(18, 101) if h[k] - hi[k]})
+    tr = s.debug_traces()
+    for k in range(8):
+        n = int(tr[k, 0])
+        if n <= 0: continue
+        print(f"slow feasible relaxation {k}: {n} iterations, objective {tr[k,1]:.6f}, depth {int(tr[k,2])}")
+        for it in range(min(n, 100)):
+            a, mu, rp, sg, lm = tr[k, 8 + 5 * it: 13 + 5 * it]
+            print(f"   it {it:2d} alpha {a:.3e} mu {mu:.3e} rp {rp:.3e} sigma {sg:.3e} lmax {lm:.3e}")
+        if k >= 2: break
