@@ -597,7 +597,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 2 ? 3 : NW == 4 ? 2 : 1) bnb_no
         if (k < 8) { double *dst = st.dbg + (size_t)(1024 + k) * 512; dst[0] = r.iters; dst[1] = r.obj; dst[2] = nmeta.x; for (int q = 8; q < 8 + 5 * 100; ++q) dst[q] = w.dbgrow[q]; }
       }
       atomicAdd(&st.prof[134], (unsigned long long)r.c_a); atomicAdd(&st.prof[135], (unsigned long long)r.c_ared); atomicAdd(&st.prof[136], (unsigned long long)r.c_d);
-      atomicAdd(&st.prof[137], (unsigned long long)r.c_e); atomicAdd(&st.prof[138], (unsigned long long)r.c_g);
+      atomicAdd(&st.prof[137], (unsigned long long)r.c_e); atomicAdd(&st.prof[138], (unsigned long long)r.c_g); atomicAdd(&st.prof[139], (unsigned long long)r.c_atr);
     }
 #endif
     if (lane == 0) {

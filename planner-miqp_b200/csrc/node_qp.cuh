@@ -116,16 +116,30 @@ __device__ __forceinline__ int warp_sum_i(int v) {
   return v;
 }
 
-// sum / max over the sg adjacent lanes that share a stage; the result is valid in the leader (g == 0)
-__device__ __forceinline__ double sg_sum(const WarpCtx &w, double v) {
-  double t = v;
-  for (int d = 1; d < w.sg; ++d) t += __shfl_down_sync(FULL, v, d);
-  return t;
+// sums over the sg adjacent lanes that share a stage, for CNT values at once; the results are valid in the leader
+// (g == 0).  One straight-line variant per sg: with a run-time trip count the shuffles of the values serialise
+// (6.3 k cycles for the 31 sums of pass A instead of a few hundred).
+template <int SG, int CNT>
+__device__ __forceinline__ void sg_reduce_fixed(double (&a)[CNT]) {
+#pragma unroll
+  for (int t = 0; t < CNT; ++t) {
+    const double v = a[t];
+    double r = v;
+#pragma unroll
+    for (int d = 1; d < SG; ++d) r += __shfl_down_sync(FULL, v, d);
+    a[t] = r;
+  }
 }
-__device__ __forceinline__ double sg_max(const WarpCtx &w, double v) {
-  double t = v;
-  for (int d = 1; d < w.sg; ++d) { const double o = __shfl_down_sync(FULL, v, d); t = o > t ? o : t; }
-  return t;
+template <int CNT>
+__device__ __forceinline__ void sg_reduce(const WarpCtx &w, double (&a)[CNT]) {
+  switch (w.sg) {   // uniform over the team
+    case 2: sg_reduce_fixed<2, CNT>(a); break;
+    case 3: sg_reduce_fixed<3, CNT>(a); break;
+    case 4: sg_reduce_fixed<4, CNT>(a); break;
+    case 5: sg_reduce_fixed<5, CNT>(a); break;
+    case 6: sg_reduce_fixed<6, CNT>(a); break;
+    default: break;
+  }
 }
 // team-wide {max a, max b, sum c, sum d}; every thread receives bitwise identical results
 __device__ __forceinline__ void team_reduce(const WarpCtx &w, double &a, double &b, double &c, double &d) {
@@ -475,9 +489,11 @@ __device__ __forceinline__ void riccati_factor(const WarpCtx &w, const PhiEntry 
     const double *Pn = T + T_P + 24 * ((i + 1) & 1), *pn = T + T_PV + 6 * ((i + 1) & 1);
     double *Pc = T + T_P + 24 * (i & 1), *pc = T + T_PV + 6 * (i & 1);
     // phase 1: Phi entries and phi
-    const double m1 = (lane < 21) ? Si[lane] : 0.0;                                            // + Mxx (M_ux = 0)
-    const double m2 = (lane == 1) ? Si[S_MUU] : (lane == 3) ? Si[S_MUU + 1] : 0.0;             // + Muu on entries 33, 35
-    const double gv = (lane < 8) ? Vi[V_G + lane] : 0.0;
+    // unconditional loads from clamped indices + selects (a conditional load compiles to a branch)
+    const double m1r = Si[lane < 21 ? lane : 0], m2r = Si[S_MUU + (lane == 3 ? 1 : 0)], gvr = Vi[V_G + (lane < 8 ? lane : 0)];
+    const double m1 = (lane < 21) ? m1r : 0.0;                                                 // + Mxx (M_ux = 0)
+    const double m2 = (lane == 1 || lane == 3) ? m2r : 0.0;                                    // + Muu on entries 33, 35
+    const double gv = (lane < 8) ? gvr : 0.0;
     const double phi1 = m1 + e1.eval(Pn);
     const double phi2 = m2 + e2.eval(Pn);
     const double phiv = fma(pcf[2], pn[prow0 + 2 < 6 ? prow0 + 2 : 5], fma(pcf[1], pn[prow0 + 1 < 6 ? prow0 + 1 : 5], fma(pcf[0], pn[prow0], gv)));
@@ -513,7 +529,24 @@ struct SweepRec {
   }
 };
 
-// vector-only backward sweep with a new gradient (V_G), all lanes redundantly
+// vector-only backward sweep with a new gradient (V_G), all lanes redundantly; two stages per trip with
+// ping-pong records so that the prefetched values are never copied
+__device__ __forceinline__ void riccati_vector_stage(const WarpCtx &w, int i, const SweepRec &rec, const double g[8], double pn[6],
+                                                     double ts, double c2, double c3) {
+  double phi[8];
+#pragma unroll
+  for (int ax = 0; ax < 2; ++ax) {
+    const double pp = pn[3 * ax], pv = pn[3 * ax + 1], pa = pn[3 * ax + 2];
+    phi[3 * ax] = g[3 * ax] + pp;
+    phi[3 * ax + 1] = g[3 * ax + 1] + ts * pp + pv;
+    phi[3 * ax + 2] = g[3 * ax + 2] + c2 * pp + ts * pv + pa;
+    phi[6 + ax] = g[6 + ax] + c3 * pp + c2 * pv + ts * pa;
+  }
+  const double k0 = -(rec.F[0] * phi[6] + rec.F[1] * phi[7]), k1 = -(rec.F[1] * phi[6] + rec.F[2] * phi[7]);
+#pragma unroll
+  for (int t = 0; t < 6; ++t) pn[t] = phi[t] + rec.G[t] * k0 + rec.G[6 + t] * k1;
+  if (w.lane == 6) { double *Vi = w.V + i * V_STRIDE; Vi[V_K] = k0; Vi[V_K + 1] = k1; }
+}
 __device__ __forceinline__ void riccati_vector(const WarpCtx &w) {
   const DevProb &p = *w.p;
   const int N = w.N;
@@ -521,74 +554,72 @@ __device__ __forceinline__ void riccati_vector(const WarpCtx &w) {
   double pn[6];
 #pragma unroll
   for (int t = 0; t < 6; ++t) pn[t] = w.V[(N - 1) * V_STRIDE + V_G + t];
-  SweepRec cur, nxt;
-  double gcur[8], gnxt[8];
-  cur.load(w.S + (N - 2) * S_STRIDE);
+  SweepRec ra, rb;
+  double ga[8], gb[8];
+  ra.load(w.S + (N - 2) * S_STRIDE);
 #pragma unroll
-  for (int t = 0; t < 8; ++t) gcur[t] = w.V[(N - 2) * V_STRIDE + V_G + t];
-  for (int i = N - 2; i >= 0; --i) {
-    const int ip = (i > 0) ? i - 1 : 0;
-    nxt.load(w.S + ip * S_STRIDE);
+  for (int t = 0; t < 8; ++t) ga[t] = w.V[(N - 2) * V_STRIDE + V_G + t];
+  for (int i = N - 2; i >= 0; i -= 2) {
+    const int i1 = (i > 0) ? i - 1 : 0, i2 = (i > 1) ? i - 2 : 0;
+    rb.load(w.S + i1 * S_STRIDE);
 #pragma unroll
-    for (int t = 0; t < 8; ++t) gnxt[t] = w.V[ip * V_STRIDE + V_G + t];
-    double phi[8];
+    for (int t = 0; t < 8; ++t) gb[t] = w.V[i1 * V_STRIDE + V_G + t];
+    riccati_vector_stage(w, i, ra, ga, pn, ts, c2, c3);
+    if (i == 0) break;
+    ra.load(w.S + i2 * S_STRIDE);
 #pragma unroll
-    for (int ax = 0; ax < 2; ++ax) {
-      const double pp = pn[3 * ax], pv = pn[3 * ax + 1], pa = pn[3 * ax + 2];
-      phi[3 * ax] = gcur[3 * ax] + pp;
-      phi[3 * ax + 1] = gcur[3 * ax + 1] + ts * pp + pv;
-      phi[3 * ax + 2] = gcur[3 * ax + 2] + c2 * pp + ts * pv + pa;
-      phi[6 + ax] = gcur[6 + ax] + c3 * pp + c2 * pv + ts * pa;
-    }
-    const double k0 = -(cur.F[0] * phi[6] + cur.F[1] * phi[7]), k1 = -(cur.F[1] * phi[6] + cur.F[2] * phi[7]);
-#pragma unroll
-    for (int t = 0; t < 6; ++t) pn[t] = phi[t] + cur.G[t] * k0 + cur.G[6 + t] * k1;
-    if (w.lane == 6) { double *Vi = w.V + i * V_STRIDE; Vi[V_K] = k0; Vi[V_K + 1] = k1; }
-    cur = nxt;
-#pragma unroll
-    for (int t = 0; t < 8; ++t) gcur[t] = gnxt[t];
+    for (int t = 0; t < 8; ++t) ga[t] = w.V[i2 * V_STRIDE + V_G + t];
+    riccati_vector_stage(w, i - 1, rb, gb, pn, ts, c2, c3);
   }
   __syncwarp();
 }
 
 // forward sweep, all lanes redundantly; writes the step of every stage at offset `dst`
+__device__ __forceinline__ void riccati_forward_stage(const WarpCtx &w, int i, int dst, bool has_input, const SweepRec &rec, double kc0, double kc1,
+                                                      double dx[6], double ts, double c2, double c3) {
+  double *Vi = w.V + i * V_STRIDE;
+  double du0 = 0.0, du1 = 0.0;
+  if (has_input) {
+    // two partial chains per row of G dx
+    const double t0 = (rec.G[0] * dx[0] + rec.G[1] * dx[1] + rec.G[2] * dx[2]) + (rec.G[3] * dx[3] + rec.G[4] * dx[4] + rec.G[5] * dx[5]);
+    const double t1 = (rec.G[6] * dx[0] + rec.G[7] * dx[1] + rec.G[8] * dx[2]) + (rec.G[9] * dx[3] + rec.G[10] * dx[4] + rec.G[11] * dx[5]);
+    du0 = kc0 - (rec.F[0] * t0 + rec.F[1] * t1);
+    du1 = kc1 - (rec.F[1] * t0 + rec.F[2] * t1);
+  }
+  {  // lane t < 8 stores component t (one predicated store instead of eight branches)
+    double val = dx[0];
+    val = (w.lane == 1) ? dx[1] : val; val = (w.lane == 2) ? dx[2] : val; val = (w.lane == 3) ? dx[3] : val;
+    val = (w.lane == 4) ? dx[4] : val; val = (w.lane == 5) ? dx[5] : val;
+    val = (w.lane == 6) ? du0 : val;   val = (w.lane == 7) ? du1 : val;
+    if (w.lane < 8) Vi[dst + w.lane] = val;
+  }
+#pragma unroll
+  for (int ax = 0; ax < 2; ++ax) {
+    const double P = dx[3 * ax], Vv = dx[3 * ax + 1], A = dx[3 * ax + 2], U = ax ? du1 : du0;
+    dx[3 * ax] = P + ts * Vv + c2 * A + c3 * U;
+    dx[3 * ax + 1] = Vv + ts * A + c2 * U;
+    dx[3 * ax + 2] = A + ts * U;
+  }
+}
 __device__ __forceinline__ void riccati_forward(const WarpCtx &w, int dst) {
   const DevProb &p = *w.p;
   const int N = w.N;
   const double ts = p.ts, c2 = p.c2, c3 = p.c3;
   double dx[6] = {0, 0, 0, 0, 0, 0};
-  SweepRec cur, nxt;
-  double kc0, kc1, kn0, kn1;
-  cur.load(w.S);
-  kc0 = w.V[V_K]; kc1 = w.V[V_K + 1];
-  for (int i = 0; i < N; ++i) {
-    double *Vi = w.V + i * V_STRIDE;
-    const int in = (i + 1 < N - 1) ? i + 1 : 0;        // stage N-1 has no input: its record is never used
-    nxt.load(w.S + in * S_STRIDE);
-    kn0 = w.V[in * V_STRIDE + V_K]; kn1 = w.V[in * V_STRIDE + V_K + 1];
-    double du0 = 0.0, du1 = 0.0;
-    if (i < N - 1) {
-      // two partial chains per row of G dx
-      const double t0 = (cur.G[0] * dx[0] + cur.G[1] * dx[1] + cur.G[2] * dx[2]) + (cur.G[3] * dx[3] + cur.G[4] * dx[4] + cur.G[5] * dx[5]);
-      const double t1 = (cur.G[6] * dx[0] + cur.G[7] * dx[1] + cur.G[8] * dx[2]) + (cur.G[9] * dx[3] + cur.G[10] * dx[4] + cur.G[11] * dx[5]);
-      du0 = kc0 - (cur.F[0] * t0 + cur.F[1] * t1);
-      du1 = kc1 - (cur.F[1] * t0 + cur.F[2] * t1);
-    }
-    {  // lane t < 8 stores component t (one predicated store instead of eight branches)
-      double val = dx[0];
-      val = (w.lane == 1) ? dx[1] : val; val = (w.lane == 2) ? dx[2] : val; val = (w.lane == 3) ? dx[3] : val;
-      val = (w.lane == 4) ? dx[4] : val; val = (w.lane == 5) ? dx[5] : val;
-      val = (w.lane == 6) ? du0 : val;   val = (w.lane == 7) ? du1 : val;
-      if (w.lane < 8) Vi[dst + w.lane] = val;
-    }
-#pragma unroll
-    for (int ax = 0; ax < 2; ++ax) {
-      const double P = dx[3 * ax], Vv = dx[3 * ax + 1], A = dx[3 * ax + 2], U = ax ? du1 : du0;
-      dx[3 * ax] = P + ts * Vv + c2 * A + c3 * U;
-      dx[3 * ax + 1] = Vv + ts * A + c2 * U;
-      dx[3 * ax + 2] = A + ts * U;
-    }
-    cur = nxt; kc0 = kn0; kc1 = kn1;
+  SweepRec ra, rb;
+  double ka0, ka1, kb0, kb1;
+  ra.load(w.S);
+  ka0 = w.V[V_K]; ka1 = w.V[V_K + 1];
+  for (int i = 0; i < N; i += 2) {
+    // stage N-1 has no input: its record is never used, any valid stage may be fetched in its place
+    const int i1 = (i + 1 < N - 1) ? i + 1 : 0, i2 = (i + 2 < N - 1) ? i + 2 : 0;
+    rb.load(w.S + i1 * S_STRIDE);
+    kb0 = w.V[i1 * V_STRIDE + V_K]; kb1 = w.V[i1 * V_STRIDE + V_K + 1];
+    riccati_forward_stage(w, i, dst, i < N - 1, ra, ka0, ka1, dx, ts, c2, c3);
+    if (i + 1 >= N) break;
+    ra.load(w.S + i2 * S_STRIDE);
+    ka0 = w.V[i2 * V_STRIDE + V_K]; ka1 = w.V[i2 * V_STRIDE + V_K + 1];
+    riccati_forward_stage(w, i + 1, dst, i + 1 < N - 1, rb, kb0, kb1, dx, ts, c2, c3);
   }
   __syncwarp();
 }
@@ -600,7 +631,7 @@ struct QpResult {
   long rows;      // active rows x iterations (work counter)
 #ifdef MQ_PROF
   long long c_rows, c_factor, c_sweeps;   // clock64 cycles: row passes / Riccati factorisation / vector + forward sweeps
-  long long c_a, c_ared, c_d, c_e, c_g;   // split of c_rows: pass A visit, pass A reduce + epilogue + team reduce, D, E, G
+  long long c_a, c_ared, c_d, c_e, c_g, c_atr;   // split of c_rows: pass A visit, pass A reduce + epilogue + team reduce, D, E, G
 #endif
 };
 
@@ -615,7 +646,7 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
   const bool lead = (w.g == 0);
   QpResult res; res.status = 1; res.iters = 0; res.obj = 0.0; res.rows = 0;
 #ifdef MQ_PROF
-  res.c_rows = res.c_factor = res.c_sweeps = 0; res.c_a = res.c_ared = res.c_d = res.c_e = res.c_g = 0;
+  res.c_rows = res.c_factor = res.c_sweeps = 0; res.c_a = res.c_ared = res.c_d = res.c_e = res.c_g = res.c_atr = 0;
   long long qc0 = 0;
 #define MQ_T0 qc0 = clock64();
 #define MQ_T1(field) res.field += clock64() - qc0;
@@ -673,8 +704,7 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
       }
       visit_rows(w, i, v);
     }
-#pragma unroll
-    for (int t = 0; t < 8; ++t) v.gl[t] = sg_sum(w, v.gl[t]);
+    sg_reduce(w, v.gl);
     if (act && lead) {
       double *Vi = w.V + i * V_STRIDE;
       const double *cst = D + p.o_cost + 16 * i;
@@ -711,11 +741,7 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
         MQ_T1(c_a)
       }
       MQ_T0
-#pragma unroll
-      for (int t = 0; t < 21; ++t) v.H[t] = sg_sum(w, v.H[t]);
-      v.Huu[0] = sg_sum(w, v.Huu[0]); v.Huu[1] = sg_sum(w, v.Huu[1]);
-#pragma unroll
-      for (int t = 0; t < 8; ++t) v.gx[t] = sg_sum(w, v.gx[t]);
+      sg_reduce(w, v.H); sg_reduce(w, v.Huu); sg_reduce(w, v.gx);
       if (act && lead) {
         double *Vi = w.V + i * V_STRIDE, *Si = w.S + i * S_STRIDE;
         const double *cst = D + p.o_cost + 16 * i;
@@ -730,8 +756,10 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
       rpn = fmax(rpn, v.rpn); musum += v.musum; lmax = fmax(lmax, v.lmax); mcount += (double)v.m;
     }
     sc.pending = false;
-    team_reduce(w, rpn, lmax, musum, mcount);
     MQ_T1(c_ared)
+    MQ_T0
+    team_reduce(w, rpn, lmax, musum, mcount);
+    MQ_T1(c_atr)
     const long m = (long)mcount;
     res.rows += m;
     const double mu = (m > 0) ? musum / m : 0.0;
@@ -779,8 +807,7 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
         for (int t = 0; t < 8; ++t) { v.y[t] = Vi[V_Z + t]; v.da[t] = Vi[V_DZA + t]; }
         visit_rows(w, i, v);
       }
-#pragma unroll
-      for (int t = 0; t < 8; ++t) v.gx[t] = sg_sum(w, v.gx[t]);
+      sg_reduce(w, v.gx);
       if (act && lead) {
         double *Vi = w.V + i * V_STRIDE;
         const double *cst = D + p.o_cost + 16 * i;

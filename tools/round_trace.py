@@ -32,7 +32,7 @@ if sum(prof):
     print("cycles: rows %.1f%% factor %.1f%% sweeps %.1f%% of node total; per node %.0f cycles; per iter %.0f cycles" % (
         100 * c[0] / c[3], 100 * c[1] / c[3], 100 * c[2] / c[3], c[3] / tot, c[3] / max(sum(k * v for k, v in enumerate(h)), 1)))
     its = max(sum(k * v for k, v in enumerate(h)), 1)
-    print("row passes, cycles per iteration: A visit %.0f, A reduce+epilogue %.0f, D %.0f, E %.0f, G %.0f" % tuple(x / its for x in prof[134:139]))
+    print("row passes, cycles per iteration: A visit %.0f, A sub-lane reduce+epilogue %.0f, D %.0f, E %.0f, G %.0f, A team reduce (incl. wait) %.0f" % tuple(x / its for x in prof[134:140]))
     hi = prof[150:251]
     print("iterations of infeasible relaxations (iters: count):", {k: v for k, v in enumerate(hi) if v})
     print("iterations of feasible relaxations >= 18:", {k: h[k] - hi[k] for k in range(18, 101) if h[k] - hi[k]})
