@@ -1,0 +1,86 @@
+"""GPU parity on the synthetic shapes BASELINE.json names, through the solver C ABI:
+config 2 (single agent, static + dynamic obstacle, N=40, R=32), the lane-following shape of config 1c,
+random single-agent plans of config 4, against the CPU oracle on the same seeded inputs; at the full
+bench size through size-independent properties (proven gap, feasibility of every returned vector against
+the full big-M model, bound <= objective, independence of a plan's result from its batch).
+
+Tolerance: both solvers stop at a proven relative gap of 1e-4, so two optimal objectives may differ by
+2e-4 relative (asserted); constraint violation <= 1e-6 (north_star)."""
+import numpy as np
+import pytest
+
+import planner_miqp_b200 as P
+from planner_miqp_b200.scenarios import obstacle_scenario, lane_following, random_single_agent
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+GAP = 1e-4
+
+
+@pytest.fixture(scope="module")
+def solver():
+    s = P.Solver()
+    yield s
+    s.close()
+
+
+def _check_batch(solver, plans, label):
+    xs, infos = solver.solve_batch(plans, gap_tol=GAP, time_limit=120.0)
+    for k, (p, x, info) in enumerate(zip(plans, xs, infos)):
+        xo, io = O.solve(p, gap_tol=GAP, time_limit=120.0)
+        assert io.status == info.status, (label, k, io.status, info.status)
+        if io.status != 0:
+            continue
+        assert info.proven and io.proven, (label, k)
+        assert info.objective == pytest.approx(io.objective, rel=2 * GAP, abs=1e-9), (label, k)
+        viol, worst = O.max_violation(p, x)
+        assert viol <= 1e-6, (label, k, viol, worst)
+        # the bound comes from interior-point solves (1e-9 residuals), the objective from the re-evaluated vector
+        assert info.best_bound <= info.objective + 1e-6 * abs(info.objective)
+
+
+def test_config2_obstacle_plans_match_oracle(solver):
+    _check_batch(solver, [obstacle_scenario(s).build() for s in range(20)], "config 2")
+
+
+def test_config2_soft_obstacles_match_oracle(solver):
+    _check_batch(solver, [obstacle_scenario(100 + s, soft=True).build() for s in range(8)], "config 2 soft")
+
+
+def test_lane_following_and_random_single_agent_match_oracle(solver):
+    plans = [lane_following(seed=s).build() for s in range(6)] + [random_single_agent(s).build() for s in range(18)]
+    _check_batch(solver, plans, "config 1c / 4")
+
+
+def test_time_limit_statuses(solver):
+    """a time limit that ends the search early: SUCCESS with an unproven gap if an incumbent exists, else FAILED_TIMEOUT
+    (reference src/cplex_wrapper.cpp:231-246, test/cplex_wrapper_test.cc:821-842)"""
+    s = P.Solver(max_rounds=3)          # the round cap acts like an expired time limit
+    p = obstacle_scenario(3).build()
+    x, info = s.solve(p, gap_tol=GAP, time_limit=60.0)
+    assert info.status in (0, 3)
+    if info.status == 0:
+        assert not info.proven
+        viol, _ = O.max_violation(p, x)
+        assert viol <= 1e-6
+    else:
+        assert np.isnan(info.objective) and np.isnan(info.gap)
+    s.close()
+
+
+def test_full_size_batch_properties(solver):
+    """bench-size batch (2048 config-2 plans): every plan proven to 1e-4, every vector feasible for the big-M model"""
+    plans = [obstacle_scenario(s).build() for s in range(2048)]
+    xs, infos = solver.solve_batch(plans, gap_tol=GAP, time_limit=600.0)
+    assert all(i.status == 0 and i.proven for i in infos)
+    assert max(i.max_violation for i in infos) <= 1e-6
+    assert all(i.gap <= GAP and i.best_bound <= i.objective + 1e-6 * abs(i.objective) for i in infos)
+    # device-side evaluation agrees with the oracle's evaluator on a sample
+    for k in (0, 511, 1024, 2047):
+        assert O.objective(plans[k], xs[k]) == pytest.approx(infos[k].objective, rel=1e-10)
+        assert O.max_violation(plans[k], xs[k])[0] <= 1e-6
+    # a plan's result does not depend on the batch it is solved in (beyond the gap both runs prove)
+    sub = [7, 300, 840, 1500]
+    xs2, infos2 = solver.solve_batch([plans[k] for k in sub], gap_tol=GAP, time_limit=600.0)
+    for k, i2 in zip(sub, infos2):
+        assert i2.objective == pytest.approx(infos[k].objective, rel=2 * GAP)
