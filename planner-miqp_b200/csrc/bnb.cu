@@ -195,6 +195,7 @@ __global__ void __launch_bounds__(SEL_THREADS) bnb_select_kernel(BnbState st, co
     T = s_prefix; remaining = s_remaining;
   }
   // 5. hand the selected nodes to the work list, keep the rest
+  __syncthreads();   // every thread has read n1 = s_out (no barrier in between when n1 <= K; racecheck finding)
   if (tid == 0) s_out = 0;
   __syncthreads();
   int nsel_total = 0;
