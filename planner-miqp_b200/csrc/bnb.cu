@@ -530,7 +530,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 2 ? 3 : NW == 4 ? 2 : 1) bnb_no
   const NodeSmem L = node_smem_layout(maxN, st.kmax, st.ndec_stride);
   WarpCtx w;
   w.D = dblob; w.I = iblob; w.lane = lane; w.wid = wid; w.nw = nw; w.red = s_red;
-  w.dbgrow = nullptr;
+  w.dbgrow = nullptr; w.tau_k = st.tau_k;
 #ifdef MQ_PROF
   if (st.dbg && blockIdx.x < 1024) w.dbgrow = st.dbg + (size_t)blockIdx.x * 512;
 #endif

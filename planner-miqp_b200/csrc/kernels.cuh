@@ -42,6 +42,7 @@ struct BnbState {
   double *zpool;        // [count][cap][zp_stride] relaxed optimum of the parent (warm start of the child's interior-point solve); null = off
   int zp_stride;
   double warm_mu;       // complementarity target of the warm start
+  double tau_k;         // step fraction to the boundary = max(0.995, 1 - tau_k * mu); 0 = constant 0.995
   // per plan
   double *ub;           // incumbent objective (inf if none)
   double *cutoff;       // snapshot used by the node kernel in the current round

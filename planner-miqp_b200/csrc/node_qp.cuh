@@ -74,6 +74,7 @@ struct WarpCtx {
   double *T;            // [T_SIZE] Riccati scratch (value function of the next stage)
   double2 *rows;        // [kmax+1][NP] (s, lambda) per inequality row
   double *red;          // [8][4] team reduction scratch
+  double tau_k;
   double *dbgrow;       // [-DMQ_PROF] iteration trace of this CTA
   int lane, N;
   int wid, nw;          // warp of the team, warps per team
@@ -837,7 +838,9 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
     team_reduce(w, rmax, bad_step, s1, s2);
     MQ_T1(c_g)
     if (bad_step > 0.0) { status = 2; break; }  // singular stage system
-    double alpha = (rmax > 0.995) ? 0.995 / rmax : 1.0;
+    // fraction to the boundary: 0.995 far from the solution, -> 1 as mu -> 0 (superlinear end phase)
+    const double tau = (w.tau_k > 0.0) ? fmin(fmax(0.995, 1.0 - w.tau_k * mu), 1.0 - 1e-9) : 0.995;
+    double alpha = (rmax > tau) ? tau / rmax : 1.0;
     sc.alpha = alpha; sc.sigmu = sigmu; sc.pending = true;
 #ifdef MQ_PROF
     if (w.dbgrow && threadIdx.x == 0 && it < 100) { double *q = w.dbgrow + 8 + 5 * it; q[0] = alpha; q[1] = mu; q[2] = rpn; q[3] = sigma; q[4] = lmax; }

@@ -206,6 +206,8 @@ void setup_bnb(MiqpB200Solver *s) {
   if (cap <= 0) {
     // warm start of the children from the parent's relaxed optimum (single-car nodes): N x 8 doubles per node
     st.warm_mu = 0.0; st.zp_stride = 0;
+    st.tau_k = 1.0;   // profiles/r1k: 9.45 -> 8.6 interior-point iterations per node
+    if (const char *e = getenv("MIQP_TAU_K")) st.tau_k = atof(e);
     if (const char *e = getenv("MIQP_WARM_MU")) st.warm_mu = atof(e);
     if (st.warm_mu > 0.0 && s->n_single > 0) st.zp_stride = s->single_maxN * 8;
     const size_t node_bytes = (size_t)st.ndec_stride + 48 + (size_t)8 * st.zp_stride;
