@@ -607,9 +607,15 @@ __global__ void __launch_bounds__(NW * 32, NW == 2 ? 3 : NW == 4 ? 2 : 1) bnb_no
       atomicAdd(&st.stat_rows[s], (unsigned long long)r.rows);
     }
     if (r.status != 0) continue;  // infeasible: the node dies
-    double obj = r.obj + pen;
+    // fval: objective of the point in V_Z (an upper bound of the relaxation); obj: lower bound of the node.  They coincide
+    // when the interior-point iteration converged; a stalled iteration only inherits the bound of its parent.
+    const double fval = r.obj + pen;
+    double obj = r.converged ? fval : nbound;
     if (obj < nbound) obj = nbound;  // numerical monotonicity
     if (obj >= cutoff) { if (lane == 0) atomic_min_double(&st.pruned_lb[s], obj); continue; }
+#ifdef MQ_PROF
+    if (lane == 0 && !r.converged) atomicAdd(&st.prof[149], 1ULL);
+#endif
 
     Branch br;
     const int und = scan_node(w, br);
@@ -620,14 +626,15 @@ __global__ void __launch_bounds__(NW * 32, NW == 2 ? 3 : NW == 4 ? 2 : 1) bnb_no
       __threadfence();
       const double cur = *reinterpret_cast<volatile double *>(&st.ub[s]);
       const unsigned long long cuid = *reinterpret_cast<volatile unsigned long long *>(&st.inc_uid[s]);
-      if (obj < cur || (obj == cur && nuid < cuid)) {
+      const double inc = fval > obj ? fval : obj;   // value of the stored point (never below the node's bound)
+      if (inc < cur || (inc == cur && nuid < cuid)) {
         double *iz = st.inc_z + (long)s * st.zstride;
         for (int i = lane; i < p.N; i += 32)
           for (int t = 0; t < 8; ++t) iz[i * 8 + t] = w.V[i * V_STRIDE + V_Z + t];
         copy_bytes16(st.inc_dec + (long)s * st.ndec_stride, w.dec, st.ndec_stride, lane);
         __threadfence();
         __syncwarp();
-        if (lane == 0) { st.ub[s] = obj; st.inc_uid[s] = nuid; }
+        if (lane == 0) { st.ub[s] = inc; st.inc_uid[s] = nuid; }
       }
       __syncwarp();
       if (lane == 0) { __threadfence(); atomicExch(&st.lock[s], 0); }
@@ -658,7 +665,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 2 ? 3 : NW == 4 ? 2 : 1) bnb_no
     // serve as scratch.  Children that reach the cutoff are dropped.
     double *cb = reinterpret_cast<double *>(w.rows);
     if (br.kind == 0) { if (lane == 0) cb[0] = obj; }
-    else for (int a = lane; a < nalt; a += 32) cb[a] = fmax(obj, r.obj + pen + 0.999 * alt_delta(w, br, alts[a]));
+    else for (int a = lane; a < nalt; a += 32) cb[a] = r.converged ? fmax(obj, fval + 0.999 * alt_delta(w, br, alts[a])) : obj;
     __syncwarp();
     {
       int nk = 0; double pm = MQ_INF;

@@ -626,7 +626,8 @@ __device__ __forceinline__ void riccati_forward(const WarpCtx &w, int dst) {
 }
 
 struct QpResult {
-  int status;     // 0 optimal, 1 infeasible
+  int status;     // 0 optimal (or, with converged == 0, merely a feasible point), 1 infeasible
+  int converged;  // 1: obj is the optimum of the relaxation (a valid bound); 0: the iteration stalled, obj is only an upper bound
   int iters;
   double obj;     // without soft-decision penalties
   long rows;      // active rows x iterations (work counter)
@@ -645,7 +646,7 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
   const double *D = w.D;
   const int N = w.N;
   const bool lead = (w.g == 0);
-  QpResult res; res.status = 1; res.iters = 0; res.obj = 0.0; res.rows = 0;
+  QpResult res; res.status = 1; res.converged = 0; res.iters = 0; res.obj = 0.0; res.rows = 0;
 #ifdef MQ_PROF
   res.c_rows = res.c_factor = res.c_sweeps = 0; res.c_a = res.c_ared = res.c_d = res.c_e = res.c_g = res.c_atr = 0;
   long long qc0 = 0;
@@ -839,7 +840,7 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
     MQ_T1(c_g)
     if (bad_step > 0.0) { status = 2; break; }  // singular stage system
     // fraction to the boundary: 0.995 far from the solution, -> 1 as mu -> 0 (superlinear end phase)
-    const double tau = (w.tau_k > 0.0) ? fmin(fmax(0.995, 1.0 - w.tau_k * mu), 1.0 - 1e-9) : 0.995;
+    const double tau = (w.tau_k > 0.0) ? fmin(fmax(0.995, 1.0 - w.tau_k * mu), 0.9999) : 0.995;
     double alpha = (rmax > tau) ? tau / rmax : 1.0;
     sc.alpha = alpha; sc.sigmu = sigmu; sc.pending = true;
 #ifdef MQ_PROF
@@ -856,6 +857,7 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
     if (alpha < 1e-6) { if (++stall >= 5) { status = 2; break; } } else stall = 0;
   }
   res.iters = it;
+  res.converged = (status == 0);
   MQ_TICK(c_rows)
   if (status != 0) {
     // not converged: infeasible only if the primal point violates its rows

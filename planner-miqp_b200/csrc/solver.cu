@@ -540,6 +540,8 @@ int miqp_b200_batch_fetch(MiqpB200Solver *s, double *const *x_out, MiqpB200Solve
       in.nodes = (long)s->h_stats[k]; in.qp_iters = (long)s->h_stats[count + k]; in.rounds = s->stats.rounds;
       in.best_bound = s->h_bb[k];
       if (have) {
+        // every open or pruned node may lie above the incumbent: report min(bound, incumbent) like CPLEX's best bound
+        if (in.best_bound > s->h_ub[k]) in.best_bound = s->h_ub[k];
         in.status = MIQP_B200_SUCCESS;
         in.objective = s->h_obj[k];  // re-evaluated on the full vector by evaluate_kernel
         in.max_violation = s->h_viol[k];

@@ -45,3 +45,4 @@ if sum(prof):
             a, mu, rp, sg, lm = tr[k, 8 + 5 * it: 13 + 5 * it]
             print(f"   it {it:2d} alpha {a:.3e} mu {mu:.3e} rp {rp:.3e} sigma {sg:.3e} lmax {lm:.3e}")
         if k >= 2: break
+    print("accepted without convergence (stalled iteration, feasible point):", prof[149])
