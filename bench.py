@@ -305,7 +305,8 @@ def main():
                    "nodes_per_plan_per_round": args.nodes_per_round or "auto"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "plans/s", "h2d_bytes_per_step": st2["h2d_bytes"], "d2h_bytes_per_step": st2["d2h_bytes"],
-                "ms_per_step": 1e3 * e2e_s / args.steps},
+                "ms_per_step": 1e3 * e2e_s / args.steps,
+                "host_ms_last_step": {"pack": st2.get("pack_ms"), "h2d_tables_pool": st2.get("upload_ms"), "d2h_scatter": st2.get("fetch_ms")}},
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": {"value": cpu_rate, "unit": "plans/s", "cores": 1, "kind": "port",

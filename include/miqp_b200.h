@@ -155,6 +155,7 @@ typedef struct MiqpB200RunStats {
   double node_kernel_ms, total_ms;
   long h2d_bytes, d2h_bytes;
   long rows_visited;     /* sum over node relaxations and IPM iterations of active rows */
+  double pack_ms, upload_ms, fetch_ms; /* host wall time of the last batch: flatten into the staging blobs / H2D + tables + pool setup / D2H + scatter */
 } MiqpB200RunStats;
 int miqp_b200_run_stats(const MiqpB200Solver *s, MiqpB200RunStats *out);
 

@@ -68,7 +68,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError(f"nvcc failed on {src}")
         objs.append(obj)
-    cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart"]
+    cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart", "-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

@@ -78,7 +78,7 @@ class CRunStats(C.Structure):
     _fields_ = [("launches", C.c_long), ("node_kernel_launches", C.c_long), ("nodes", C.c_long),
                 ("qp_iters", C.c_long), ("rounds", C.c_long), ("node_kernel_ms", C.c_double),
                 ("total_ms", C.c_double), ("h2d_bytes", C.c_long), ("d2h_bytes", C.c_long),
-                ("rows_visited", C.c_long)]
+                ("rows_visited", C.c_long), ("pack_ms", C.c_double), ("upload_ms", C.c_double), ("fetch_ms", C.c_double)]
 
 
 @dataclass

@@ -3,6 +3,7 @@
 // mode alternatives per car and the MIP-start decisions of a full column vector
 // (src/cplex_wrapper.cpp:494-639).  Pure C++; used by the host driver (solver.cu).
 #pragma once
+#include <cstddef>
 #include <algorithm>
 #include <new>
 #include <cmath>
@@ -40,24 +41,52 @@ using DVec = std::vector<double>;
 using IVec = std::vector<int>;
 #endif
 
-struct Packed {
+template <class DV, class IV>
+struct PackedT {
   std::vector<DevProb> probs;
-  DVec dblob;
-  IVec iblob;
+  DV dblob;
+  IV iblob;
   long total_rows = 0, total_nnz = 0, total_cols = 0, max_rows = 0;
   int maxN = 0, max_ndec = 0, max_kmax = 0, max_z = 0, maxC = 0;
+  // device-filled tables are not staged on the host: they only reserve space behind the inputs of the whole batch
+  long dderived = 0, iderived = 0;
+  void reset() { probs.clear(); dblob.clear(); iblob.clear(); total_rows = total_nnz = total_cols = max_rows = 0;
+                 maxN = max_ndec = max_kmax = max_z = maxC = 0; dderived = iderived = 0; }
 };
+using Packed = PackedT<DVec, IVec>;                                   // the batch: page-locked staging blobs
+using PackedLocal = PackedT<std::vector<double>, std::vector<int>>;   // one worker's share while packing in parallel
 
-inline long push_d(DVec &b, const double *src, size_t n) {
+template <class V> inline long push_d(V &b, const double *src, size_t n) {
   long off = (long)b.size();
   if (src) b.insert(b.end(), src, src + n); else b.resize(b.size() + n, 0.0);
   return off;
 }
-inline long push_i(IVec &b, const int *src, size_t n) {
+template <class V> inline long push_i(V &b, const int *src, size_t n) {
   long off = (long)b.size();
   if (src) b.insert(b.end(), src, src + n); else b.resize(b.size() + n, 0);
   return off;
 }
+
+// Offsets of the device-filled tables are counted from 0 while packing (PackedT::dderived / iderived); place_plan moves
+// a plan to its final position: inputs by (dshift, ishift), device-filled tables by (dder, ider) = end of all inputs + the
+// tables of the plans before it.
+inline void place_plan(DevProb &p, long dshift, long ishift, long dder, long ider, long rows, long nnz, long cols) {
+  static_assert(offsetof(DevProb, o_poly) + 5 * sizeof(long) - offsetof(DevProb, o_safety) == 34 * sizeof(long), "input offsets of the double blob must be contiguous");
+  static_assert(offsetof(DevProb, o_wtab) - offsetof(DevProb, o_envtab) == 5 * sizeof(long), "table offsets of the double blob must be contiguous");
+  static_assert(offsetof(DevProb, o_nalt) - offsetof(DevProb, o_initreg) == 6 * sizeof(long), "input offsets of the int blob must be contiguous");
+  static_assert(offsetof(DevProb, o_obsstep_nnz) - offsetof(DevProb, o_posspre) == 4 * sizeof(long), "table offsets of the int blob must be contiguous");
+  long *d = &p.o_safety;
+  for (int k = 0; k < 35; ++k) d[k] += dshift;
+  long *dt = &p.o_envtab;
+  for (int k = 0; k < 6; ++k) dt[k] += dder;
+  long *i = &p.o_initreg;
+  for (int k = 0; k < 7; ++k) i[k] += ishift;
+  long *it = &p.o_posspre;
+  for (int k = 0; k < 5; ++k) it[k] += ider;
+  p.row_base += rows; p.nnz_base += nnz; p.x_base += cols;
+}
+template <class PK> inline long reserve_d(PK &pk, size_t n) { const long off = pk.dderived; pk.dderived += (long)n; return off; }
+template <class PK> inline long reserve_i(PK &pk, size_t n) { const long off = pk.iderived; pk.iderived += (long)n; return off; }
 
 inline void layout_of(const MiqpB200Problem &q, MiqpB200Layout &l) {
   l.C = q.C; l.N = q.N; l.R = q.R; l.O = q.O; l.L = q.L; l.E = q.E; l.K = q.C - 1;
@@ -135,7 +164,7 @@ inline void mode_alternatives(const MiqpB200Problem &q, int c, std::vector<int> 
   }
 }
 
-inline void pack_one(const MiqpB200Problem &q, Packed &pk) {
+template <class PK> inline void pack_one(const MiqpB200Problem &q, PK &pk) {
   DevProb p;
   std::memset(&p, 0, sizeof p);
   const int N = q.N, R = q.R, C = q.C, O = q.O, L = q.L, E = q.E;
@@ -176,12 +205,12 @@ inline void pack_one(const MiqpB200Problem &q, Packed &pk) {
   p.o_frac = push_d(d, q.frac, (size_t)R * 4);
   const double *poly[6] = {q.poly_sint_ub, q.poly_sint_lb, q.poly_coss_ub, q.poly_coss_lb, q.poly_kappa_max, q.poly_kappa_min};
   for (int k = 0; k < 6; ++k) p.o_poly[k] = push_d(d, poly[k], (size_t)R * 3);
-  p.o_envtab = push_d(d, nullptr, (size_t)p.nEnvEdges * 3);
-  p.o_obstab = push_d(d, nullptr, (size_t)O * N * L * 3);
-  p.o_modetab = push_d(d, nullptr, (size_t)R * 20);
-  p.o_fronttab = push_d(d, nullptr, (size_t)C * R * 12);
-  p.o_cost = push_d(d, nullptr, (size_t)C * N * 16);
-  p.o_wtab = push_d(d, nullptr, (size_t)C * N * 14);
+  p.o_envtab = reserve_d(pk, (size_t)p.nEnvEdges * 3);
+  p.o_obstab = reserve_d(pk, (size_t)O * N * L * 3);
+  p.o_modetab = reserve_d(pk, (size_t)R * 20);
+  p.o_fronttab = reserve_d(pk, (size_t)C * R * 12);
+  p.o_cost = reserve_d(pk, (size_t)C * N * 16);
+  p.o_wtab = reserve_d(pk, (size_t)C * N * 14);
 
   p.o_initreg = push_i(ib, q.initial_region, C);
   p.o_possible = push_i(ib, q.possible_region, (size_t)C * R);
@@ -196,11 +225,11 @@ inline void pack_one(const MiqpB200Problem &q, Packed &pk) {
     ib[p.o_nalt + c] = (int)alts.size();
     for (size_t a = 0; a < alts.size(); ++a) ib[p.o_alt + c * 4 * R + a] = alts[a];
   }
-  p.o_posspre = push_i(ib, nullptr, (size_t)C * (R + 1));
-  p.o_obsrowpre = push_i(ib, nullptr, (size_t)N * (O + 1));
-  p.o_obsnnzpre = push_i(ib, nullptr, (size_t)N * (O + 1));
-  p.o_obsstep_rows = push_i(ib, nullptr, N + 1);
-  p.o_obsstep_nnz = push_i(ib, nullptr, N + 1);
+  p.o_posspre = reserve_i(pk, (size_t)C * (R + 1));
+  p.o_obsrowpre = reserve_i(pk, (size_t)N * (O + 1));
+  p.o_obsnnzpre = reserve_i(pk, (size_t)N * (O + 1));
+  p.o_obsstep_rows = reserve_i(pk, N + 1);
+  p.o_obsstep_nnz = reserve_i(pk, N + 1);
 
   MiqpB200Layout l; layout_of(q, l);
   p.base_nwe = l.base_nwe; p.base_ar = l.base_ar; p.base_rcna = l.base_rcna; p.base_dcc = l.base_dcc;

@@ -16,6 +16,7 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <algorithm>
 #include <vector>
 
@@ -64,6 +65,7 @@ struct MiqpB200Solver {
   int num_sms = 0;
   // batch
   Packed pk;
+  std::vector<hostpack::PackedLocal> pack_parts;
   std::vector<double> time_limits;
   DevBuf<DevProb> d_probs;
   DevBuf<double> d_dblob;
@@ -96,6 +98,7 @@ struct MiqpB200Solver {
   std::vector<unsigned long long> h_stats;
   std::vector<int> h_done;
   int single_maxN = 2;
+  size_t pool_budget = 0;
 };
 
 namespace {
@@ -109,8 +112,8 @@ void upload_packed(MiqpB200Solver *s) {
   Packed &pk = s->pk;
   const int count = (int)pk.probs.size();
   s->d_probs.ensure(count);
-  s->d_dblob.ensure(std::max<size_t>(pk.dblob.size(), 1));
-  s->d_iblob.ensure(std::max<size_t>(pk.iblob.size(), 1));
+  s->d_dblob.ensure(std::max<size_t>(pk.dblob.size() + (size_t)pk.dderived, 1));   // inputs of all plans, then the device-filled tables
+  s->d_iblob.ensure(std::max<size_t>(pk.iblob.size() + (size_t)pk.iderived, 1));
   CK(cudaMemcpyAsync(s->d_probs.p, pk.probs.data(), sizeof(DevProb) * count, cudaMemcpyHostToDevice, s->stream));
   CK(cudaMemcpyAsync(s->d_dblob.p, pk.dblob.data(), sizeof(double) * pk.dblob.size(), cudaMemcpyHostToDevice, s->stream));
   CK(cudaMemcpyAsync(s->d_iblob.p, pk.iblob.data(), sizeof(int) * pk.iblob.size(), cudaMemcpyHostToDevice, s->stream));
@@ -120,15 +123,66 @@ void upload_packed(MiqpB200Solver *s) {
 }
 
 void pack_batch(MiqpB200Solver *s, const MiqpB200Problem *problems, int count) {
-  s->pk.probs.clear(); s->pk.dblob.clear(); s->pk.iblob.clear();   // keeps the page-locked capacity of the last batch
-  s->pk.total_rows = s->pk.total_nnz = s->pk.total_cols = s->pk.max_rows = 0;
-  s->pk.maxN = s->pk.max_ndec = s->pk.max_kmax = s->pk.max_z = s->pk.maxC = 0;
+  Packed &pk = s->pk;
+  pk.reset();   // keeps the page-locked capacity of the last batch
   s->time_limits.clear();
-  for (int k = 0; k < count; ++k) {
-    std::string v = validate(problems[k]);
-    if (!v.empty()) throw std::invalid_argument("plan " + std::to_string(k) + ": " + v);
-    pack_one(problems[k], s->pk);
-    s->time_limits.push_back(problems[k].time_limit);
+  for (int k = 0; k < count; ++k) s->time_limits.push_back(problems[k].time_limit);
+  const int hw = (int)std::thread::hardware_concurrency();
+  const int nthr = std::max(1, std::min(std::min(8, hw > 0 ? hw : 1), count / 128));
+  if (nthr == 1) {
+    for (int k = 0; k < count; ++k) {
+      std::string v = validate(problems[k]);
+      if (!v.empty()) throw std::invalid_argument("plan " + std::to_string(k) + ": " + v);
+      pack_one(problems[k], pk);
+    }
+    for (DevProb &p : pk.probs) hostpack::place_plan(p, 0, 0, (long)pk.dblob.size(), (long)pk.iblob.size(), 0, 0, 0);
+    return;
+  }
+  // large batches: workers pack contiguous shares into local blobs, which are then moved into the staging blobs
+  std::vector<hostpack::PackedLocal> &part = s->pack_parts;   // kept between calls: no fresh pages to fault in
+  part.resize(nthr);
+  for (hostpack::PackedLocal &q : part) q.reset();
+  std::vector<std::string> errs(nthr);
+  {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthr; ++t)
+      th.emplace_back([&, t]() {
+        const int k0 = (int)((long)count * t / nthr), k1 = (int)((long)count * (t + 1) / nthr);
+        for (int k = k0; k < k1; ++k) {
+          std::string v = validate(problems[k]);
+          if (!v.empty()) { errs[t] = "plan " + std::to_string(k) + ": " + v; return; }
+          pack_one(problems[k], part[t]);
+        }
+      });
+    for (std::thread &t : th) t.join();
+  }
+  for (const std::string &e : errs) if (!e.empty()) throw std::invalid_argument(e);
+  std::vector<long> dbase(nthr + 1, 0), ibase(nthr + 1, 0), rbase(nthr + 1, 0), zbase(nthr + 1, 0), cbase(nthr + 1, 0), ddbase(nthr + 1, 0), idbase(nthr + 1, 0);
+  for (int t = 0; t < nthr; ++t) {
+    dbase[t + 1] = dbase[t] + (long)part[t].dblob.size(); ibase[t + 1] = ibase[t] + (long)part[t].iblob.size();
+    ddbase[t + 1] = ddbase[t] + part[t].dderived; idbase[t + 1] = idbase[t] + part[t].iderived;
+    rbase[t + 1] = rbase[t] + part[t].total_rows; zbase[t + 1] = zbase[t] + part[t].total_nnz; cbase[t + 1] = cbase[t] + part[t].total_cols;
+    pk.max_rows = std::max(pk.max_rows, part[t].max_rows); pk.maxN = std::max(pk.maxN, part[t].maxN);
+    pk.max_ndec = std::max(pk.max_ndec, part[t].max_ndec); pk.max_kmax = std::max(pk.max_kmax, part[t].max_kmax);
+    pk.max_z = std::max(pk.max_z, part[t].max_z); pk.maxC = std::max(pk.maxC, part[t].maxC);
+  }
+  pk.total_rows = rbase[nthr]; pk.total_nnz = zbase[nthr]; pk.total_cols = cbase[nthr];
+  pk.dderived = ddbase[nthr]; pk.iderived = idbase[nthr];
+  pk.dblob.resize((size_t)dbase[nthr]); pk.iblob.resize((size_t)ibase[nthr]); pk.probs.resize(count);
+  {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthr; ++t)
+      th.emplace_back([&, t]() {
+        std::memcpy(pk.dblob.data() + dbase[t], part[t].dblob.data(), sizeof(double) * part[t].dblob.size());
+        std::memcpy(pk.iblob.data() + ibase[t], part[t].iblob.data(), sizeof(int) * part[t].iblob.size());
+        const int k0 = (int)((long)count * t / nthr);
+        for (size_t j = 0; j < part[t].probs.size(); ++j) {
+          DevProb p = part[t].probs[j];
+          hostpack::place_plan(p, dbase[t], ibase[t], dbase[nthr] + ddbase[t], ibase[nthr] + idbase[t], rbase[t], zbase[t], cbase[t]);
+          pk.probs[k0 + j] = p;
+        }
+      });
+    for (std::thread &t : th) t.join();
   }
 }
 
@@ -212,9 +266,12 @@ void setup_bnb(MiqpB200Solver *s) {
     if (st.warm_mu > 0.0 && s->n_single > 0) st.zp_stride = s->single_maxN * 8;
     const size_t node_bytes = (size_t)st.ndec_stride + 48 + (size_t)8 * st.zp_stride;
     // pool budget: a third of the free HBM, at most 48 GiB (B200: 180 GB per GPU)
-    size_t free_b = 0, total_b = 0;
-    size_t budget = (size_t)8 << 30;
-    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) budget = std::min<size_t>(free_b / 3, (size_t)48 << 30);
+    if (s->pool_budget == 0) {   // asked once per solver: cudaMemGetInfo costs about a millisecond
+      size_t free_b = 0, total_b = 0;
+      s->pool_budget = (size_t)8 << 30;
+      if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) s->pool_budget = std::min<size_t>(free_b / 3, (size_t)48 << 30);
+    }
+    const size_t budget = s->pool_budget;
     size_t c = budget / (node_bytes * (size_t)count);
     if (c > (1u << 20)) c = 1u << 20;
     if (c < 256) c = 256;
@@ -409,7 +466,9 @@ int miqp_b200_batch_upload(MiqpB200Solver *s, const MiqpB200Problem *problems, i
   try {
     CK(cudaSetDevice(s->opt.device));
     s->uploaded = false; s->ran = false;
+    const auto tp0 = std::chrono::steady_clock::now();
     pack_batch(s, problems, count);
+    const auto tp1 = std::chrono::steady_clock::now();
     upload_packed(s);
     setup_bnb(s);
     // MIP starts
@@ -430,6 +489,8 @@ int miqp_b200_batch_upload(MiqpB200Solver *s, const MiqpB200Problem *problems, i
       s->stats.h2d_bytes += (long)(s->h_warm.size() + sizeof(int) * count);
     }
     CK(cudaStreamSynchronize(s->stream));
+    s->stats.pack_ms = std::chrono::duration<double, std::milli>(tp1 - tp0).count();
+    s->stats.upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp1).count();
     s->uploaded = true;
   } catch (const std::invalid_argument &ex) {
     return fail(s, MIQP_B200_ERR_ARG, ex.what());
@@ -516,6 +577,7 @@ int miqp_b200_batch_fetch(MiqpB200Solver *s, double *const *x_out, MiqpB200Solve
     CK(cudaSetDevice(s->opt.device));
     const int count = s->st.count;
     const long ncols = s->pk.total_cols;
+    const auto tf0 = std::chrono::steady_clock::now();
     s->h_x.resize(ncols); s->h_viol.resize(count); s->h_obj.resize(count); s->h_bb.resize(count); s->h_ub.resize(count);
     s->h_stats.resize((size_t)3 * count); s->h_done.resize(count);
     CK(cudaMemcpyAsync(s->h_x.data(), s->d_x.p, sizeof(double) * ncols, cudaMemcpyDeviceToHost, s->stream));
@@ -528,9 +590,23 @@ int miqp_b200_batch_fetch(MiqpB200Solver *s, double *const *x_out, MiqpB200Solve
     CK(cudaStreamSynchronize(s->stream));
     s->stats.d2h_bytes = (long)(sizeof(double) * (ncols + 4 * count) + sizeof(unsigned long long) * 3 * count + sizeof(int) * count);
     long nodes = 0, iters = 0, rows = 0;
+    if (x_out) {   // scatter of the solution vectors into the caller's buffers: a few host threads for large batches
+      const int nthr = (ncols * (long)sizeof(double) > (8L << 20)) ? 4 : 1;
+      auto scatter = [&](int k0, int k1) {
+        for (int k = k0; k < k1; ++k) {
+          const DevProb &p = s->pk.probs[k];
+          if (x_out[k]) std::memcpy(x_out[k], s->h_x.data() + p.x_base, sizeof(double) * p.ncols);
+        }
+      };
+      if (nthr == 1) scatter(0, count);
+      else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthr; ++t) th.emplace_back(scatter, (int)((long)count * t / nthr), (int)((long)count * (t + 1) / nthr));
+        for (std::thread &t : th) t.join();
+      }
+    }
     for (int k = 0; k < count; ++k) {
       const DevProb &p = s->pk.probs[k];
-      if (x_out && x_out[k]) std::memcpy(x_out[k], s->h_x.data() + p.x_base, sizeof(double) * p.ncols);
       nodes += (long)s->h_stats[k]; iters += (long)s->h_stats[count + k]; rows += (long)s->h_stats[2 * count + k];
       if (!infos) continue;
       MiqpB200SolveInfo &in = infos[k];
@@ -555,6 +631,7 @@ int miqp_b200_batch_fetch(MiqpB200Solver *s, double *const *x_out, MiqpB200Solve
       }
     }
     s->stats.nodes = nodes; s->stats.qp_iters = iters; s->stats.rows_visited = rows;
+    s->stats.fetch_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tf0).count();
   } catch (const std::exception &ex) {
     return fail(s, MIQP_B200_ERR_CUDA, ex.what());
   }

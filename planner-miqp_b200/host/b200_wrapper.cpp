@@ -1,6 +1,7 @@
 // b200_wrapper.cpp -- see b200_wrapper.hpp.  Host driver of libmiqp_b200.so in the shape of the
 // reference's CplexWrapper (src/cplex_wrapper.cpp).
 #include "b200_wrapper.hpp"
+#include "dat_reader.hpp"
 
 #include <chrono>
 #include <cmath>
@@ -257,12 +258,14 @@ bool WriteParametersDat(const MiqpB200Problem &p, const ModelParameters &m, cons
 // ---------------------------------------------------------------------------------------
 B200Wrapper::B200Wrapper() : B200Wrapper(12) {}
 B200Wrapper::B200Wrapper(int precision) : results_(std::make_shared<RawResults>()), precision_(precision) {}
-B200Wrapper::B200Wrapper(const std::string &, const std::string &, ParameterSource, int precision) : B200Wrapper(precision) {}
+B200Wrapper::B200Wrapper(const std::string &modpath, const std::string &, ParameterSource source, int precision) : B200Wrapper(precision) {
+  source_ = source; modPath_ = modpath;
+}
 B200Wrapper::B200Wrapper(const B200Wrapper &o)
     : parameters_(o.parameters_), results_(std::make_shared<RawResults>()), precision_(o.precision_), device_(o.device_),
       useSos_(o.useSos_), useBranchingPriorities_(o.useBranchingPriorities_), bufferOutputs_(o.bufferOutputs_),
       debugPrint_(o.debugPrint_), collectSizes_(o.collectSizes_), prioStart_(o.prioStart_), prioExtent_(o.prioExtent_),
-      debugPath_(o.debugPath_), debugPrefix_(o.debugPrefix_) {}
+      debugPath_(o.debugPath_), debugPrefix_(o.debugPrefix_), source_(o.source_), modPath_(o.modPath_), datFile_(o.datFile_) {}
 B200Wrapper &B200Wrapper::operator=(const B200Wrapper &o) { debugPath_ = o.debugPath_; return *this; }
 B200Wrapper::~B200Wrapper() { if (solver_) miqp_b200_destroy(solver_); }
 
@@ -304,8 +307,16 @@ struct B200Wrapper::Prepared {
 
 bool B200Wrapper::Prepare(double timestamp, Prepared &pr) {
   error_.clear();
-  if (!parameters_) { error_ = "resetParameters() has not been called"; return false; }
-  try { Flatten(*parameters_, precision_, pr.flat); } catch (const std::exception &ex) { error_ = ex.what(); return false; }
+  if (source_ == DATFILE) {   // the file is the problem (fixtures, parameter dumps): no rounding on top of what was written
+    try {
+      if (!parameters_) parameters_ = std::make_shared<ModelParameters>();
+      datio::ReadParametersDat(datFile_, *parameters_);
+      Flatten(*parameters_, 0, pr.flat);
+    } catch (const std::exception &ex) { error_ = ex.what(); return false; }
+  } else {
+    if (!parameters_) { error_ = "resetParameters() has not been called"; return false; }
+    try { Flatten(*parameters_, precision_, pr.flat); } catch (const std::exception &ex) { error_ = ex.what(); return false; }
+  }
   if (miqp_b200_layout(&pr.flat.p, &pr.layout) != MIQP_B200_OK) { error_ = "malformed ModelParameters"; return false; }
   pr.have_warm = false;
   if (useRecedingWarm_ && recedingWarm_ && recedingWarm_->NrCars == pr.layout.C && recedingWarm_->N == pr.layout.N &&

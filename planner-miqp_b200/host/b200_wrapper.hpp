@@ -58,6 +58,10 @@ class B200Wrapper {
   ~B200Wrapper();
 
   void resetParameters(std::shared_ptr<ModelParameters> parameters) { parameters_ = parameters; }
+  // DATFILE source: the OPL .dat file is read at every callCplex (host/dat_reader.hpp); values are taken as written
+  void setParameterDatFileAbsolute(const char *datfile) { datFile_ = datfile; }
+  void setParameterDatFileRelative(const char *datfile) { datFile_ = modPath_ + datfile; }
+  void setParameterSource(ParameterSource src) { source_ = src; }
   void addRecedingHorizonWarmstart(std::shared_ptr<RawResults> warmstart, WarmstartType type);
   void setLastSolutionWarmstart(WarmstartType type);
   void deleteLastSolutionWarmstartFile();
@@ -98,6 +102,8 @@ class B200Wrapper {
   bool useSos_ = false, useBranchingPriorities_ = false, bufferOutputs_ = false, debugPrint_ = false, collectSizes_ = false;
   int prioStart_ = 1, prioExtent_ = 0;
   std::string debugPath_, debugPrefix_, lastParameterFile_, error_;
+  ParameterSource source_ = CPPINPUTS;
+  std::string modPath_, datFile_;
   // MIP starts
   std::shared_ptr<RawResults> recedingWarm_;
   bool useRecedingWarm_ = false, useLastSolution_ = false;

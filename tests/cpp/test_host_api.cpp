@@ -6,6 +6,7 @@
 #include <cstring>
 #include <string>
 
+#include "../../planner-miqp_b200/host/dat_reader.hpp"
 #include "../../planner-miqp_b200/host/miqp_planner.hpp"
 
 using namespace miqp::planner;
@@ -88,6 +89,34 @@ static void cpu_part() {
   CHECK(std::isnan(y[l.base_ar + 19 * 16]) && !std::isnan(y[l.base_ar + 18 * 16]) && !std::isnan(y[19]));
 }
 
+static std::string g_root;   // repository root (argv[2])
+
+// .dat dialect: the reference fixture parses into ModelParameters, and a written dump reads back unchanged
+static void dat_part() {
+  ModelParameters m;
+  datio::ReadParametersDat(g_root + "/tests/golden/cplexmodel_testcase.dat", m);
+  CHECK(m.NumSteps == 20 && m.nr_regions == 32 && m.NumCars == 1 && m.nr_obstacles == 1 && m.nr_environments == 1 && m.max_lines_obstacles == 4);
+  CHECK(std::fabs(m.ts - 0.2f) < 1e-7 && std::fabs(m.relative_mip_gap_tolerance - 0.1f) < 1e-7 && m.max_solution_time == 60.f);
+  CHECK(m.IntitialState(0, MIQP_STATE_VX) == 5.0 && m.IntitialState(0, MIQP_STATE_VY) == 0.1 && m.x_ref(0, 19) == 19.0);
+  CHECK(m.ObstacleConvexPolygon.size() == 1 && m.ObstacleConvexPolygon[0].size() == 20 && m.ObstacleConvexPolygon[0][0].rows() == 4);
+  CHECK(m.ObstacleConvexPolygon[0][3](0, 0) == 23.0 && m.ObstacleConvexPolygon[0][3](0, 1) == -1.0 && m.ObstacleConvexPolygon[0][3](2, 0) == 17.0);
+  CHECK(m.fraction_parameters.rows() == 32 && m.poly_curvature_params.POLY_KAPPA_AX_MAX.rows() == 32 && m.obstacle_is_soft[0] == 0);
+  cplex::FlatProblem f1, f2;
+  cplex::Flatten(m, 0, f1);
+  const std::string tmp = "/tmp/miqp_b200_test_roundtrip.dat";
+  CHECK(cplex::WriteParametersDat(f1.p, m, tmp));
+  ModelParameters m2;
+  datio::ReadParametersDat(tmp, m2);
+  cplex::Flatten(m2, 0, f2);
+  CHECK(f1.p.N == f2.p.N && f1.p.R == f2.p.R && f1.p.O == f2.p.O && f1.p.E == f2.p.E && f1.p.ts == f2.p.ts);
+  bool same = f1.d.size() == f2.d.size();
+  for (size_t k = 0; same && k < f1.d.size(); ++k) same = (f1.d[k] == f2.d[k]);   // 12 printed digits reproduce every fixture value
+  CHECK(same);
+  bool threw = false;
+  try { datio::ReadParametersDat("/nonexistent.dat", m2); } catch (const std::runtime_error &) { threw = true; }
+  CHECK(threw);
+}
+
 static void gpu_part() {
   Settings s = DefaultSettings();
   s.relative_mip_gap_tolerance = 1e-4f;
@@ -131,6 +160,27 @@ static void gpu_part() {
   CHECK(!blocked.Plan(0.0));
   SolutionProperties bp = blocked.GetSolutionProperties();
   CHECK(std::isnan(bp.objective) && std::isnan(bp.gap) && bp.status == 103);
+  // DATFILE source (reference test/cplex_wrapper_test.cc:474-505): the dump written by a CPPINPUTS solve, solved again
+  // from the file, gives the same objective and gap
+  {
+    MiqpPlanner src(sc, map);
+    src.AddCar(st, ref, 5, 1);
+    src.AddObstacle({{20.0, 1.0, 0.0}}, 2.0, 1.0, false, true);
+    src.ActivateDebugFileWrite("/tmp", "miqp_b200_hostapi_");
+    CHECK(src.Plan(7.0));
+    const std::string dump = src.GetCplexWrapper().getDebugOutputParameterFilePath();
+    CHECK(!dump.empty());
+    CplexWrapper fromfile("", "cplexmodel.mod", CplexWrapper::DATFILE, 12);
+    fromfile.setParameterDatFileAbsolute(dump.c_str());
+    CHECK(fromfile.callCplex(7.0) == SUCCESS);
+    const SolutionProperties a1 = src.GetSolutionProperties(), a2 = fromfile.getSolutionProperties();
+    CHECK(std::fabs(a1.objective - a2.objective) <= 1e-7 * std::fabs(a1.objective) && a2.gap <= 1e-4);
+    // the reference fixture through the same path: known optimum 9.57603 (test/cplex_wrapper_test.cc:874)
+    CplexWrapper fixture("", "cplexmodel.mod", CplexWrapper::DATFILE, 12);
+    fixture.setParameterDatFileAbsolute((g_root + "/tests/golden/cplexmodel_testcase.dat").c_str());
+    CHECK(fixture.callCplex(0.0) == SUCCESS);
+    CHECK(std::fabs(fixture.getSolutionProperties().objective - 9.57603) <= 0.1 * 9.57603);   // the file asks for a 10 % gap
+  }
   // batched dispatch
   MiqpPlanner p1(sc, map), p2(sc, map);
   double s1[6] = {0, 3, 0, 0.5, 0.1, 0}, s2[6] = {0, 6, 0, -0.5, 0.1, 0};
@@ -140,7 +190,9 @@ static void gpu_part() {
 }
 
 int main(int argc, char **argv) {
+  g_root = (argc > 2) ? argv[2] : ".";
   cpu_part();
+  dat_part();
   if (argc > 1 && std::strcmp(argv[1], "gpu") == 0) gpu_part();
   std::printf(failures ? "%d check(s) failed\n" : "all checks passed\n", failures);
   return failures ? 1 : 0;

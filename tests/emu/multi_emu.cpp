@@ -49,6 +49,10 @@ extern "C" int emu_multi_solve(const MiqpB200Problem *q, double gap_tol, double 
   if (!v.empty()) { fprintf(stderr, "emu: %s\n", v.c_str()); return -2; }
   pack_one(*q, pk);
   DevProb &p = pk.probs[0];
+  // the device-filled tables live behind the inputs (host_pack.hpp:place_plan); on the host they need real storage
+  place_plan(p, 0, 0, (long)pk.dblob.size(), (long)pk.iblob.size(), 0, 0, 0);
+  pk.dblob.resize(pk.dblob.size() + (size_t)pk.dderived, 0.0);
+  pk.iblob.resize(pk.iblob.size() + (size_t)pk.iderived, 0);
   prepare_tables_parallel(p, pk.dblob.data(), pk.iblob.data(), 0, 1);
   prepare_tables_serial(p, pk.dblob.data(), pk.iblob.data());
   const int nds = p.ndec_pad;
