@@ -31,6 +31,17 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
+# Everything libraries print to fd 1 (NCCL prints its version there at the first collective) goes to stderr;
+# the one JSON line is written to the real stdout.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 GAP = 1e-4
 WORKLOAD = "single agent, static + dynamic-occupancy obstacle, N=40, R=32 (BASELINE.json configs[1])"
 
@@ -145,7 +156,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "plans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -316,7 +327,7 @@ def main():
                    "oracle_mismatches_in_sample": mism, "nodes_per_plan": st["nodes"] / B, "rounds": st["rounds"]},
         "wall_s_timed_region": t_wall,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
