@@ -314,16 +314,13 @@ MQ_FN MNodeOut m_process_node(const MCtx &k, MShared *sh, double nbound, double 
   const MQpResult r = m_solve_node_qp(k);
   out.iters = r.iters; out.rows = r.rows;
   if (r.status != 0) return out;
-  // fval: objective of the point found (an upper bound of the relaxation); obj: lower bound of the node.  A stalled
-  // interior-point iteration yields a feasible point but no bound: the node keeps the bound of its parent (bnb.cu).
-  const double fval = r.obj + pen;
-  double obj = r.converged ? fval : nbound;
+  double obj = r.obj + pen;
   if (obj < nbound) obj = nbound;  // numerical monotonicity
   out.obj = obj;
   if (obj >= cutoff) { out.what = MN_PRUNED; return out; }
   MBranch br;
   const int und = m_scan_node(k, br, &sh->br, ndec_pad);
-  if (br.kind == 0 && und == 0) { out.what = MN_INCUMBENT; out.obj = fval > obj ? fval : obj; return out; }
+  if (br.kind == 0 && und == 0) { out.what = MN_INCUMBENT; return out; }
   out.what = MN_BRANCH;
   if (br.kind == 0) { out.nalt = 1; out.from_imp = true; out.soff = -1; if (k.tid == 0) sh->cb[0] = obj; k.sync(); return out; }
   if (br.kind == 1) {
@@ -348,7 +345,7 @@ MQ_FN MNodeOut m_process_node(const MCtx &k, MShared *sh, double nbound, double 
   }
   k.sync();
   // child bounds; children that reach the cutoff are dropped here
-  PFOR(a, out.nalt) sh->cb[a] = r.converged ? fmax(obj, fval + 0.999 * m_alt_delta(k, br, sh->alts[a])) : obj;
+  PFOR(a, out.nalt) sh->cb[a] = fmax(obj, r.obj + pen + 0.999 * m_alt_delta(k, br, sh->alts[a]));
   k.sync();
   if (k.tid == 0) {
     int n = 0; double pm = MQM_INF;

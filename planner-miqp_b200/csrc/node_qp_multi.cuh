@@ -782,7 +782,7 @@ MQ_FN void m_riccati_forward(const MCtx &k, double *dst) {
   }
 }
 
-struct MQpResult { int status, iters; double obj; long rows; int converged; };   // converged == 0: stalled iteration, obj is only an upper bound
+struct MQpResult { int status, iters; double obj; long rows; };
 
 // Solves the node QP of k.dec (k.jeff filled).  On success Z holds the optimal stage vectors
 // and sig[..][SG_VAL] the slacks.
@@ -790,7 +790,7 @@ MQ_FN MQpResult m_solve_node_qp(const MCtx &k) {
   const DevProb &p = *k.p;
   const double *D = k.D;
   const int N = k.N, C = k.C, nz = k.nz, P = k.P, nxx = k.nxx;
-  MQpResult res; res.status = 1; res.iters = 0; res.obj = 0.0; res.rows = 0; res.converged = 0;
+  MQpResult res; res.status = 1; res.iters = 0; res.obj = 0.0; res.rows = 0;
 
   // trivially infeasible boxes
   int bad = 0;
@@ -955,7 +955,6 @@ MQ_FN MQpResult m_solve_node_qp(const MCtx &k) {
     if (alpha < 1e-6) { if (++stall >= 5) { status = 2; break; } } else stall = 0;
   }
   res.iters = it;
-  res.converged = (status == 0);
   if (status != 0) {
     // not converged: infeasible only if the primal point violates its rows
     PairAcc acc; acc.worst = 0.0;
