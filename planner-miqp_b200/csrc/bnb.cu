@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(SEL_THREADS) bnb_select_kernel(BnbState st, co
   const int s = blockIdx.x;
   const int tid = threadIdx.x;
   __shared__ int warp_tot[SEL_THREADS / 32];
-  __shared__ int s_out, s_free, s_tie, s_wbase;
+  __shared__ int s_out, s_free, s_tie, s_wbase, s_nsusp;
   __shared__ int hist[256];
   __shared__ double s_pruned[SEL_THREADS / 32];
   __shared__ unsigned long long s_prefix; __shared__ int s_remaining;
@@ -114,8 +114,12 @@ __global__ void __launch_bounds__(SEL_THREADS) bnb_select_kernel(BnbState st, co
   // 1. release the slots processed in the last round
   const int nsel_prev = st.sel_cnt[s];
   const int free0 = st.free_cnt[s];
-  for (int k = tid; k < nsel_prev; k += SEL_THREADS) st.free_stack[pb + free0 + k] = st.sel_idx[(long)s * KS + k];
-  if (tid == 0) { s_free = free0 + nsel_prev; s_out = 0; s_tie = 0; }
+  // (a parked relaxation keeps its node slot: it is back in the open list and continues this round)
+  if (tid == 0) {
+    int f = free0;
+    for (int k = 0; k < nsel_prev; ++k) { const int sl = st.sel_idx[(long)s * KS + k]; if (!st.susp_slot || st.susp_slot[pb + sl] < 0) st.free_stack[pb + f++] = sl; }
+    s_free = f; s_out = 0; s_tie = 0; s_nsusp = 0;
+  }
   // 2. cutoff snapshot
   const double ub = st.ub[s];
   const bool have_inc = ub < MQ_INF;
@@ -146,7 +150,10 @@ __global__ void __launch_bounds__(SEL_THREADS) bnb_select_kernel(BnbState st, co
       slot = st.open_idx[pb + idx];
       const double b = st.bound[pb + slot];
       keep = (b < cutoff);
-      if (keep) { int2 m = st.meta[pb + slot]; key = node_key(b, m.x, meta_rank(m.y), st.uid[pb + slot], have_inc, meta_birth(m.y) == round - 1); }
+      const bool parked = st.susp_slot && st.susp_slot[pb + slot] >= 0;
+      if (parked && !keep) st.susp_slot[pb + slot] = -1;                 // pruned while parked
+      if (parked && keep) { key = 0ULL; atomicAdd(&s_nsusp, 1); }        // continues first: its state is only kept for one round
+      else if (keep) { int2 m = st.meta[pb + slot]; key = node_key(b, m.x, meta_rank(m.y), st.uid[pb + slot], have_inc, meta_birth(m.y) == round - 1); }
       else { pruned = fmin(pruned, b); int pos = atomicAdd(&s_free, 1); st.free_stack[pb + pos] = slot; }
     }
     int total; const int rank = block_excl_scan(keep, warp_tot, total);
@@ -167,6 +174,7 @@ __global__ void __launch_bounds__(SEL_THREADS) bnb_select_kernel(BnbState st, co
   }
   // a plan whose frontier stays large after pruning is a hard one: let it run wide even while the easy
   // plans still fill the machine (its sequential depth, not the node count, is what ends the batch)
+  K += s_nsusp; if (K > KS) K = KS;   // parked relaxations do not take the place of new nodes
   if (have_inc && st.wide_div > 0) { int kw = n1 / st.wide_div; if (kw > KS) kw = KS; if (kw > K) K = kw; }
   // 4. threshold key of the K best
   unsigned long long T = ~0ULL; int remaining = n1;  // take everything
@@ -234,7 +242,7 @@ __global__ void __launch_bounds__(SEL_THREADS) bnb_select_kernel(BnbState st, co
   }
 }
 
-__global__ void bnb_round_reset_kernel(BnbState st) { *st.active_prev = *st.active; *st.work_cnt = 0; *st.work_next = 0; *st.active = 0; *st.work_cnt2 = 0; *st.work_next2 = 0; }
+__global__ void bnb_round_reset_kernel(BnbState st) { if (st.susp_cnt) *st.susp_cnt = 0; *st.active_prev = *st.active; *st.work_cnt = 0; *st.work_next = 0; *st.active = 0; *st.work_cnt2 = 0; *st.work_next2 = 0; }
 
 void launch_bnb_select(const BnbState &st, const DevProb *probs, int round, cudaStream_t s) {
   bnb_round_reset_kernel<<<1, 1, 0, s>>>(st);
@@ -558,7 +566,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 2 ? 3 : NW == 4 ? 2 : 1) bnb_no
     const long pb = (long)s * st.cap;
     w.p = &p; w.N = p.N;
     w.sg = team_sublanes(p.N, nw); w.spw = 32 / w.sg; w.ls = lane / w.sg; w.g = lane - w.ls * w.sg;
-    w.sgmul = 65536 / w.sg + 1; w.NP = team_row_stride(p.N, w.sg);
+    w.sgmul = 65536 / w.sg + 1; w.NP = team_row_stride(p.N, w.sg); w.kmax = st.kmax;
     double pen = 0.0;
     if (wid == 0) {
       copy_bytes16(w.dec, st.dec + (pb + slot) * st.ndec_stride, st.ndec_stride, lane);
@@ -580,7 +588,26 @@ __global__ void __launch_bounds__(NW * 32, NW == 2 ? 3 : NW == 4 ? 2 : 1) bnb_no
 #endif
     const double *zw = st.zpool ? st.zpool + (pb + slot) * (long)st.zp_stride : nullptr;
     if (zw && !(zw[0] == zw[0])) zw = nullptr;   // NaN marks a node without parent optimum
-    QpResult r = solve_node_qp(w, e1, e2, zw, st.warm_mu);
+    SuspendIO sio;
+    sio.resume = nullptr; sio.pool = nullptr; sio.counter = st.susp_cnt; sio.nslots = st.susp_slots; sio.stride = st.susp_stride; sio.budget = st.susp_budget;
+    if (st.susp_slot) {
+      const int ss = st.susp_slot[pb + slot];
+      if (ss >= 0) sio.resume = st.susp_pool[(round + 1) & 1] + (long)ss * st.susp_stride;   // parked by the previous round
+      sio.pool = st.susp_pool[round & 1];
+    }
+    QpResult r = solve_node_qp(w, e1, e2, zw, st.warm_mu, sio);
+    if (r.status == 3) {
+      // parked: the node stays open (its bound still counts) and continues in the next round
+      if (threadIdx.x == 0) {
+        st.susp_slot[pb + slot] = r.susp_index;
+        const int opos = atomicAdd(&st.open_cnt[s], 1);
+        st.open_idx[pb + opos] = slot;
+        atomicAdd(&st.stat_iters[s], (unsigned long long)r.iters);
+        atomicAdd(&st.stat_rows[s], (unsigned long long)r.rows);
+      }
+      continue;
+    }
+    if (threadIdx.x == 0 && st.susp_slot) st.susp_slot[pb + slot] = -1;
     if (wid != 0) continue;
     // ---- warp 0: bookkeeping, scan of the relaxed optimum, children ----
     const double nbound = st.bound[pb + slot];
@@ -704,6 +731,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 2 ? 3 : NW == 4 ? 2 : 1) bnb_no
         st.meta[pb + cs] = make_int2(nmeta.x >= (1 << 20) ? nmeta.x : nmeta.x + 1, (round << 8) | (rank + 1));
         st.uid[pb + cs] = mix64(nuid * 0x9e3779b97f4a7c15ULL + (unsigned long long)(a + 1));
         st.open_idx[pb + opos + a] = cs;
+        if (st.susp_slot) st.susp_slot[pb + cs] = -1;
       }
     }
     __syncwarp();

@@ -39,6 +39,9 @@ struct BnbState {
   int *free_stack; int *free_cnt;
   int *sel_idx; int *sel_cnt;      // slots handed to the node kernel in the last round [count][sel_per_plan]
   unsigned long long *keybuf;      // [count][cap]
+  // suspended relaxations: a node whose interior-point solve exceeds its iteration budget is parked with its state and
+  // continues in the next round (two pools, written alternately; susp_slot = index in the pool of the round that parked it)
+  double *susp_pool[2]; int *susp_slot; int *susp_cnt; int susp_slots; long susp_stride; int susp_budget;
   double *zpool;        // [count][cap][zp_stride] relaxed optimum of the parent (warm start of the child's interior-point solve); null = off
   int zp_stride;
   double warm_mu;       // complementarity target of the warm start

@@ -81,6 +81,7 @@ struct WarpCtx {
   int sg, g, ls, spw;   // sub-lanes per stage, my sub-lane, my stage slot in the warp (idle if >= spw), stages per warp
   int sgmul;            // 65536 / sg + 1: slot % sg without a division
   int NP;               // stage stride of `rows`
+  int kmax;             // row slots per stage
   __device__ __forceinline__ bool mine(int slot) const { const int q = (slot * sgmul) >> 16; return slot - q * sg == g; }
 };
 
@@ -626,7 +627,8 @@ __device__ __forceinline__ void riccati_forward(const WarpCtx &w, int dst) {
 }
 
 struct QpResult {
-  int status;     // 0 optimal (or, with converged == 0, merely a feasible point), 1 infeasible
+  int status;     // 0 optimal (or, with converged == 0, merely a feasible point), 1 infeasible, 3 parked (iteration budget used up)
+  int susp_index; // status 3: slot of the saved state
   int converged;  // 1: obj is the optimum of the relaxation (a valid bound); 0: the iteration stalled, obj is only an upper bound
   int iters;
   double obj;     // without soft-decision penalties
@@ -641,12 +643,22 @@ struct QpResult {
 // null) = relaxed optimum of the parent node, [N][8].  On
 // success V_Z holds the optimal stage vectors.  All control decisions derive from team_reduce results,
 // which are bitwise identical in every thread, so the barriers inside stay uniform.
-__device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEntry &e1, const PhiEntry &e2, const double *zwarm, double warm_mu) {
+// Parked relaxations: state = header (8 doubles: iteration, stall count, alpha, sigma mu, pending, dual residual, cn, -) +
+// the stage vectors V + the (s, lambda) records.
+constexpr int SUSP_HDR = 8;
+struct SuspendIO {
+  const double *resume;   // state to continue from (null: fresh solve)
+  double *pool;           // pool of this round (null: never park)
+  int *counter; int nslots; long stride; int budget;
+};
+
+__device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEntry &e1, const PhiEntry &e2, const double *zwarm, double warm_mu,
+                                                  const SuspendIO &sio) {
   const DevProb &p = *w.p;
   const double *D = w.D;
   const int N = w.N;
   const bool lead = (w.g == 0);
-  QpResult res; res.status = 1; res.converged = 0; res.iters = 0; res.obj = 0.0; res.rows = 0;
+  QpResult res; res.status = 1; res.converged = 0; res.iters = 0; res.obj = 0.0; res.rows = 0; res.susp_index = -1;
 #ifdef MQ_PROF
   res.c_rows = res.c_factor = res.c_sweeps = 0; res.c_a = res.c_ared = res.c_d = res.c_e = res.c_g = res.c_atr = 0;
   long long qc0 = 0;
@@ -660,8 +672,22 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
 #define MQ_T1(field)
 #endif
 
+  const int nV = (N * V_STRIDE + 1) & ~1, nRows = (w.kmax + 1) * N;   // stage vectors (doubles), (s, lambda) records (double2)
+  double cn = 0.0, rdn = 0.0;
+  StepCtx sc; sc.alpha = 0.0; sc.sigmu = 0.0; sc.pending = false;
+  int stall = 0, it0 = 0;
+  if (sio.resume) {
+    // continue a parked relaxation: stage vectors, (s, lambda) records and the scalars of the iteration
+    const double *hdr = sio.resume;
+    it0 = (int)hdr[0]; stall = (int)hdr[1]; sc.alpha = hdr[2]; sc.sigmu = hdr[3]; sc.pending = hdr[4] != 0.0; rdn = hdr[5]; cn = hdr[6];
+    for (int k = threadIdx.x; k < N * V_STRIDE; k += blockDim.x) w.V[k] = hdr[SUSP_HDR + k];
+    // records are parked as [slot][N]: the padded stride NP depends on the team size, which may differ between the rounds
+    const double2 *src = reinterpret_cast<const double2 *>(hdr + SUSP_HDR + nV);
+    for (int k = threadIdx.x; k < nRows; k += blockDim.x) { const int sl = k / N; w.rows[sl * w.NP + (k - sl * N)] = src[k]; }
+    __syncthreads();
+  } else {
   // trivially infeasible boxes (build_node_qp of the oracle); cn = largest linear cost coefficient
-  double bad = 0.0, cn = 0.0, z0 = 0.0, z1 = 0.0;
+  double bad = 0.0, z0 = 0.0, z1 = 0.0;
   MQ_FOR_STAGES(i, act) {
     if (!act || !lead) continue;
     const unsigned char m = (i > 0) ? w.dec[p.off_mode + i] : (unsigned char)0;
@@ -683,7 +709,6 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
 
   // start: zero jerk (free response), s = max(h - g.z, 1), lambda = 1
   const double x0[6] = {D[p.o_x0], D[p.o_x0 + 1], D[p.o_x0 + 2], D[p.o_x0 + 3], D[p.o_x0 + 4], D[p.o_x0 + 5]};
-  double rdn = 0.0;
   MQ_FOR_STAGES(i, act) {
     PassInit v; v.io.init(w.rows, w.NP, act ? i : 0);
 #pragma unroll
@@ -720,10 +745,28 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
     }
   }
   { double q0 = 0.0, q1 = 0.0, q2 = 0.0; team_reduce(w, rdn, q0, q1, q2); }
+  }   // fresh solve
 
-  StepCtx sc; sc.alpha = 0.0; sc.sigmu = 0.0; sc.pending = false;
-  int status = 2, stall = 0, it = 0;
-  for (it = 0; it < 100; ++it) {
+  int status = 2, it = 0;
+  bool may_park = (sio.pool != nullptr);
+  for (it = it0; it < 100; ++it) {
+    if (may_park && it - it0 >= sio.budget) {
+      // iteration budget of this round used up: park the relaxation (it continues in the next round) if a slot is left
+      if (threadIdx.x == 0) w.red[0] = (double)atomicAdd(sio.counter, 1);
+      __syncthreads();
+      const int ss = (int)w.red[0];
+      __syncthreads();
+      if (ss < sio.nslots) {
+        double *hdr = sio.pool + (long)ss * sio.stride;
+        if (threadIdx.x == 0) { hdr[0] = it; hdr[1] = stall; hdr[2] = sc.alpha; hdr[3] = sc.sigmu; hdr[4] = sc.pending ? 1.0 : 0.0; hdr[5] = rdn; hdr[6] = cn; hdr[7] = 0.0; }
+        for (int k = threadIdx.x; k < N * V_STRIDE; k += blockDim.x) hdr[SUSP_HDR + k] = w.V[k];
+        double2 *dst = reinterpret_cast<double2 *>(hdr + SUSP_HDR + nV);
+        for (int k = threadIdx.x; k < nRows; k += blockDim.x) { const int sl = k / N; dst[k] = w.rows[sl * w.NP + (k - sl * N)]; }
+        res.status = 3; res.susp_index = ss; res.iters = it - it0;
+        return res;
+      }
+      may_park = false;   // pool exhausted: run to the end
+    }
     // ---- pass A ----
     double rpn = 0.0, musum = 0.0, lmax = 0.0, mcount = 0.0;
     MQ_FOR_STAGES(i, act) {
@@ -856,7 +899,7 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
     __syncthreads();
     if (alpha < 1e-6) { if (++stall >= 5) { status = 2; break; } } else stall = 0;
   }
-  res.iters = it;
+  res.iters = it - it0;
   res.converged = (status == 0);
   MQ_TICK(c_rows)
   if (status != 0) {

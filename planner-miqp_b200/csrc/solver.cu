@@ -79,7 +79,8 @@ struct MiqpB200Solver {
   // bnb state buffers
   BnbState st;
   DevBuf<unsigned char> b_dec, b_incdec;
-  DevBuf<double> b_bound, b_ub, b_cutoff, b_pruned, b_incz, b_zpool, b_dbg;
+  DevBuf<double> b_bound, b_ub, b_cutoff, b_pruned, b_incz, b_zpool, b_dbg, b_susp0, b_susp1;
+  DevBuf<int> b_suspslot, b_suspcnt;
   DevBuf<int2> b_meta, b_work;
   DevBuf<unsigned long long> b_uid, b_keybuf, b_incuid, b_stats, b_prof;
   DevBuf<int> b_open, b_opencnt, b_free, b_freecnt, b_sel, b_selcnt, b_done, b_lock, b_ctrl;
@@ -283,6 +284,19 @@ void setup_bnb(MiqpB200Solver *s) {
   const size_t nodes = (size_t)count * cap;
   s->b_dec.ensure(nodes * st.ndec_stride); st.dec = s->b_dec.p;
   s->b_bound.ensure(nodes); st.bound = s->b_bound.p;
+  // parked relaxations (single-car nodes): iteration budget per round, two state pools written alternately
+  st.susp_budget = 10;   // profiles/r1k: 2048 plans 129 -> 86 ms, 1024 plans 78 -> 53 ms (budgets 6 / 8 / 12 / 16: 98 / 97 / 96 / 101 ms)
+  if (const char *e = getenv("MIQP_SUSP_BUDGET")) st.susp_budget = atoi(e);
+  st.susp_slot = nullptr; st.susp_cnt = nullptr; st.susp_pool[0] = st.susp_pool[1] = nullptr; st.susp_slots = 0; st.susp_stride = 0;
+  if (st.susp_budget > 0 && s->n_single > 0) {
+    const int np = s->single_maxN + 7;
+    st.susp_stride = (8 + (long)s->single_maxN * 35 + 1 + 2L * (st.kmax + 1) * np + 1) & ~1L;   // SUSP_HDR + V + (s, lambda) records, 16-byte aligned
+    st.susp_slots = std::min(st.work_cap, 4096);
+    s->b_susp0.ensure((size_t)st.susp_slots * st.susp_stride); s->b_susp1.ensure((size_t)st.susp_slots * st.susp_stride);
+    st.susp_pool[0] = s->b_susp0.p; st.susp_pool[1] = s->b_susp1.p;
+    s->b_suspslot.ensure(nodes); st.susp_slot = s->b_suspslot.p;
+    s->b_suspcnt.ensure(1); st.susp_cnt = s->b_suspcnt.p;
+  }
   st.zpool = nullptr;
   if (st.zp_stride > 0) { s->b_zpool.ensure(nodes * (size_t)st.zp_stride); st.zpool = s->b_zpool.p; }
   s->b_meta.ensure(nodes); st.meta = s->b_meta.p;
@@ -366,7 +380,7 @@ void miqp_b200_destroy(MiqpB200Solver *s) {
   s->b_pruned.release(); s->b_incz.release(); s->b_meta.release(); s->b_work.release();
   s->b_uid.release(); s->b_keybuf.release(); s->b_incuid.release(); s->b_stats.release(); s->b_open.release();
   s->b_opencnt.release(); s->b_free.release(); s->b_freecnt.release(); s->b_sel.release(); s->b_selcnt.release();
-  s->b_zpool.release(); s->b_done.release(); s->b_lock.release(); s->b_ctrl.release(); s->b_multi_ws.release(); s->b_work2.release();
+  s->b_zpool.release(); s->b_susp0.release(); s->b_susp1.release(); s->b_suspslot.release(); s->b_suspcnt.release(); s->b_done.release(); s->b_lock.release(); s->b_ctrl.release(); s->b_multi_ws.release(); s->b_work2.release();
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   if (s->evr0) cudaEventDestroy(s->evr0);
@@ -512,6 +526,7 @@ int miqp_b200_batch_run(MiqpB200Solver *s, float *device_ms) {
     long launches = 0, node_launches = 0, rounds = 0;
     double node_ms = 0.0;
     CK(cudaMemsetAsync(s->b_prof.p, 0, 256 * sizeof(unsigned long long), s->stream));
+    if (s->st.susp_slot) CK(cudaMemsetAsync(s->st.susp_slot, 0xff, sizeof(int) * (size_t)s->st.count * s->st.cap, s->stream));
     CK(cudaEventRecord(s->ev0, s->stream));
     launch_bnb_init(s->st, s->d_probs.p, s->any_warm ? s->d_warm.p : nullptr, s->any_warm ? s->d_haswarm.p : nullptr, s->stream);
     ++launches;
