@@ -84,3 +84,19 @@ def test_full_size_batch_properties(solver):
     xs2, infos2 = solver.solve_batch([plans[k] for k in sub], gap_tol=GAP, time_limit=600.0)
     for k, i2 in zip(sub, infos2):
         assert i2.objective == pytest.approx(infos[k].objective, rel=2 * GAP)
+
+
+def test_parked_relaxations_do_not_change_the_result(testcase_problem, monkeypatch):
+    """a node relaxation that runs out of its per-round iteration budget is parked in HBM and continues in the next
+    round (bnb.cu / node_qp.cuh:SuspendIO); with a tiny budget almost every relaxation is parked several times"""
+    plans = [obstacle_scenario(s).build() for s in range(12)] + [testcase_problem]
+    results = {}
+    for budget in ("0", "3", "10"):
+        monkeypatch.setenv("MIQP_SUSP_BUDGET", budget)
+        s = P.Solver()
+        xs, infos = s.solve_batch(plans, gap_tol=GAP, time_limit=120.0)
+        s.close()
+        assert all(i.status == 0 and i.proven and i.max_violation <= 1e-6 for i in infos), budget
+        results[budget] = [i.objective for i in infos]
+    for a, b, c in zip(results["0"], results["3"], results["10"]):
+        assert b == pytest.approx(a, rel=2 * GAP) and c == pytest.approx(a, rel=2 * GAP)
