@@ -16,6 +16,8 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=o
 # formulation.cu is compared bit for bit with the oracle: no FMA contraction there
 if os.environ.get("MIQP_PROF") == "1":      # per-phase cycle counters of the node kernel (miqp_b200_debug_profile)
     COMMON.append("-DMQ_PROF")
+if os.environ.get("MIQP_TEAMS_PER_SM"):
+    COMMON.append("-DMQ_TEAMS_PER_SM=" + os.environ["MIQP_TEAMS_PER_SM"])
 UNITS = [("formulation.cu", ["--fmad=false"]), ("bnb.cu", []), ("bnb_multi.cu", []), ("solver.cu", []), ("peaks.cu", [])]
 
 

@@ -528,7 +528,7 @@ int node_kernel_smem_per_warp(int maxN, int kmax, int ndec_stride) { return node
 // NW = 8 (one CTA per SM, 6 sub-lanes per stage at N = 40) is launched for rounds that hold fewer nodes than SMs: the
 // round time is then the latency of its slowest node, and the wider team shortens the row passes.
 template <int NW>
-__global__ void __launch_bounds__(NW * 32, NW == 2 ? 3 : NW == 4 ? 2 : 1) bnb_nodes_kernel(BnbState st, const DevProb *probs, const double *dblob,
+__global__ void __launch_bounds__(NW * 32, NW == 4 ? NODE_TEAMS_PER_SM : 1) bnb_nodes_kernel(BnbState st, const DevProb *probs, const double *dblob,
                                                                                             const int *iblob, int smem_per_node, int maxN, int round) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double s_red[32];

@@ -67,6 +67,10 @@ void launch_bnb_init(const BnbState &st, const DevProb *probs, const unsigned ch
                      const int *has_warm, cudaStream_t s);
 void launch_bnb_select(const BnbState &st, const DevProb *probs, int round, cudaStream_t s);
 constexpr int NODE_TEAM_WARPS = 4;        // warps that share one node relaxation (bnb_nodes_kernel), 2 teams per SM
+#ifndef MQ_TEAMS_PER_SM
+#define MQ_TEAMS_PER_SM 2
+#endif
+constexpr int NODE_TEAMS_PER_SM = MQ_TEAMS_PER_SM;   // 2: 255 registers per thread; 3: 168 registers (spills), A/B in profiles/r1k
 constexpr int NODE_TEAM_WARPS_WIDE = 8;   // the same for rounds with fewer nodes than SMs, 1 team per SM
 // returns 0 or a cudaError
 int launch_bnb_nodes(const BnbState &st, const DevProb *probs, const double *dblob, const int *iblob,

@@ -224,7 +224,7 @@ void setup_bnb(MiqpB200Solver *s) {
     }
     int fm = 1;
     if (const char *e = getenv("MIQP_FILL_MULT")) fm = std::max(1, atoi(e));
-    st.nwarps += s->ctas * fm;
+    st.nwarps += 2 * s->num_sms * fm;   // the round-width rules are tuned for two teams per SM, whatever the launch uses
   }
   if (s->n_multi > 0) {
     s->multi_threads = (maxCm <= 2) ? 64 : 128;
