@@ -29,3 +29,25 @@ def test_layout_is_host_only(testcase_problem):
 def test_no_cpu_fallback():
     with pytest.raises(P.MiqpB200Error):
         P.Solver()
+
+
+def test_every_function_declared_in_the_headers_is_exported():
+    """parses include/*.h for function declarations and looks each one up in the shared libraries"""
+    import ctypes
+    import os
+    import re
+    from planner_miqp_b200 import planner_capi as PC
+    inc = os.path.join(os.path.dirname(__file__), "..", "include")
+    solver = P.load_library()
+    planner = PC.load_library()
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(inc, "miqp_b200.h")).read(), flags=re.S)
+    names = sorted(set(re.findall(r"\b(miqp_b200_\w+)\s*\(", text)))
+    assert len(names) >= 16
+    for n in names:
+        assert hasattr(solver, n), n
+    assert sorted(names) == sorted(P.DECLARED_SYMBOLS)
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(inc, "miqp_planner_c_api.h")).read(), flags=re.S)
+    names = sorted(set(re.findall(r"\b(\w+CMiqpPlan\w*|GetCollisionRadius)\s*\(", text)))
+    assert len(names) == 19, names
+    for n in names:
+        assert hasattr(planner, n), n
