@@ -260,7 +260,7 @@ void setup_bnb(MiqpB200Solver *s) {
   int cap = s->opt.pool_capacity;
   if (cap <= 0) {
     // warm start of the children from the parent's relaxed optimum (single-car nodes): N x 8 doubles per node
-    st.warm_mu = 0.0; st.zp_stride = 0;
+    st.warm_mu = 10.0; st.zp_stride = 0;   // profiles/r1k: with parked relaxations 84.2 -> 76.9 ms (2048 plans), 8.6 -> 7.7 iterations per node
     st.tau_k = 1.0;   // profiles/r1k: 9.45 -> 8.6 interior-point iterations per node
     if (const char *e = getenv("MIQP_TAU_K")) st.tau_k = atof(e);
     if (const char *e = getenv("MIQP_WARM_MU")) st.warm_mu = atof(e);
