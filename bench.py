@@ -270,7 +270,7 @@ def main():
     peaks = measured_peaks()
     # algorithmic HBM bytes: every node relaxation reads its record and writes its children
     ndec = 6 * N + 5 * plans[0].O * N
-    node_bytes = 2.0 * (ndec + 32)
+    node_bytes = 2.0 * (ndec + 32 + 64 * N)   # decisions + bookkeeping + the parent's relaxed optimum (8 N doubles), read once and written per child
     hbm_gbs = st["nodes"] * node_bytes / (node_ms_last * 1e-3) / 1e9 if node_ms_last > 0 else 0.0
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "node_kernel_traffic.json")
