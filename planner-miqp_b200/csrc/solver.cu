@@ -285,7 +285,7 @@ void setup_bnb(MiqpB200Solver *s) {
   s->b_dec.ensure(nodes * st.ndec_stride); st.dec = s->b_dec.p;
   s->b_bound.ensure(nodes); st.bound = s->b_bound.p;
   // parked relaxations (single-car nodes): iteration budget per round, two state pools written alternately
-  st.susp_budget = 10;   // profiles/r1k: 2048 plans 129 -> 86 ms, 1024 plans 78 -> 53 ms (budgets 6 / 8 / 12 / 16: 98 / 97 / 96 / 101 ms)
+  st.susp_budget = 8;   // profiles/r1k: cold starts 10 was best (129 -> 86 ms); with the warm start 6 / 7 / 8 / 10 / 12: 88 / 83 / 69 / 77 / 88 ms per 2048 plans
   if (const char *e = getenv("MIQP_SUSP_BUDGET")) st.susp_budget = atoi(e);
   st.susp_slot = nullptr; st.susp_cnt = nullptr; st.susp_pool[0] = st.susp_pool[1] = nullptr; st.susp_slots = 0; st.susp_stride = 0;
   if (st.susp_budget > 0 && s->n_single > 0) {
