@@ -480,5 +480,23 @@ void MiqpPlanner::Get2ndOrderStateFromSolution(int i, int c, double out[6]) cons
   out[3] = r->pos_y(c, i); out[4] = r->vel_y(c, i); out[5] = r->acc_y(c, i);
 }
 
+std::vector<std::array<double, 5>> MiqpPlanner::GetTrajectory(int c, double start_time) const {
+  const std::shared_ptr<RawResults> r = cplexWrapper_.getRawResults();
+  std::vector<std::array<double, 5>> out;
+  const float dt = parameters_->ts;
+  for (int i = 0; i < r->N; ++i) {
+    const double vx = r->vel_x(c, i), vy = r->vel_y(c, i);
+    if (!IsVxVyValid(vx, vy)) break;   // heading undefined from here on
+    out.push_back({start_time + i * dt, r->pos_x(c, i), r->pos_y(c, i), std::atan2(vy, vx), std::sqrt(vx * vx + vy * vy)});
+  }
+  return out;
+}
+
+void MiqpPlanner::CarStateToMiqpState(float x, float y, float theta, float v, float a, double out[6]) {
+  out[MIQP_STATE_X] = (double)x; out[MIQP_STATE_Y] = (double)y;
+  out[MIQP_STATE_VX] = (double)(std::cos(theta) * v); out[MIQP_STATE_VY] = (double)(std::sin(theta) * v);
+  out[MIQP_STATE_AX] = (double)(std::cos(theta) * a); out[MIQP_STATE_AY] = (double)(std::sin(theta) * a);
+}
+
 }  // namespace planner
 }  // namespace miqp

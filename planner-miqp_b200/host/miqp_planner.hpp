@@ -18,6 +18,8 @@
 // (common/map/convexified_map.cpp, Voronoi + merging) is outside the hot path and not rebuilt:
 // UpdateConvexifiedMap returns false for such input.
 #pragma once
+#include <array>
+#include <cmath>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -83,8 +85,15 @@ class MiqpPlanner {
   const std::vector<RefPoint> &GetLastReference(int carIdx) const { return referenceGenerator_.at(carIdx).GetLastTrajectory(); }
   void ActivateDebugFileWrite(const std::string &path, const std::string &name);
   void SetDoWarmstart(MiqpPlannerWarmstartType in) { doWarmstart_ = in; }
-  // state {x, vx, ax, y, vy, ay} of the plan at step timeIdx (Get2ndOrderStateFromSolution)
+  // state {x, vx, ax, y, vy, ay} of the plan at step timeIdx (Get2ndOrderStateFromSolution / GetThirdOrderStateAtResultIdx)
   void Get2ndOrderStateFromSolution(int timeIdx, int carIdx, double out[6]) const;
+  // Plan of one car as rows {t, x, y, theta, v} (the reference's GetBarkTrajectory, src/miqp_planner.cpp:1132-1170):
+  // theta = atan2(vy, vx), v = |(vx, vy)|; the trajectory is cut at the first step whose |vx| and |vy| are both
+  // <= 0.7 m/s, where the heading is no longer defined.
+  std::vector<std::array<double, 5>> GetTrajectory(int carIdx, double start_time) const;
+  static bool IsVxVyValid(double vx, double vy) { return std::fabs(vx) > 0.7 || std::fabs(vy) > 0.7; }
+  // {x, y, theta, v, a} -> {x, vx, ax, y, vy, ay}, in float like the reference (src/miqp_planner.cpp:1189-1199)
+  static void CarStateToMiqpState(float x, float y, float theta, float v, float a, double out[6]);
 
  private:
   struct PlanContext { std::vector<std::vector<int>> combos; size_t next = 0; std::vector<char> rollback; bool ready = false; };

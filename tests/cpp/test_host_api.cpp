@@ -65,6 +65,11 @@ static void cpu_part() {
   threw = false;
   try { MiqpPlanner q(bad); } catch (const std::invalid_argument &) { threw = true; }
   CHECK(threw);
+  // state conversions of the facade
+  double ms[6];
+  MiqpPlanner::CarStateToMiqpState(1.f, 2.f, (float)M_PI / 2, 3.f, 0.5f, ms);
+  CHECK(ms[MIQP_STATE_X] == 1.0 && ms[MIQP_STATE_Y] == 2.0 && std::fabs(ms[MIQP_STATE_VX]) < 1e-6 && std::fabs(ms[MIQP_STATE_VY] - 3.0) < 1e-6 && std::fabs(ms[MIQP_STATE_AY] - 0.5) < 1e-6);
+  CHECK(MiqpPlanner::IsVxVyValid(0.71, 0.0) && MiqpPlanner::IsVxVyValid(0.0, -0.8) && !MiqpPlanner::IsVxVyValid(0.7, -0.7));
   // the solver class keeps the reference's configuration surface
   CplexWrapper w("cplexmodel/", "cplexmodel.mod", CplexWrapper::CPPINPUTS, 12);
   w.setSpecialOrderedSets(true); w.setUseBranchingPriorities(true); w.setBranchingPriorityValueExtent(1, 19);
@@ -143,6 +148,11 @@ static void gpu_part() {
   CHECK(rr->N == 20 && rr->NrCars == 1 && rr->pos_x(0, 0) == 0.0 && rr->active_region(0, 0, 0) == 1);
   for (int i = 0; i < 20; ++i) { int sum = 0; for (int j = 0; j < 16; ++j) sum += rr->active_region(0, i, j); CHECK(sum == 1); }
   CHECK(planner.HasValidWarmstart());
+  {   // {t, x, y, theta, v} rows of the plan; the car drives along +x at about 4-5 m/s
+    const std::vector<std::array<double, 5>> tr = planner.GetTrajectory(0, 1.0);
+    CHECK(tr.size() == 20 && tr[0][0] == 1.0 && std::fabs(tr[1][0] - 1.25) < 1e-12 && tr[0][1] == 0.0);
+    CHECK(std::fabs(tr[0][3] - std::atan2(0.1, 4.0)) < 1e-9 && std::fabs(tr[0][4] - std::sqrt(16.01)) < 1e-9 && tr[19][1] > 15.0);
+  }
   // receding horizon: the next plan starts from the shifted solution and reaches the same objective as a cold planner
   double nxt[6]; planner.Get2ndOrderStateFromSolution(1, 0, nxt);
   planner.UpdateCar(0, nxt, ref);
