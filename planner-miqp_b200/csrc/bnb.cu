@@ -12,11 +12,12 @@
 //                      bound, picks the K best nodes (radix select on 64-bit priority keys:
 //                      depth first until an incumbent exists, best bound first afterwards)
 //                      and appends them to the global work list.
-//   bnb_nodes_kernel   persistent warps pull (plan, node) items from the work list; each warp
-//                      solves its node relaxation (node_qp.cuh), scans the relaxed optimum for
-//                      violated disjunctions, and either records an incumbent, or pushes the
-//                      children (one per alternative of the most violated disjunction) onto
-//                      the plan's pool.
+//   bnb_nodes_kernel   persistent teams (one CTA of four warps, eight when a round holds fewer nodes than SMs) pull
+//                      (plan, node) items from the work list; a team solves its node relaxation (node_qp.cuh)
+//                      -- started from the parent's relaxed optimum, parked in HBM and continued next round if it
+//                      needs more than its iteration budget --, warp 0 then scans the relaxed optimum for violated
+//                      disjunctions and either records an incumbent or pushes the children (one per alternative
+//                      of the most violated disjunction, with their lower bounds) onto the plan's pool.
 //
 // The host only launches rounds and polls one integer (number of unfinished plans).
 #include "kernels.cuh"
