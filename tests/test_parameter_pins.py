@@ -93,3 +93,24 @@ def test_possible_regions_of_a_straight_reference_cpp(tmp_path):
     got = read_dat(path)
     assert list(np.flatnonzero(got.possible_region[0])) == [0, 1, 30, 31]
     p.close()
+
+
+def test_reference_trajectory_pins_python_and_cpp():
+    """common/tests/reference_trajectory_generator_test.cc:22-95: straight centre line, speed ramp over 0.1 m"""
+    from planner_miqp_b200.model_parameters import PolyLine, reference_trajectory
+    line = PolyLine([[0, 0], [50, 0], [100, 0]], 0.2)
+    traj = reference_trajectory(line, 0.0, 0.0, 5.0, 20, 0.2, 10.0, 0.1)      # rows x, y, theta, v; row 0 is filled by the caller
+    assert traj[1, 3] == pytest.approx(10.0, abs=1e-3) and traj[-1, 3] == pytest.approx(10.0, abs=1e-3)
+    assert traj[1, 0] == pytest.approx(5.0 * 0.2, abs=1e-3) and traj[2, 0] == pytest.approx(5.0 * 0.2 + 10.0 * 0.2, abs=1e-3)
+    slow = reference_trajectory(line, 0.0, 0.0, 0.1, 20, 0.2, 10.0, 0.1)      # "starting": from 0.1 m/s
+    assert slow[1, 3] > 0.1 and slow[-1, 3] == pytest.approx(10.0, abs=1e-3)
+    s = PC.default_settings()
+    s.ts = 0.2
+    p = PC.CMiqpPlanner(s)
+    p.add_car([0, 5, 0, 0, 0, 0], [0, 0, 50, 0, 100, 0], 10.0, 0.1)
+    ref = p.last_reference(0)
+    v = np.hypot(ref[:, 3], ref[:, 4])
+    assert v[0] == pytest.approx(5.0, abs=1e-3) and v[1] == pytest.approx(10.0, abs=1e-3) and v[-1] == pytest.approx(10.0, abs=1e-3)
+    assert ref[1, 1] == pytest.approx(1.0, abs=1e-3) and ref[2, 1] == pytest.approx(3.0, abs=1e-3)
+    np.testing.assert_allclose(ref[1:, 1], traj[1:, 0], atol=1e-9)             # C++ and Python generators agree point by point
+    p.close()
