@@ -114,3 +114,33 @@ def test_reference_trajectory_pins_python_and_cpp():
     assert ref[1, 1] == pytest.approx(1.0, abs=1e-3) and ref[2, 1] == pytest.approx(3.0, abs=1e-3)
     np.testing.assert_allclose(ref[1:, 1], traj[1:, 0], atol=1e-9)             # C++ and Python generators agree point by point
     p.close()
+
+
+def test_fitting_table_spot_values():
+    """common/tests/fitting_polynomial_parameters_test.cc:26-34, :59-76 and test/miqp_planner_test.cc:127-134 (exact values)"""
+    from planner_miqp_b200.model_parameters import fitting_tables
+    t32 = fitting_tables(32, 20, 2)
+    assert t32["POLY_SINT_UB"][0, 0] == 0.18825 and t32["POLY_SINT_UB"][31, 2] == 0.049029
+    assert t32["POLY_COSS_LB"][0, 0] == 0.97651
+    assert list(t32["POLY_SINT_UB"][7]) == [1.0047, -0.0055247, 0.00032035]
+    t16 = fitting_tables(16, 20, 2)
+    assert t16["POLY_SINT_UB"][0, 0] == 0.348508875688441 and t16["POLY_SINT_UB"][3, 0] == 1.0037509353218053
+    assert fitting_tables(64, 10, 1)["POLY_SINT_UB"].shape == (64, 3)
+    for bad in ((64, 20, 2), (128, 10, 1), (32, 15, 2)):          # combinations the reference does not ship throw
+        with pytest.raises(ValueError):
+            fitting_tables(*bad)
+
+
+def test_fitting_tables_in_the_cpp_host(tmp_path):
+    """the C++ host selects the same tables (generated include of host/planner_prep.hpp): 16 regions, default settings"""
+    from planner_miqp_b200.model_parameters import fitting_tables
+    p = PC.CMiqpPlanner(PC.default_settings())
+    p.add_car([0, 5, 0, 0, 0.1, 0], [0, 0, 100, 0], 5, 1)
+    path = str(tmp_path / "p.txt")
+    assert p.write_parameters(path)
+    got = read_dat(path)
+    t16 = fitting_tables(16, 20, 2)
+    for k in t16:
+        np.testing.assert_allclose(got.poly[k], np.round(t16[k], 10), atol=1e-12, err_msg=k)   # reals enter the model rounded to 10 decimals
+    assert got.poly["POLY_SINT_UB"][0, 0] == pytest.approx(0.348508875688441, abs=1e-10)
+    p.close()
