@@ -379,6 +379,17 @@ OptimizationStatus B200Wrapper::Finish(const Prepared &pr, const MiqpB200SolveIn
   return info.status == MIQP_B200_FAILED_TIMEOUT ? FAILED_TIMEOUT : FAILED_NO_SOLUT;
 }
 
+bool B200Wrapper::setSolutionVector(const double *x, int ncols) {
+  if (!parameters_) return false;
+  FlatProblem f;
+  MiqpB200Layout l;
+  try { Flatten(*parameters_, precision_, f); } catch (const std::exception &) { return false; }
+  if (miqp_b200_layout(&f.p, &l) != MIQP_B200_OK || l.ncols != ncols) return false;
+  Unpack(l, x, *results_);
+  lastX_.assign(x, x + ncols); lastLayout_ = l; haveLast_ = true;
+  return true;
+}
+
 OptimizationStatus B200Wrapper::callCplex(double timestamp) {
   Prepared pr;
   if (!Prepare(timestamp, pr)) return FAILED_SEG_FAULT;

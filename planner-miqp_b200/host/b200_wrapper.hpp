@@ -83,6 +83,8 @@ class B200Wrapper {
   static std::vector<OptimizationStatus> callBatch(const std::vector<B200Wrapper *> &solvers, double timestamp = 0.0);
 
   std::shared_ptr<RawResults> getRawResults() const { return results_; }
+  // injects a solution vector as if a solve had returned it (replay of recorded solutions, tests of the warm-start logic)
+  bool setSolutionVector(const double *x, int ncols);
   SolutionProperties getSolutionProperties() const { return props_; }
   const std::vector<double> &getSolutionVector() const { return lastX_; }
   const std::string &lastError() const { return error_; }

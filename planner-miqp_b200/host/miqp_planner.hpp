@@ -85,6 +85,8 @@ class MiqpPlanner {
   const std::vector<RefPoint> &GetLastReference(int carIdx) const { return referenceGenerator_.at(carIdx).GetLastTrajectory(); }
   void ActivateDebugFileWrite(const std::string &path, const std::string &name);
   void SetDoWarmstart(MiqpPlannerWarmstartType in) { doWarmstart_ = in; }
+  // receding-horizon MIP start from the solution the solver currently holds (what Plan() does after a success)
+  void RecomputeWarmstart() { CalculateWarmstart(); }
   // state {x, vx, ax, y, vy, ay} of the plan at step timeIdx (Get2ndOrderStateFromSolution / GetThirdOrderStateAtResultIdx)
   void Get2ndOrderStateFromSolution(int timeIdx, int carIdx, double out[6]) const;
   // Plan of one car as rows {t, x, y, theta, v} (the reference's GetBarkTrajectory, src/miqp_planner.cpp:1132-1170):

@@ -158,6 +158,21 @@ void GetSolutionPropertiesCMiqpPlanner(CMiqpPlanner h, double out[8]) {
   out[5] = s.NrConstraints; out[6] = s.NrBinaryVariables; out[7] = s.NrFloatVariables;
 }
 
+// test hooks: inject a solution vector (decision_variables.mod order) and read back the receding-horizon MIP start the
+// planner derives from it (MiqpPlanner::CalculateWarmstart), packed into the same column order (NaN = undecided)
+bool DebugSetSolutionCMiqpPlanner(CMiqpPlanner h, const double *x, int ncols) { return P(h)->GetCplexWrapper().setSolutionVector(x, ncols); }
+int DebugWarmstartCMiqpPlanner(CMiqpPlanner h, double *out, int ncols, bool relax_last_step) {
+  P(h)->RecomputeWarmstart();
+  miqp::planner::cplex::FlatProblem f;
+  MiqpB200Layout l;
+  miqp::planner::cplex::Flatten(*P(h)->GetParameters(), P(h)->GetSettings().precision, f);
+  if (miqp_b200_layout(&f.p, &l) != MIQP_B200_OK || l.ncols != ncols) return -1;
+  std::vector<double> x;
+  miqp::planner::cplex::Pack(l, *P(h)->GetWarmstart(), relax_last_step, x);
+  for (int k = 0; k < ncols; ++k) out[k] = x[k];
+  return ncols;
+}
+
 // test hook: the flattened problem of the planner's current ModelParameters, written as an OPL .dat file
 bool DebugWriteParametersCMiqpPlanner(CMiqpPlanner h, const char *path, int initial_region_combination) {
   miqp::planner::cplex::FlatProblem f;

@@ -117,6 +117,10 @@ def load_library():
     lib.GetSolutionPropertiesCMiqpPlanner.argtypes = [vp, _dp]
     lib.DebugWriteParametersCMiqpPlanner.argtypes = [vp, C.c_char_p, i]
     lib.DebugWriteParametersCMiqpPlanner.restype = b
+    lib.DebugSetSolutionCMiqpPlanner.argtypes = [vp, _dp, i]
+    lib.DebugSetSolutionCMiqpPlanner.restype = b
+    lib.DebugWarmstartCMiqpPlanner.argtypes = [vp, _dp, i, b]
+    lib.DebugWarmstartCMiqpPlanner.restype = i
     _lib = lib
     return lib
 
@@ -215,6 +219,17 @@ class CMiqpPlanner:
         self.lib.GetSolutionPropertiesCMiqpPlanner(self.h, out.ctypes.data_as(_dp))
         keys = ("objective", "gap", "time", "status", "nodes", "rows", "binaries", "continuous")
         return dict(zip(keys, out.tolist()))
+
+    def set_solution(self, x) -> bool:
+        a, ap = _arr(x)
+        return bool(self.lib.DebugSetSolutionCMiqpPlanner(self.h, ap, a.size))
+
+    def warmstart_vector(self, ncols: int, relax_last_step: bool = True) -> np.ndarray:
+        out = np.zeros(ncols)
+        n = self.lib.DebugWarmstartCMiqpPlanner(self.h, out.ctypes.data_as(_dp), ncols, relax_last_step)
+        if n != ncols:
+            raise ValueError("column count does not match the planner's model")
+        return out
 
     def write_parameters(self, path: str) -> bool:
         return bool(self.lib.DebugWriteParametersCMiqpPlanner(self.h, path.encode(), 0))

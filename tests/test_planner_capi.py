@@ -145,3 +145,41 @@ def test_host_preparation_matches_python_builder(tmp_path, state, ref, vdes):
     diff = np.argwhere(np.asarray(got.possible_region) != mask_start)
     assert len(diff) <= 1
     p.close()
+
+
+def test_receding_horizon_warm_start_matches_python_mirror(tmp_path):
+    """MiqpPlanner::CalculateWarmstart (C++, reference src/miqp_planner.cpp:787-1051) against results.shift_warmstart:
+    every family one step to the left, Euler extrapolation of the last step, last step of the binaries undecided"""
+    from planner_miqp_b200.capi import ncols_of
+    from planner_miqp_b200.results import shift_warmstart, block_views
+    p = PC.CMiqpPlanner(PC.default_settings())
+    p.add_car([0, 4, 0, 0, 0.1, 0], [0, 0, 50, 0], 5, 1)
+    box = [[[20, -1], [23, -1], [23, 2], [20, 2]]] * p.N
+    assert p.add_obstacle(box) == 0
+    path = str(tmp_path / "p.txt")
+    assert p.write_parameters(path)
+    prob = read_dat(path)
+    n = ncols_of(prob)
+    rng = np.random.default_rng(3)
+    x = np.zeros(n)
+    v = block_views(prob, x)
+    for name, a in v.items():
+        if a.dtype == np.float64 and name in ("u_x", "u_y", "pos_x", "vel_x", "acc_x", "pos_y", "vel_y", "acc_y",
+                                               "pos_x_front_UB", "pos_x_front_LB", "pos_y_front_UB", "pos_y_front_LB"):
+            a[...] = rng.normal(size=a.shape) * 3.0 + 5.0
+        else:
+            a[...] = rng.integers(0, 2, size=a.shape)
+    assert p.set_solution(x)
+    w_cpp = p.warmstart_vector(n, relax_last_step=True)
+    w_py = shift_warmstart(prob, x, relax_last=True)
+    vc, vp = block_views(prob, w_cpp), block_views(prob, w_py)
+    for name in ("u_x", "u_y", "pos_x", "vel_x", "acc_x", "pos_y", "vel_y", "acc_y"):
+        np.testing.assert_allclose(vc[name], vp[name], atol=1e-12, err_msg=name)
+    for name in ("deltacc", "deltacc_front", "region_change_not_allowed_x_positive"):
+        np.testing.assert_array_equal(np.isnan(vc[name]), np.isnan(vp[name]), err_msg=name)
+        np.testing.assert_array_equal(np.nan_to_num(vc[name]), np.nan_to_num(vp[name]), err_msg=name)
+    # active region: shifted, last step undecided
+    np.testing.assert_array_equal(vc["active_region"][:, :-1], v["active_region"][:, 1:])
+    assert np.all(np.isnan(vc["active_region"][:, -1]))
+    assert not p.set_solution(x[:-1])          # wrong size is refused
+    p.close()
