@@ -37,33 +37,33 @@ struct MiqpPlannerSettings {
   float ts;                              /* step length [s] */
   int precision;                         /* reals enter the model rounded to precision-2 decimals */
   /* --- model constants --- */
-  float constant_agent_safety_distance_slack;
-  float minimum_region_change_speed;
+  float constant_agent_safety_distance_slack; /* [m] soft safety distance between cars */
+  float minimum_region_change_speed;     /* [m/s] below it the orientation region is frozen */
   float lambda;                          /* cost share of the ego car in a joint plan */
-  float wheelBase;
-  float collisionRadius;
-  float slackWeight;
-  float slackWeightObstacle;
-  float jerkWeight;
-  float positionWeight;
-  float velocityWeight;
+  float wheelBase;                       /* [m] rear axle to front axle */
+  float collisionRadius;                 /* [m] radius of the two circles (rear / front axle) */
+  float slackWeight;                     /* cost of the agent-to-agent safety slack */
+  float slackWeightObstacle;             /* cost of giving up a soft obstacle */
+  float jerkWeight;                      /* tracking weights: scaled by lambda (ego) or (1 - lambda) / (cars - 1) */
+  float positionWeight;                  /*   position error */
+  float velocityWeight;                  /*   velocity error */
   float acclerationWeight;               /* (sic) spelling is part of the ABI */
-  float accLonMaxLimit;
-  float accLonMinLimit;
-  float jerkLonMaxLimit;
-  float accLatMinMaxLimit;
-  float jerkLatMinMaxLimit;
+  float accLonMaxLimit;                  /* [m/s^2] straight-driving limits, rotated into every region */
+  float accLonMinLimit;                  /* [m/s^2] (negative) */
+  float jerkLonMaxLimit;                 /* [m/s^3] symmetric */
+  float accLatMinMaxLimit;               /* [m/s^2] symmetric */
+  float jerkLatMinMaxLimit;              /* [m/s^3] symmetric */
   /* --- geometry preparation (CPU) --- */
-  float simplificationDistanceMap;
-  float simplificationDistanceReferenceLine;
-  float bufferReference;
-  float buffer_for_merging_tolerance;
-  float refLineInterpInc;
-  int additionalStepsForReferenceLongerHorizon;
+  float simplificationDistanceMap;       /* [m] Douglas-Peucker tolerance of the road polygon */
+  float simplificationDistanceReferenceLine; /* [m] the same for reference lines */
+  float bufferReference;                 /* [m] cells within this distance of a reference are kept */
+  float buffer_for_merging_tolerance;    /* [m] slack when convex cells are merged */
+  float refLineInterpInc;                /* [m] resampling step of reference lines */
+  int additionalStepsForReferenceLongerHorizon; /* extra steps of the reference used for the possible regions */
   /* --- solver --- */
   float max_solution_time;               /* time limit [s] */
   float relative_mip_gap_tolerance;      /* stop at |bound - incumbent| / (1e-10 + |incumbent|) <= this */
-  int mipdisplay;
+  int mipdisplay;                        /* CPLEX knobs from here to mircuts: stored, not used */
   int mipemphasis;
   float relobjdif;
   int cutpass;
@@ -73,17 +73,17 @@ struct MiqpPlannerSettings {
   int varsel;
   int mircuts;
   char cplexModelpath[1000];
-  bool useSos;
-  bool useBranchingPriorities;
+  bool useSos;                           /* stored; region choices are multi-way disjunctions anyway */
+  bool useBranchingPriorities;           /* stored, not used */
   enum MiqpPlannerWarmstartType warmstartType;
   enum MiqpPlannerParallelMode parallelMode;
   float max_velocity_fitting;            /* vmax of the fitted polynomial tables (10 or 20) */
   bool buffer_cplex_outputs;
   /* --- obstacle region of interest --- */
-  bool obstacle_roi_filter;
-  float obstacle_roi_behind_distance;
-  float obstacle_roi_front_distance;
-  float obstacle_roi_side_distance;
+  bool obstacle_roi_filter;              /* drop obstacles outside a rectangle around the ego car */
+  float obstacle_roi_behind_distance;    /* [m] */
+  float obstacle_roi_front_distance;     /* [m] */
+  float obstacle_roi_side_distance;      /* [m] */
 };
 
 #ifndef __cplusplus
