@@ -183,3 +183,29 @@ def test_receding_horizon_warm_start_matches_python_mirror(tmp_path):
     assert np.all(np.isnan(vc["active_region"][:, -1]))
     assert not p.set_solution(x[:-1])          # wrong size is refused
     p.close()
+
+
+def test_parameter_dump_of_a_two_car_plan_with_environment(tmp_path):
+    """the OPL .dat dump written by the C++ host (reference: parameters_<t>.txt, src/cplex_wrapper.cpp:141-155) is read back by
+    the oracle's parser: two cars, one drivable cell, a moving obstacle"""
+    s = PC.default_settings()
+    p = PC.CMiqpPlanner(s)
+    assert p.update_map([-50, -50, -50, 50, 50, 50, 50, -50, -50, -50])
+    assert p.add_car([0, 4, 0, 1, -0.1, 0], [0, 0, 50, 0], 10, 1) == 0
+    assert p.add_car([20, -4, 0, -1, 0.1, 0], [20, 0, -30, 0], 10, 1) == 1
+    box = [[[5 + 0.2 * i, 3], [7 + 0.2 * i, 3], [7 + 0.2 * i, 5], [5 + 0.2 * i, 5]] for i in range(p.N)]
+    assert p.add_obstacle(box, is_static=False, is_soft=True) == 0
+    path = str(tmp_path / "two_cars.txt")
+    assert p.write_parameters(path)
+    got = read_dat(path)
+    assert (got.C, got.N, got.R, got.O, got.L) == (2, 20, 16, 1, 4)
+    assert got.obs_soft[0] == 1 and np.all(got.obs_nedges == 4)
+    np.testing.assert_allclose(got.obs_edges[0, 3, 0], [5.6, 3, 7.6, 3], atol=1e-9)       # edge 0 of step 3: vertex 0 -> vertex 1
+    np.testing.assert_allclose(got.x0, [[0, 4, 0, 1, -0.1, 0], [20, -4, 0, -1, 0.1, 0]], atol=1e-9)
+    # ego gets lambda = 0.5 of the weights, the other car the rest (src/miqp_planner.cpp:346-352)
+    np.testing.assert_allclose(got.car["WEIGHTS_POS_X"], [1.0, 1.0], atol=1e-9)
+    np.testing.assert_allclose(got.car["WEIGHTS_JERK_X"], [0.5, 0.5], atol=1e-9)
+    assert got.ref["x_ref"].shape == (2, 20) and got.ref["x_ref"][1, -1] < 20 < got.ref["x_ref"][0, -1] + 25
+    # the environment is selected inside Plan() (ResetEnvironment); before the first plan the dump has none
+    assert got.E == 0
+    p.close()
