@@ -324,7 +324,9 @@ def main():
                          "sample": f"first {sample} plans of the batch, oracle/miqp_oracle_bnb.c, {cpu_dt:.1f} s"},
         "latency_p50_ms": {"e2e": statistics.median(lat_e2e), "device": statistics.median(lat_dev), "plans": len(lat_e2e)},
         "solved": {"proven_optimal": n_ok_all, "plans": world * B, "worst_violation": worst_viol,
-                   "oracle_mismatches_in_sample": mism, "nodes_per_plan": st["nodes"] / B, "rounds": st["rounds"]},
+                   "oracle_mismatches_in_sample": mism, "nodes_per_plan": st["nodes"] / B, "rounds": st["rounds"],
+                   "nodes_closed_without_certificate": sum(i.uncertified for i in infos),
+                   "plans_with_exhausted_pool": sum(i.pool_exhausted for i in infos)},
         "wall_s_timed_region": t_wall,
     }
     emit(line)

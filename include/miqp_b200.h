@@ -37,7 +37,7 @@ enum {
   MIQP_B200_ERR_CUDA = -1,        /* no device / CUDA runtime error (see miqp_b200_last_error) */
   MIQP_B200_ERR_ARG = -2,         /* malformed problem or argument */
   MIQP_B200_ERR_UNSUPPORTED = -3, /* shape outside what the kernels are built for */
-  MIQP_B200_ERR_RESOURCE = -4     /* node pool exhausted */
+  MIQP_B200_ERR_RESOURCE = -4     /* (unused since pool exhaustion is reported per plan: MiqpB200SolveInfo.pool_exhausted) */
 };
 
 /* OptimizationStatus of the reference (src/cplex_wrapper.hpp:54-59) */
@@ -102,6 +102,8 @@ typedef struct MiqpB200SolveInfo {
   double seconds;        /* wall time of the batch this plan was solved in */
   double max_violation;  /* of the returned vector against the full big-M model, device-evaluated */
   long nodes, qp_iters, rounds;
+  long uncertified;      /* node relaxations closed without optimum, feasible point or Farkas certificate; their bounds stay in best_bound */
+  int pool_exhausted;    /* 1: the node pool of this plan ran out (children were dropped, their bound stays in best_bound; result not proven) */
 } MiqpB200SolveInfo;
 
 typedef struct MiqpB200Options {

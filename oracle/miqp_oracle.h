@@ -101,6 +101,7 @@ typedef struct OrcSolveInfo {
   double objective, best_bound, gap, seconds, max_violation;
   long nodes, qp_solves, qp_iters;
   int proven;          /* 1 if gap <= gap_tol was reached */
+  long uncertified;    /* nodes closed without a converged relaxation or a Farkas certificate (their bound stays in best_bound) */
 } OrcSolveInfo;
 
 /* Solve the MIQP.  x_out[ncols] receives the incumbent (full column vector).

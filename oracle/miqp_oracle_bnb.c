@@ -157,11 +157,40 @@ static int condense(const Ctx *k, QP *q, const SRow *r, double *constviol) {
   return 1;
 }
 
+/* Farkas certificate of infeasibility of {G z <= h, |z_a| <= B_a}: multipliers lam >= 0 with
+ *   h'lam + sum_a |(G'lam)_a| B_a < 0.
+ * (Every feasible z has lam'(Gz - h) <= 0, i.e. (G'lam)'z <= h'lam, while (G'lam)'z >= -sum |(G'lam)_a| B_a.)
+ * B_a: the jerks are bounded by the global jerk box (model_region_constraints.mod:36-39, rows of every node),
+ * the pair slacks by maximum_slack (decision_variables.mod:53).  The multipliers of a diverging
+ * interior-point iteration converge to such a certificate when the node is infeasible. */
+static int farkas_certificate(const Ctx *k, const QP *q, const double *lam, double *r /* [n] scratch */) {
+  const int n = q->n, m = q->m;
+  double lmax = 0.0;
+  for (int i = 0; i < m; ++i) if (lam[i] > lmax) lmax = lam[i];
+  if (!(lmax > 0.0) || !(lmax < HUGE_VAL)) return 0;
+  const double sc = 1.0 / lmax;
+  memset(r, 0, sizeof(double) * (size_t)n);
+  double hl = 0.0, mag = 0.0;
+  for (int i = 0; i < m; ++i) {
+    const double l = lam[i] * sc;
+    if (!(l > 0.0)) continue;
+    const double *g = q->G + (size_t)i * n; const int *sg = q->seg + i * 11;
+    for (int a = 0; a < sg[0]; ++a) { int st = sg[1 + 2 * a], ln = sg[2 + 2 * a]; for (int j = 0; j < ln; ++j) r[st + j] += g[st + j] * l; }
+    hl += q->h[i] * l; mag += fabs(q->h[i]) * l;
+  }
+  const OrcProblem *p = k->p;
+  const double U = fmax(fabs(p->total_min_jerk), fabs(p->total_max_jerk));
+  double slackterm = 0.0;
+  for (int a = 0; a < n; ++a) slackterm += fabs(r[a]) * (a < k->nu ? U : p->maximum_slack);
+  return hl + slackterm < -1e-10 * (mag + slackterm) - 1e-13;
+}
+
 /* Dense Mehrotra predictor-corrector.  min 1/2 z'Qz + c'z  s.t. Gz <= h.
- * returns 0 optimal, 1 infeasible, 2 not converged (treated as infeasible by callers
- * only if the primal residual is large). */
-static int qp_solve(Ctx *k, const QP *q, double *z, double *obj_out, double cutoff) {
-  (void)cutoff;
+ * returns QP_OPTIMAL, QP_INFEASIBLE (Farkas certificate verified), QP_FEASIBLE_POINT (the iteration
+ * stalled at a primal feasible point: *obj_out is only an upper bound of the optimum) or QP_UNKNOWN
+ * (no convergence, no certificate). */
+enum { QP_OPTIMAL = 0, QP_INFEASIBLE = 1, QP_FEASIBLE_POINT = 2, QP_UNKNOWN = 3 };
+static int qp_solve(Ctx *k, const QP *q, double *z, double *obj_out, double *lb_out) {
   const int n = q->n, m = q->m;
   const double *Q = k->Q, *cv = k->cvec;
   double *s = (double *)malloc(sizeof(double) * (size_t)(m + 1) * 8);
@@ -170,7 +199,8 @@ static int qp_solve(Ctx *k, const QP *q, double *z, double *obj_out, double cuto
   double *rd = (double *)malloc(sizeof(double) * (size_t)n * 4);
   double *dz = rd + n, *rhs = dz + n, *dla = NULL;
   dla = (double *)malloc(sizeof(double) * (size_t)(m + 1));
-  int status = 2, it;
+  int status = 2, it, certified = 0; static long nchecks = 0;
+  const char *tr_ = getenv("ORC_TRACE"); const int trace2 = tr_ && tr_[0] == '2';
   double cn = 0.0; for (int a = 0; a < n; ++a) if (fabs(cv[a]) > cn) cn = fabs(cv[a]);
   memset(z, 0, sizeof(double) * (size_t)n);
   for (int r = 0; r < m; ++r) { double v = q->h[r]; s[r] = v > 1.0 ? v : 1.0; lam[r] = 1.0; }
@@ -209,7 +239,30 @@ static int qp_solve(Ctx *k, const QP *q, double *z, double *obj_out, double cuto
         }
       }
     }
-    if (chol(M, n)) { for (int a = 0; a < n; ++a) M[a * n + a] += 1e-9; if (chol(M, n)) { status = 2; break; } }
+    /* early exit for infeasible nodes: once the multipliers have grown, test them as a Farkas certificate */
+    if (it >= 3) { double lm = 0.0; for (int r = 0; r < m; ++r) if (lam[r] > lm) lm = lam[r];
+      static double thr = -1.0; if (thr < 0.0) { const char *e = getenv("ORC_FK_THR"); thr = e ? atof(e) : 1e3; }
+      if (trace2) fprintf(stderr, "   lm %.3e cn %.3e\n", lm, cn);
+      if (lm > thr * (1.0 + cn)) { nchecks++; if (farkas_certificate(k, q, lam, rhs)) { status = 1; certified = 1; break; } } }
+    if (chol(M, n)) {
+      /* numerically indefinite close to the solution (weights lam/s up to 1e10 on a condensed Hessian): shift the
+       * diagonal; the Newton step becomes inexact, the iteration still converges */
+      int failed = 1;
+      if (mu <= 1e-7 && rpn <= 1e-9) { status = 2; break; }   /* as good as converged: the Lagrangian bound below is tight here */
+      for (double shift = 1e-9; failed && shift <= 1e-3; shift *= 100.0) {
+        memcpy(M, Q, sizeof(double) * (size_t)n * n);
+        for (int r = 0; r < m; ++r) {
+          const double *g = q->G + (size_t)r * n; const int *sg = q->seg + r * 11; const double wr = w[r];
+          for (int a = 0; a < sg[0]; ++a) { int sa = sg[1 + 2 * a], la = sg[2 + 2 * a];
+            for (int ia = 0; ia < la; ++ia) { double gv = wr * g[sa + ia]; if (gv == 0.0) continue; double *Mr = M + (size_t)(sa + ia) * n;
+              for (int b = 0; b <= a; ++b) { int sb = sg[1 + 2 * b], lb = sg[2 + 2 * b]; int lim = (b == a) ? ia + 1 : lb; for (int ib = 0; ib < lim; ++ib) Mr[sb + ib] += gv * g[sb + ib]; } } }
+        }
+        double dmax = 0.0; for (int a = 0; a < n; ++a) if (M[a * n + a] > dmax) dmax = M[a * n + a];
+        for (int a = 0; a < n; ++a) M[a * n + a] += shift * dmax;
+        failed = chol(M, n);
+      }
+      if (failed) { status = 2; break; }
+    }
     /* predictor: rc = s*lam */
     for (int r = 0; r < m; ++r) t[r] = w[r] * rp[r] - lam[r]; /* (lam*rp - rc)/s */
     for (int a = 0; a < n; ++a) rhs[a] = -rd[a];
@@ -251,24 +304,53 @@ static int qp_solve(Ctx *k, const QP *q, double *z, double *obj_out, double cuto
     for (int r = 0; r < m; ++r) { s[r] += alpha * ds[r]; lam[r] += alpha * dl[r]; }
     if (alpha < 1e-6) { if (++stall >= 5) { status = 2; break; } } else stall = 0;
     double lmax = 0.0; for (int r = 0; r < m; ++r) if (lam[r] > lmax) lmax = lam[r];
+    if (trace2) fprintf(stderr, "   it %d alpha %.3e aff %.3e sigma %.3e mu %.3e rpn %.3e rdn %.3e lmax %.3e\n", it, alpha, aff, sigma, mu, rpn, rdn, lmax);
     if (lmax > 1e13) { status = 1; break; }
   }
   k->qp_iters += it;
   k->qp_solves++;
-  if (status != 0) {
-    /* decide between "not converged but fine" and infeasible from the primal residual */
+  if (status != 0 && !certified) {
+    /* not converged: a primal feasible point is still usable (as an upper bound); otherwise the node is
+     * infeasible only with a certificate */
     double worst = 0.0;
     for (int r = 0; r < m; ++r) {
       const double *g = q->G + (size_t)r * n; const int *sg = q->seg + r * 11; double gz = 0.0;
       for (int a = 0; a < sg[0]; ++a) { int st = sg[1 + 2 * a], ln = sg[2 + 2 * a]; for (int j = 0; j < ln; ++j) gz += g[st + j] * z[st + j]; }
       if (gz - q->h[r] > worst) worst = gz - q->h[r];
     }
-    status = (worst > 1e-7) ? 1 : 0;
+    if (worst <= 1e-7) status = QP_FEASIBLE_POINT;
+    else status = farkas_certificate(k, q, lam, rhs) ? QP_INFEASIBLE : QP_UNKNOWN;
   }
-  if (status == 0) {
+  double lagr = -HUGE_VAL;
+  if (status == QP_FEASIBLE_POINT) {
+    /* Lagrangian lower bound from the multipliers of the stalled iteration.  For every feasible z':
+     *   f(z') >= L(z', lam) >= L(z, lam) + grad_z L(z, lam)'(z' - z)      (L convex in z, lam >= 0)
+     * with L(z, lam) = f(z) - lam'(h - Gz) and |z'_a - z_a| bounded through the box of the variables
+     * (global jerk box, pair slacks in [0, maximum_slack]). */
+    const OrcProblem *p = k->p;
+    for (int a = 0; a < n; ++a) { double v = cv[a]; const double *Qr = Q + (size_t)a * n; for (int b = 0; b < n; ++b) v += Qr[b] * z[b]; rd[a] = v; }
+    double f = 0.0; for (int a = 0; a < n; ++a) f += z[a] * 0.5 * (rd[a] + cv[a]);
+    double comp = 0.0;
+    for (int r = 0; r < m; ++r) {
+      const double *g = q->G + (size_t)r * n; const int *sg = q->seg + r * 11; double gz = 0.0; const double l = lam[r] > 0.0 ? lam[r] : 0.0;
+      for (int a = 0; a < sg[0]; ++a) { int st = sg[1 + 2 * a], ln = sg[2 + 2 * a]; for (int j = 0; j < ln; ++j) { gz += g[st + j] * z[st + j]; rd[st + j] += g[st + j] * l; } }
+      comp += l * (q->h[r] - gz);
+    }
+    double corr = 0.0;
+    for (int a = 0; a < n; ++a) {
+      const double lo = (a < k->nu) ? p->total_min_jerk : 0.0, hi = (a < k->nu) ? p->total_max_jerk : p->maximum_slack;
+      const double range = fmax(hi - z[a], z[a] - lo);
+      corr += fabs(rd[a]) * (range > 0.0 ? range : 0.0);
+    }
+    lagr = f - comp - corr + k->cconst;
+    lagr -= 1e-12 * (fabs(f) + fabs(comp) + corr);
+  }
+  if (getenv("ORC_TRACE")) fprintf(stderr, "[qp] m %d iters %d status %d certified_early %d checks %ld\n", m, it, status, certified, nchecks);
+  if (status == QP_OPTIMAL || status == QP_FEASIBLE_POINT) {
     double o = 0.0;
     for (int a = 0; a < n; ++a) { double v = 0.0; const double *Qr = Q + (size_t)a * n; for (int b = 0; b < n; ++b) v += Qr[b] * z[b]; o += z[a] * (0.5 * v + cv[a]); }
     *obj_out = o + k->cconst;
+    if (lb_out) *lb_out = (status == QP_OPTIMAL) ? *obj_out : lagr;
   }
   free(s); free(M); free(rd); free(dla);
   return status;
@@ -938,7 +1020,8 @@ int orc_solve_fixed(const OrcProblem *p, const double *x_bin, double *x_out, dou
   double pen = 0.0, obj = 0.0;
   int rc = build_node_qp(&k, dec, &q, &pen);
   double *z = (double *)calloc((size_t)k.n, sizeof(double));
-  if (!rc) rc = qp_solve(&k, &q, z, &obj, HUGE_VAL);
+  if (!rc) rc = qp_solve(&k, &q, z, &obj, NULL);
+  if (rc == QP_FEASIBLE_POINT) rc = 0;
   if (!rc) {
     double *traj = (double *)malloc(sizeof(double) * (size_t)k.C * k.N * 8);
     simulate(&k, z, traj);
@@ -961,7 +1044,7 @@ int orc_solve(const OrcProblem *p, const double *warm, double *x_out, OrcSolveIn
   unsigned char *imp = (unsigned char *)malloc((size_t)k.ndec);
   double ub = HUGE_VAL; int have_inc = 0;
   double pruned_lb = HUGE_VAL; /* smallest bound among nodes discarded by the gap rule */
-  long nodes = 0;
+  long nodes = 0, uncertified = 0; /* uncertified: nodes closed without optimum or infeasibility certificate */
   memset(info, 0, sizeof *info);
 
   Node root; root.bound = -HUGE_VAL; root.depth = 0; root.rank = 0;
@@ -976,15 +1059,28 @@ int orc_solve(const OrcProblem *p, const double *warm, double *x_out, OrcSolveIn
   int timed_out = 0;
   while (heap.n > 0) {
     if (now_s() - t0 > tlim) { timed_out = 1; break; }
-    Node nd = heap_pop(&heap);
+    Node nd;
+    if (!have_inc && nodes >= 48 && (nodes & 1) && heap.n > 1) {
+      /* A dive that has not produced an incumbent after 48 nodes may sit below a wrong early decision (deepest-first
+       * backtracking never leaves that subtree): every second node is then taken from the best bound instead. */
+      int bi = 0;
+      for (int a = 1; a < heap.n; ++a) if (heap.a[a].bound < heap.a[bi].bound || (heap.a[a].bound == heap.a[bi].bound && heap.a[a].depth > heap.a[bi].depth)) bi = a;
+      nd = heap.a[bi]; heap.a[bi] = heap.a[--heap.n]; heap_rebuild(&heap);
+    } else nd = heap_pop(&heap);
     double cutoff = have_inc ? ub - gap_tol * fabs(ub) : HUGE_VAL;
     if (nd.bound >= cutoff) { if (nd.bound < pruned_lb) pruned_lb = nd.bound; free(nd.dec); continue; }
     nodes++;
-    double pen = 0.0, obj = 0.0;
-    int rc = build_node_qp(&k, nd.dec, &q, &pen);
-    if (!rc) rc = qp_solve(&k, &q, z, &obj, cutoff - pen);
-    if (rc) { free(nd.dec); continue; }
-    obj += pen;
+    double pen = 0.0, obj = 0.0, qlb = -HUGE_VAL;
+    int qs = QP_INFEASIBLE; /* boxes with lo > hi: infeasible by construction */
+    if (!build_node_qp(&k, nd.dec, &q, &pen)) qs = qp_solve(&k, &q, z, &obj, &qlb);
+    if (qs == QP_INFEASIBLE) { free(nd.dec); continue; }
+    if (qs == QP_UNKNOWN) { /* neither solved nor refuted: the node is closed, its bound stays in the books */
+      uncertified++; if (nd.bound < pruned_lb) pruned_lb = nd.bound; free(nd.dec); continue;
+    }
+    /* fval: objective of the point z (an upper bound of the relaxation); obj: lower bound of the node.  They
+     * coincide when the iteration converged; a stalled iteration yields the Lagrangian bound of its multipliers. */
+    const double fval = obj + pen;
+    obj = (qs == QP_OPTIMAL) ? fval : fmax(nd.bound, qlb + pen);
     if (obj < nd.bound) obj = nd.bound; /* numerical monotonicity */
     if (obj >= cutoff) { if (obj < pruned_lb) pruned_lb = obj; free(nd.dec); continue; }
     simulate(&k, z, traj);
@@ -992,8 +1088,14 @@ int orc_solve(const OrcProblem *p, const double *warm, double *x_out, OrcSolveIn
     if (verbose > 1) fprintf(stderr, "node %ld depth %d obj %.6f kind %d c%d i%d pt%d viol %.3g open %d ub %.6f\n", nodes, nd.depth, obj, br.kind, br.c, br.i, br.pt, br.viol, heap.n, ub);
     if (br.kind == 0) {
       int und = count_undecided(&k, nd.dec);
+      /* a stalled point that satisfies an alternative of every disjunction is still replaced by its completion alone;
+       * the dropped completions keep their bound in the books */
+      if (und > 0 && qs != QP_OPTIMAL && obj < pruned_lb) pruned_lb = obj;
       if (und == 0) {
-        ub = obj; have_inc = 1;
+        const double inc = fval > obj ? fval : obj;
+        if (qs != QP_OPTIMAL && obj < pruned_lb) pruned_lb = obj; /* the leaf's optimum may lie below the stalled point, but not below obj */
+        if (!(inc < ub)) { free(nd.dec); continue; }
+        ub = inc; have_inc = 1;
         fill_solution(&k, nd.dec, traj, z, x_out);
         if (verbose) fprintf(stderr, "[oracle] incumbent %.8f after %ld nodes, %.3fs\n", ub, nodes, now_s() - t0);
         if (!heap.have_inc) { heap.have_inc = 1; heap_rebuild(&heap); }
@@ -1002,7 +1104,7 @@ int orc_solve(const OrcProblem *p, const double *warm, double *x_out, OrcSolveIn
         Node ch; ch.bound = obj; ch.depth = nd.depth + 1; ch.rank = 0; ch.dec = nd.dec; memcpy(ch.dec, imp, (size_t)k.ndec);
         heap_push(&heap, ch);
       }
-      continue;
+      if (br.kind == 0) continue;
     }
     /* branch */
     int nalt = 0; unsigned char alts[260]; size_t soff = 0;
@@ -1035,7 +1137,7 @@ int orc_solve(const OrcProblem *p, const double *warm, double *x_out, OrcSolveIn
   for (int a = 0; a < heap.n; ++a) { if (heap.a[a].bound < lb) lb = heap.a[a].bound; free(heap.a[a].dec); }
   if (!timed_out && heap.n == 0 && lb == HUGE_VAL) lb = ub; /* tree exhausted */
   if (have_inc && lb > ub) lb = ub;
-  info->nodes = nodes; info->qp_solves = k.qp_solves; info->qp_iters = k.qp_iters;
+  info->nodes = nodes; info->qp_solves = k.qp_solves; info->qp_iters = k.qp_iters; info->uncertified = uncertified;
   info->seconds = now_s() - t0;
   if (have_inc) {
     info->status = 0; info->objective = ub; info->best_bound = lb;

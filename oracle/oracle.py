@@ -58,7 +58,7 @@ class OrcSolveInfo(C.Structure):
     _fields_ = [("status", C.c_int), ("objective", C.c_double), ("best_bound", C.c_double),
                 ("gap", C.c_double), ("seconds", C.c_double), ("max_violation", C.c_double),
                 ("nodes", C.c_long), ("qp_solves", C.c_long), ("qp_iters", C.c_long),
-                ("proven", C.c_int)]
+                ("proven", C.c_int), ("uncertified", C.c_long)]
 
 
 def build(force: bool = False) -> str:

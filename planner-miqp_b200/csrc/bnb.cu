@@ -73,7 +73,7 @@ __global__ void bnb_init_kernel(BnbState st, const DevProb *probs, const unsigne
     st.sel_cnt[s] = 0;
     st.ub[s] = MQ_INF; st.cutoff[s] = MQ_INF; st.pruned_lb[s] = MQ_INF;
     st.done[s] = 0; st.lock[s] = 0;
-    st.stat_nodes[s] = 0; st.stat_iters[s] = 0; st.stat_rows[s] = 0;
+    st.stat_nodes[s] = 0; st.stat_iters[s] = 0; st.stat_rows[s] = 0; st.stat_uncert[s] = 0; st.overflow[s] = 0;
     st.inc_uid[s] = ~0ULL;
     if (s == 0) { *st.active_prev = 0; *st.work_cnt = 0; *st.work_next = 0; *st.active = 0; *st.err = 0; *st.work_cnt2 = 0; *st.work_next2 = 0; }
   }
@@ -254,6 +254,10 @@ void launch_bnb_select(const BnbState &st, const DevProb *probs, int round, cuda
 // scan of a relaxed optimum: implied alternatives and the most violated disjunction
 // ---------------------------------------------------------------------------------------
 struct Branch { int kind, i, o, pt; double viol; int ord; };  // kind: 0 none, 1 mode, 2 env, 3 obs
+struct Fallback { int ord, kind, i, o, pt; };   // first undecided disjunction in scan order (branching of a stalled relaxation)
+__device__ __forceinline__ void fb_offer(Fallback &f, int ord, int kind, int i, int o, int pt) {
+  if (ord < f.ord) { f.ord = ord; f.kind = kind; f.i = i; f.o = o; f.pt = pt; }
+}
 
 __device__ __forceinline__ void branch_offer(Branch &b, double viol, int ord, int kind, int i, int o, int pt) {
   if (viol > b.viol || (viol == b.viol && ord < b.ord)) { b.viol = viol; b.ord = ord; b.kind = kind; b.i = i; b.o = o; b.pt = pt; }
@@ -296,7 +300,7 @@ __device__ __forceinline__ double edge_violation(const double *et, const double 
 }
 
 // returns number of undecided disjunctions; fills w.imp and br
-__device__ __forceinline__ int scan_node(const WarpCtx &w, Branch &br) {
+__device__ __forceinline__ int scan_node(const WarpCtx &w, Branch &br, Fallback &fb) {
   const DevProb &p = *w.p;
   const int lane = w.lane, N = w.N, O = p.O, E = p.E, L = p.L;
   const double tol = 1e-6;
@@ -323,6 +327,7 @@ __device__ __forceinline__ int scan_node(const WarpCtx &w, Branch &br) {
   __syncwarp();
   // phase 2: region chain (all lanes redundantly; the frozen alternative inherits the region)
   br.kind = 0; br.viol = tol; br.ord = 0x7fffffff; br.i = 0; br.o = 0; br.pt = 0;
+  fb.ord = 0x7fffffff; fb.kind = 0; fb.i = 0; fb.o = 0; fb.pt = 0;
   int und = 0;
   {
     int jp = w.I[p.o_initreg] - 1;
@@ -337,6 +342,7 @@ __device__ __forceinline__ int scan_node(const WarpCtx &w, Branch &br) {
         const double vfz = mode_alt_violation(w, i, MODE_FROZEN, jp, y);
         if (m == UNDEC) {
           ++und;
+          fb_offer(fb, i * ord_stride, 1, i, 0, 0);
           int best = MODE_FROZEN; double bv = vfz;
           if (bestalt[i] >= 0 && bestv[i] < vfz - 1e-12) { best = bestalt[i]; bv = bestv[i]; }
           if (lane == 0) w.imp[p.off_mode + i] = (unsigned char)best;
@@ -370,7 +376,7 @@ __device__ __forceinline__ int scan_node(const WarpCtx &w, Branch &br) {
     if (E > 0)
       for (int pt = 0; pt < 5; ++pt) {
         const unsigned char d = (E == 1) ? (unsigned char)0 : w.dec[p.off_env + i * 5 + pt];
-        if (d == UNDEC) ++und3;
+        if (d == UNDEC) { ++und3; fb_offer(fb, i * ord_stride + 1 + pt, 2, i, 0, pt); }
         if (d != UNDEC && (pt == 0 || region_decided)) continue;
         int best = -1; double bv = MQ_INF;
         for (int e = 0; e < E; ++e) {
@@ -388,7 +394,7 @@ __device__ __forceinline__ int scan_node(const WarpCtx &w, Branch &br) {
       for (int pt = 0; pt < 5; ++pt) {
         const unsigned char d = w.dec[p.off_obs + (o * N + i) * 5 + pt];
         if (d == OBS_SOFT) continue;
-        if (d == UNDEC) ++und3;
+        if (d == UNDEC) { ++und3; fb_offer(fb, i * ord_stride + 6 + o * 5 + pt, 3, i, o, pt); }
         if (d != UNDEC && (pt == 0 || region_decided)) continue;
         const int ne = w.I[p.o_obs_nedges + o * N + i];
         int best = -1; double bv = MQ_INF;
@@ -412,6 +418,11 @@ __device__ __forceinline__ int scan_node(const WarpCtx &w, Branch &br) {
     branch_offer(mine, o.viol, o.ord, o.kind, o.i, o.o, o.pt);
   }
   br = mine;
+  for (int off = 16; off > 0; off >>= 1) {
+    const int oo = __shfl_xor_sync(FULL, fb.ord, off), ok = __shfl_xor_sync(FULL, fb.kind, off), oi = __shfl_xor_sync(FULL, fb.i, off);
+    const int ob = __shfl_xor_sync(FULL, fb.o, off), op = __shfl_xor_sync(FULL, fb.pt, off);
+    fb_offer(fb, oo, ok, oi, ob, op);
+  }
   und += warp_sum_i(und3);
   __syncwarp();
   return und;
@@ -621,7 +632,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? NODE_TEAMS_PER_SM : 1) bnb_
       atomicAdd(&st.prof[128], (unsigned long long)r.c_rows); atomicAdd(&st.prof[129], (unsigned long long)r.c_factor);
       atomicAdd(&st.prof[130], (unsigned long long)r.c_sweeps); atomicAdd(&st.prof[131], (unsigned long long)(clock64() - pt0));
       if (r.status != 0) { atomicAdd(&st.prof[132], 1ULL); atomicAdd(&st.prof[133], (unsigned long long)r.iters); atomicAdd(&st.prof[150 + (r.iters > 100 ? 100 : r.iters)], 1ULL); }
-      if (w.dbgrow && r.iters >= 30 && r.status == 0) {   // keep the traces of the first eight slow feasible relaxations
+      if (w.dbgrow && ((r.iters >= 30 && r.status == 0) || (r.status == 0 && !r.converged) || r.status == 4)) {   // keep the traces of the first eight slow / stalled relaxations
         const unsigned long long k = atomicAdd(&st.prof[140], 1ULL);
         if (k < 8) { double *dst = st.dbg + (size_t)(1024 + k) * 512; dst[0] = r.iters; dst[1] = r.obj; dst[2] = nmeta.x; for (int q = 8; q < 8 + 5 * 100; ++q) dst[q] = w.dbgrow[q]; }
       }
@@ -634,21 +645,35 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? NODE_TEAMS_PER_SM : 1) bnb_
       atomicAdd(&st.stat_iters[s], (unsigned long long)r.iters);
       atomicAdd(&st.stat_rows[s], (unsigned long long)r.rows);
     }
-    if (r.status != 0) continue;  // infeasible: the node dies
+    if (r.status == 1) continue;  // proven infeasible (empty box or Farkas certificate): the node dies
+    if (r.status != 0) {
+      // neither solved nor refuted: the node is closed, but its bound stays in the books (the plan cannot be reported as
+      // proven below it) and the event is counted
+      if (lane == 0) { atomic_min_double(&st.pruned_lb[s], nbound); atomicAdd(&st.stat_uncert[s], 1ULL); }
+      continue;
+    }
     // fval: objective of the point in V_Z (an upper bound of the relaxation); obj: lower bound of the node.  They coincide
-    // when the interior-point iteration converged; a stalled iteration only inherits the bound of its parent.
+    // when the interior-point iteration converged; a stalled iteration yields the Lagrangian bound of its multipliers.
     const double fval = r.obj + pen;
-    double obj = r.converged ? fval : nbound;
+    double obj = r.converged ? fval : fmax(nbound, r.lb + pen);
     if (obj < nbound) obj = nbound;  // numerical monotonicity
     if (obj >= cutoff) { if (lane == 0) atomic_min_double(&st.pruned_lb[s], obj); continue; }
 #ifdef MQ_PROF
     if (lane == 0 && !r.converged) atomicAdd(&st.prof[149], 1ULL);
 #endif
 
-    Branch br;
-    const int und = scan_node(w, br);
+    Branch br; Fallback fb;
+    const int und = scan_node(w, br, fb);
+    if (br.kind == 0 && und > 0 && !r.converged) {
+      // The stalled point satisfies an alternative of every disjunction without being the optimum of the relaxation.  The
+      // node is still replaced by the completion `imp` alone (branching on the hundreds of disjunctions that a trajectory
+      // satisfies anyway would never end); the other completions are dropped, so their bound obj stays in the books: the plan
+      // is reported as proven only if the incumbent comes within the gap of it.
+      if (lane == 0) atomic_min_double(&st.pruned_lb[s], obj);
+    }
     if (br.kind == 0 && und == 0) {
       // every disjunction decided and satisfied: incumbent candidate
+      if (lane == 0 && !r.converged) atomic_min_double(&st.pruned_lb[s], obj);   // the leaf's optimum may lie below the stalled point, not below obj
       if (lane == 0) { while (atomicCAS(&st.lock[s], 0, 1) != 0) {} }
       __syncwarp();
       __threadfence();
@@ -711,7 +736,9 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? NODE_TEAMS_PER_SM : 1) bnb_
     int fbase = 0, opos = 0, ok = 1;
     if (lane == 0) {
       const int old = atomicSub(&st.free_cnt[s], nalt);
-      if (old < nalt) { atomicAdd(&st.free_cnt[s], nalt); atomicExch(st.err, 1); ok = 0; }
+      if (old < nalt) {   // node pool of this plan exhausted: the children are dropped, their bound stays in the books
+        atomicAdd(&st.free_cnt[s], nalt); atomicExch(&st.overflow[s], 1); atomic_min_double(&st.pruned_lb[s], obj); ok = 0;
+      }
       else { fbase = old - nalt; opos = atomicAdd(&st.open_cnt[s], nalt); }
     }
     ok = __shfl_sync(FULL, ok, 0); fbase = __shfl_sync(FULL, fbase, 0); opos = __shfl_sync(FULL, opos, 0);

@@ -59,14 +59,19 @@ __global__ void __launch_bounds__(MULTI_MAX_THREADS) bnb_nodes_multi_kernel(BnbS
       atomicAdd(&st.stat_rows[s], (unsigned long long)out.rows);
     }
     if (out.what == MN_INFEASIBLE) continue;
+    if (out.what == MN_UNKNOWN) {   // closed without optimum or certificate: its bound stays in the books
+      if (tid == 0) { atomic_min_double(&st.pruned_lb[s], nbound); atomicAdd(&st.stat_uncert[s], 1ULL); }
+      continue;
+    }
     if (out.what == MN_PRUNED) { if (tid == 0) atomic_min_double(&st.pruned_lb[s], out.obj); continue; }
     if (out.what == MN_INCUMBENT) {
       if (tid == 0) {
+        if (!out.converged) atomic_min_double(&st.pruned_lb[s], out.obj);   // the leaf's optimum may lie below the stalled point, not below obj
         while (atomicCAS(&st.lock[s], 0, 1) != 0) {}
         __threadfence();
         const double cur = *reinterpret_cast<volatile double *>(&st.ub[s]);
         const unsigned long long cuid = *reinterpret_cast<volatile unsigned long long *>(&st.inc_uid[s]);
-        s_i[1] = (out.obj < cur || (out.obj == cur && nuid < cuid)) ? 1 : 0;
+        s_i[1] = (out.fval < cur || (out.fval == cur && nuid < cuid)) ? 1 : 0;
       }
       __syncthreads();
       if (s_i[1]) {
@@ -84,7 +89,7 @@ __global__ void __launch_bounds__(MULTI_MAX_THREADS) bnb_nodes_multi_kernel(BnbS
       }
       __syncthreads();
       if (tid == 0) {
-        if (s_i[1]) { st.ub[s] = out.obj; st.inc_uid[s] = nuid; }
+        if (s_i[1]) { st.ub[s] = out.fval; st.inc_uid[s] = nuid; }
         __threadfence();
         atomicExch(&st.lock[s], 0);
       }
@@ -97,7 +102,9 @@ __global__ void __launch_bounds__(MULTI_MAX_THREADS) bnb_nodes_multi_kernel(BnbS
     if (nalt == 0) continue;
     if (tid == 0) {
       const int old = atomicSub(&st.free_cnt[s], nalt);
-      if (old < nalt) { atomicAdd(&st.free_cnt[s], nalt); atomicExch(st.err, 1); s_i[1] = 0; }
+      if (old < nalt) {   // node pool of this plan exhausted: the children are dropped, their bound stays in the books
+        atomicAdd(&st.free_cnt[s], nalt); atomicExch(&st.overflow[s], 1); atomic_min_double(&st.pruned_lb[s], out.obj); s_i[1] = 0;
+      }
       else { s_i[1] = 1; s_i[2] = old - nalt; s_i[3] = atomicAdd(&st.open_cnt[s], nalt); }
     }
     __syncthreads();

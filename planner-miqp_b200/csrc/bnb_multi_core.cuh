@@ -294,8 +294,10 @@ MQ_FN double m_alt_delta(const MCtx &k, const MBranch &br, int alt) {
 }
 
 // outcome of one node
-enum { MN_INFEASIBLE = 0, MN_PRUNED, MN_INCUMBENT, MN_BRANCH };
-struct MNodeOut { int what, iters, nalt, soff; long rows; double obj, pruned_min; bool from_imp; };
+enum { MN_INFEASIBLE = 0, MN_PRUNED, MN_INCUMBENT, MN_BRANCH, MN_UNKNOWN };
+// obj: valid lower bound of the node; fval: objective of the point in Z (an upper bound of the relaxation, = obj if converged);
+// est: ordering hint of the children (the dive follows it; bounds and pruning never use it)
+struct MNodeOut { int what, iters, nalt, soff, converged; long rows; double obj, fval, pruned_min; bool from_imp; };
 
 // Shared scratch of the node processing that is not part of the QP workspace
 struct MShared { MBranch br; int nkeep; double pruned_min; unsigned char alts[260]; double cb[260]; };
@@ -312,17 +314,25 @@ MQ_FN MNodeOut m_process_node(const MCtx &k, MShared *sh, double nbound, double 
   nsoft = k.rsumi(nsoft);
   const double pen = nsoft * p.w_slack_obs;
   const MQpResult r = m_solve_node_qp(k);
-  out.iters = r.iters; out.rows = r.rows;
-  if (r.status != 0) return out;
-  double obj = r.obj + pen;
+  out.iters = r.iters; out.rows = r.rows; out.converged = r.converged;
+  if (r.status == 1) return out;                               // proven infeasible
+  if (r.status != 0) { out.what = MN_UNKNOWN; out.obj = nbound; return out; }   // neither solved nor refuted
+  // a stalled relaxation is only a feasible point: its objective is an upper bound of the relaxation; the node's lower
+  // bound is the Lagrangian bound of the multipliers (or the parent's bound)
+  const double fval = r.obj + pen;
+  double obj = r.converged ? fval : fmax(nbound, r.lb + pen);
   if (obj < nbound) obj = nbound;  // numerical monotonicity
-  out.obj = obj;
+  out.obj = obj; out.fval = fval > obj ? fval : obj;
   if (obj >= cutoff) { out.what = MN_PRUNED; return out; }
   MBranch br;
   const int und = m_scan_node(k, br, &sh->br, ndec_pad);
+  // (a stalled point that satisfies an alternative of every disjunction is still replaced by its completion alone; the
+  // dropped completions are accounted for by the caller: pruned_min = obj)
+  if (br.kind == 0 && und > 0 && !r.converged) out.pruned_min = obj;
   if (br.kind == 0 && und == 0) { out.what = MN_INCUMBENT; return out; }
   out.what = MN_BRANCH;
   if (br.kind == 0) { out.nalt = 1; out.from_imp = true; out.soff = -1; if (k.tid == 0) sh->cb[0] = obj; k.sync(); return out; }
+  out.pruned_min = MQM_INF;
   if (br.kind == 1) {
     out.soff = p.off_mode + br.c * k.N + br.i;
     const int na = k.I[p.o_nalt + br.c];
@@ -345,7 +355,7 @@ MQ_FN MNodeOut m_process_node(const MCtx &k, MShared *sh, double nbound, double 
   }
   k.sync();
   // child bounds; children that reach the cutoff are dropped here
-  PFOR(a, out.nalt) sh->cb[a] = fmax(obj, r.obj + pen + 0.999 * m_alt_delta(k, br, sh->alts[a]));
+  PFOR(a, out.nalt) sh->cb[a] = r.converged ? fmax(obj, fval + 0.999 * m_alt_delta(k, br, sh->alts[a])) : obj;
   k.sync();
   if (k.tid == 0) {
     int n = 0; double pm = MQM_INF;

@@ -56,6 +56,8 @@ struct BnbState {
   unsigned char *inc_dec;  // [count][ndec_stride]
   unsigned long long *inc_uid;  // tie break between equal incumbents (deterministic result)
   unsigned long long *stat_nodes, *stat_iters, *stat_rows;
+  unsigned long long *stat_uncert;   // node relaxations closed without optimum, feasible point or infeasibility certificate
+  int *overflow;                     // per plan: 1 if its node pool ran out (children dropped, bound kept in pruned_lb)
   double *dbg;                // [-DMQ_PROF] per-CTA iteration traces [ctas + 8][512]; slots ctas.. hold the claimed slow relaxations
   unsigned long long *prof;   // [256] diagnostics (filled only by -DMQ_PROF builds): [it] histogram of IPM iterations per node, [128..] cycles
   // round control

@@ -416,10 +416,40 @@ struct PassG {  // step length of the combined step
   __device__ __forceinline__ void general(int slot, const double a[6], double rhs) { row(slot, dot6(a, y), dot6(a, d), dot6(a, da), rhs); }
 };
 
-struct PassViol {  // worst primal violation of the current point
-  double y[8]; double worst;
-  template <int T> __device__ __forceinline__ void bound(int, double sgn, double rhs) { worst = fmax(worst, sgn * y[T] - rhs); }
-  __device__ __forceinline__ void general(int, const double a[6], double rhs) { worst = fmax(worst, dot6(a, y) - rhs); }
+struct PassViol {  // worst primal violation of the current point, largest multiplier
+  RowIO io; double y[8]; double worst, lmax;
+  template <int T> __device__ __forceinline__ void bound(int slot, double sgn, double rhs) { worst = fmax(worst, sgn * y[T] - rhs); lmax = fmax(lmax, io.ld(slot).y); }
+  __device__ __forceinline__ void general(int slot, const double a[6], double rhs) { worst = fmax(worst, dot6(a, y) - rhs); lmax = fmax(lmax, io.ld(slot).y); }
+};
+
+struct PassDual {  // G' lambda, h' lambda and lambda' G z of a stage (multipliers after the pending step, scaled)
+  RowIO io; StepCtx sc; double scale;
+  double y[8], d[8], da[8];
+  double gl[8]; double hl, lgz, mag;
+  __device__ __forceinline__ double lam_of(int slot, double gz, double gdz, double gda, double rhs) {
+    const double2 v = io.ld(slot);
+    double lam = v.y;
+    if (sc.pending) {   // same update as PassA::core
+      const double s = v.x;
+      const double rp_old = (gz - sc.alpha * gdz) + s - rhs;
+      const double inv = fast_rcp(s);
+      const double dsa = -rp_old - gda;
+      const double dla = -lam - (lam * inv) * dsa;
+      const double ds = -rp_old - gdz;
+      const double rc = s * lam + dsa * dla - sc.sigmu;
+      const double dl = -(rc + lam * ds) * inv;
+      lam += sc.alpha * dl;
+    }
+    lam = (lam > 0.0 ? lam : 0.0) * scale;
+    hl += lam * rhs; lgz += lam * gz; mag += lam * fabs(rhs);
+    return lam;
+  }
+  template <int T> __device__ __forceinline__ void bound(int slot, double sgn, double rhs) { gl[T] += sgn * lam_of(slot, sgn * y[T], sgn * d[T], sgn * da[T], rhs); }
+  __device__ __forceinline__ void general(int slot, const double a[6], double rhs) {
+    const double lam = lam_of(slot, dot6(a, y), dot6(a, d), dot6(a, da), rhs);
+#pragma unroll
+    for (int t = 0; t < 6; ++t) gl[t] += a[t] * lam;
+  }
 };
 
 // ---------------------------------------------------------------------------------------
@@ -627,11 +657,13 @@ __device__ __forceinline__ void riccati_forward(const WarpCtx &w, int dst) {
 }
 
 struct QpResult {
-  int status;     // 0 optimal (or, with converged == 0, merely a feasible point), 1 infeasible, 3 parked (iteration budget used up)
+  int status;     // 0 optimal (or, with converged == 0, merely a feasible point), 1 infeasible (Farkas certificate verified or an empty
+                  // box), 3 parked (iteration budget used up), 4 unknown (no convergence, no feasible point, no certificate)
   int susp_index; // status 3: slot of the saved state
   int converged;  // 1: obj is the optimum of the relaxation (a valid bound); 0: the iteration stalled, obj is only an upper bound
   int iters;
   double obj;     // without soft-decision penalties
+  double lb;      // valid lower bound of the relaxation: obj if converged, else the Lagrangian bound of the last multipliers
   long rows;      // active rows x iterations (work counter)
 #ifdef MQ_PROF
   long long c_rows, c_factor, c_sweeps;   // clock64 cycles: row passes / Riccati factorisation / vector + forward sweeps
@@ -652,13 +684,88 @@ struct SuspendIO {
   int *counter; int nslots; long stride; int budget;
 };
 
+// Dual information of the current iterate (z, lambda); called by every thread of the team, V_DZ is used as scratch.
+//
+// With g_i = kappa (Q_i z_i + c_i) + G_i' lambda and the costate recursion pi_i = g_x,i + A' pi_{i+1}, every trajectory
+// z' of the dynamics satisfies  sum_i g_i' z'_i = pi_0' x_0 + sum_i rho_i' u'_i,  rho_i = g_u,i + B' pi_{i+1},
+// and the jerks are confined to the global box [total_min_jerk, total_max_jerk] (model_region_constraints.mod:36-39).
+//
+// farkas (kappa = 0, lambda scaled by 1 / lmax): a feasible z' has lambda'(G z' - h) <= 0, i.e. sum_i g_i' z'_i <= h' lambda;
+//   if pi_0' x_0 - sum |rho_i| U > h' lambda no such z' exists: returns true, the node is PROVEN infeasible.
+// else (kappa = 1): Lagrangian bound  f(z') >= f(z) - lambda'(h - G z) - sum_i |rho_i| range_i  for every feasible z'
+//   (L(., lambda) is convex, its gradient along the dynamics is rho, |u'_i - u_i| <= range_i), stored in *lb.
+__device__ __forceinline__ bool dual_check(const WarpCtx &w, const StepCtx &sc, bool farkas, double lmax, double *lb) {   // one call site (solve_node_qp)
+  const DevProb &p = *w.p;
+  const double *D = w.D;
+  const int N = w.N;
+  const bool lead = (w.g == 0);
+  double hl = 0.0, lgz = 0.0, fz = 0.0, mag = 0.0;
+  MQ_FOR_STAGES(i, act) {
+    PassDual v; v.io.init(w.rows, w.NP, act ? i : 0); v.sc = sc; v.scale = farkas ? 1.0 / lmax : 1.0;
+    v.hl = 0.0; v.lgz = 0.0; v.mag = 0.0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) v.gl[t] = 0.0;
+    if (act) {
+      const double *Vi = w.V + i * V_STRIDE;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) { v.y[t] = Vi[V_Z + t]; v.d[t] = Vi[V_DZ + t]; v.da[t] = Vi[V_DZA + t]; }
+      visit_rows(w, i, v);
+    }
+    sg_reduce(w, v.gl);
+    double t3[3] = {v.hl, v.lgz, v.mag};
+    sg_reduce(w, t3);
+    if (act && lead) {
+      double *Vi = w.V + i * V_STRIDE;
+      const double *cst = D + p.o_cost + 16 * i;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        Vi[V_DZ + t] = v.gl[t] + (farkas ? 0.0 : cst[t] * v.y[t] + cst[8 + t]);
+        if (!farkas) fz += (0.5 * cst[t] * v.y[t] + cst[8 + t]) * v.y[t];
+      }
+      hl += t3[0]; lgz += t3[1]; mag += t3[2];
+    }
+  }
+  { double m0 = 0.0, m1 = 0.0; team_reduce(w, m0, m1, hl, lgz); }
+  { double m0 = 0.0, m1 = 0.0; team_reduce(w, m0, m1, fz, mag); }   // (ends with a barrier: V_DZ is complete)
+  if (w.wid == 0) {   // costate recursion, all lanes redundantly
+    const double ts = p.ts, c2 = p.c2, c3 = p.c3;
+    const double Ulo = p.total_min_jerk, Uhi = p.total_max_jerk, Uabs = fmax(fabs(Ulo), fabs(Uhi));
+    double pn[6], usum = 0.0;
+#pragma unroll
+    for (int t = 0; t < 6; ++t) pn[t] = w.V[(N - 1) * V_STRIDE + V_DZ + t];
+    for (int i = N - 2; i >= 0; --i) {
+      const double *g = w.V + i * V_STRIDE + V_DZ, *z = w.V + i * V_STRIDE + V_Z;
+#pragma unroll
+      for (int ax = 0; ax < 2; ++ax) {
+        const double pp = pn[3 * ax], pv = pn[3 * ax + 1], pa = pn[3 * ax + 2];
+        pn[3 * ax] = g[3 * ax] + pp;
+        pn[3 * ax + 1] = g[3 * ax + 1] + ts * pp + pv;
+        pn[3 * ax + 2] = g[3 * ax + 2] + c2 * pp + ts * pv + pa;
+        const double rho = g[6 + ax] + c3 * pp + c2 * pv + ts * pa;
+        const double range = farkas ? Uabs : fmax(fmax(Uhi - z[6 + ax], z[6 + ax] - Ulo), 0.0);
+        usum += fabs(rho) * range;
+      }
+    }
+    double px = 0.0;
+#pragma unroll
+    for (int t = 0; t < 6; ++t) px += pn[t] * D[p.o_x0 + t];
+    if (w.lane == 0) { w.red[0] = px; w.red[1] = usum; }
+  }
+  __syncthreads();
+  const double pi0x0 = w.red[0], usum = w.red[1];
+  __syncthreads();
+  if (farkas) return (hl - pi0x0 + usum) < -1e-10 * (mag + fabs(pi0x0) + usum) - 1e-13;
+  *lb = fz + p.cost_const - (hl - lgz) - usum - 1e-12 * (fabs(fz) + fabs(hl) + fabs(lgz) + usum);
+  return false;
+}
+
 __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEntry &e1, const PhiEntry &e2, const double *zwarm, double warm_mu,
                                                   const SuspendIO &sio) {
   const DevProb &p = *w.p;
   const double *D = w.D;
   const int N = w.N;
   const bool lead = (w.g == 0);
-  QpResult res; res.status = 1; res.converged = 0; res.iters = 0; res.obj = 0.0; res.rows = 0; res.susp_index = -1;
+  QpResult res; res.status = 1; res.converged = 0; res.iters = 0; res.obj = 0.0; res.lb = -MQ_INF; res.rows = 0; res.susp_index = -1;
 #ifdef MQ_PROF
   res.c_rows = res.c_factor = res.c_sweeps = 0; res.c_a = res.c_ared = res.c_d = res.c_e = res.c_g = res.c_atr = 0;
   long long qc0 = 0;
@@ -747,9 +854,12 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
   { double q0 = 0.0, q1 = 0.0, q2 = 0.0; team_reduce(w, rdn, q0, q1, q2); }
   }   // fresh solve
 
-  int status = 2, it = 0;
+  int status = 2, it = 0, it_start = it0, next_check = 3;
+  double lmax_last = 0.0;
   bool may_park = (sio.pool != nullptr);
-  for (it = it0; it < 100; ++it) {
+  for (;;) {   // interior-point iterations, interrupted when the multipliers are to be tested as a Farkas certificate (status 5)
+  status = 2;
+  for (it = it_start; it < 100; ++it) {
     if (may_park && it - it0 >= sio.budget) {
       // iteration budget of this round used up: park the relaxation (it continues in the next round) if a slot is left
       if (threadIdx.x == 0) w.red[0] = (double)atomicAdd(sio.counter, 1);
@@ -809,7 +919,11 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
     res.rows += m;
     const double mu = (m > 0) ? musum / m : 0.0;
     if (rpn <= 1e-9 && rdn <= 1e-8 * (1.0 + cn) && mu <= 1e-10) { status = 0; break; }
-    if (lmax > 1e13) { status = 1; break; }
+    if (lmax > 1e13) { status = 2; break; }   // diverged: infeasible if the multipliers certify it (below)
+    // early exit of infeasible relaxations: once the multipliers have grown, test them as a Farkas certificate (below; the
+    // iteration resumes here, with this pass A repeated, if they are not one yet)
+    lmax_last = lmax;
+    if (it >= next_check && rpn > 1e-5 && lmax > 1.0 + cn) { status = 5; break; }
     // ---- predictor ----
     MQ_TICK(c_rows)
     if (w.wid == 0) riccati_factor(w, e1, e2);
@@ -900,23 +1014,38 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
     if (alpha < 1e-6) { if (++stall >= 5) { status = 2; break; } } else stall = 0;
   }
   res.iters = it - it0;
-  res.converged = (status == 0);
+  if (status == 0) { res.converged = 1; break; }
   MQ_TICK(c_rows)
-  if (status != 0) {
-    // not converged: infeasible only if the primal point violates its rows
-    double worst = 0.0, nanflag = 0.0, q0 = 0.0, q1 = 0.0;
+  bool farkas = true; StepCtx dsc; dsc.alpha = 0.0; dsc.sigmu = 0.0; dsc.pending = false;
+  double dlm = lmax_last;
+  if (status == 2) {
+    // not converged.  A primal feasible point is still usable (upper bound + Lagrangian lower bound); a violated one
+    // closes the node only with a Farkas certificate, otherwise the outcome is "unknown" and the caller keeps the
+    // node's bound in the books.
+    double worst = 0.0, lmx = 0.0, nanflag = 0.0, q1 = 0.0;
     MQ_FOR_STAGES(i, act) {
       if (!act) continue;
-      PassViol v; v.worst = 0.0;
+      PassViol v; v.io.init(w.rows, w.NP, i); v.worst = 0.0; v.lmax = 0.0;
 #pragma unroll
       for (int t = 0; t < 8; ++t) v.y[t] = w.V[i * V_STRIDE + V_Z + t];
       visit_rows(w, i, v);
-      if (!(v.worst == v.worst)) nanflag = 1.0;
-      worst = fmax(worst, v.worst);
+      if (!(v.worst == v.worst) || !(v.lmax == v.lmax)) nanflag = 1.0;
+      worst = fmax(worst, v.worst); lmx = fmax(lmx, v.lmax);
     }
-    team_reduce(w, worst, nanflag, q0, q1);
-    status = (worst > 1e-7 || nanflag > 0.0) ? 1 : 0;
+    team_reduce(w, worst, lmx, nanflag, q1);
+    if (nanflag > 0.0 || !(lmx < MQ_INF) || (worst > 1e-7 && !(lmx > 0.0))) { status = 4; break; }
+    farkas = (worst > 1e-7); dsc = sc; dlm = farkas ? lmx : 1.0;
   }
+  double lbv = -MQ_INF;
+  const bool cert = dual_check(w, dsc, farkas, dlm, &lbv);
+  if (status == 5) {
+    if (cert) { status = 1; break; }
+    it_start = it; next_check = it + 3;   // not a certificate yet: carry on
+    continue;
+  }
+  if (farkas) status = cert ? 1 : 4; else { status = 0; res.lb = lbv; }
+  break;
+  }   // for (;;)
   res.status = status;
   if (status == 0) {
     double o = 0.0, q0 = 0.0, q1 = 0.0, q2 = 0.0;
@@ -929,6 +1058,7 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
     }
     team_reduce(w, q0, q1, o, q2);
     res.obj = o + p.cost_const;
+    if (res.converged) res.lb = res.obj;
   }
   return res;
 }

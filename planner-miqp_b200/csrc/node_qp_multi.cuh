@@ -453,16 +453,33 @@ struct MPassG {
   MQ_MFN void general(int slot, const double a[6], double rhs) { rmax = fmax(rmax, ip_ratio(rows[slot * N + i], dot6m(a, y), dot6m(a, d), dot6m(a, da), rhs, sigmu)); }
 };
 struct MPassViol {
-  const double *y; double worst;
-  MQ_MFN void bound(int, int T, double sgn, double rhs) { worst = fmax(worst, sgn * y[T] - rhs); }
-  MQ_MFN void general(int, const double a[6], double rhs) { worst = fmax(worst, dot6m(a, y) - rhs); }
+  double2 *rows; int N, i; const double *y; double worst, lmax;
+  MQ_MFN void bound(int slot, int T, double sgn, double rhs) { worst = fmax(worst, sgn * y[T] - rhs); lmax = fmax(lmax, rows[slot * N + i].y); }
+  MQ_MFN void general(int slot, const double a[6], double rhs) { worst = fmax(worst, dot6m(a, y) - rhs); lmax = fmax(lmax, rows[slot * N + i].y); }
+};
+struct MDualAcc { double hl, lgz, mag, fz, usum; };   // h'lambda, lambda'Gz, sum lambda |h|, f(z), sum |gradient| x range of the boxed variables
+struct MPassDual {  // G'lambda of one car-stage (multipliers as stored, scaled; any lambda >= 0 gives a valid bound / certificate)
+  double2 *rows; int N, i; double scale; const double *y; double gl[8]; MDualAcc *acc;
+  MQ_MFN double lam_of(int slot, double gz, double rhs) {
+    double lam = rows[slot * N + i].y;
+    lam = (lam > 0.0 ? lam : 0.0) * scale;
+    acc->hl += lam * rhs; acc->lgz += lam * gz; acc->mag += lam * fabs(rhs);
+    return lam;
+  }
+  MQ_MFN void bound(int slot, int T, double sgn, double rhs) { gl[T] += sgn * lam_of(slot, sgn * y[T], rhs); }
+  MQ_MFN void general(int slot, const double a[6], double rhs) {
+    const double lam = lam_of(slot, dot6m(a, y), rhs);
+#pragma unroll
+    for (int t = 0; t < 6; ++t) gl[t] += a[t] * lam;
+  }
 };
 
 // ---------------------------------------------------------------------------------------
 // pair-stage passes.  mode: 0 init, 1 pass A (Hessian), 2 recover affine slack step + pass D,
-// 3 pass E (corrector gradient), 4 recover combined slack step + pass G, 5 violation
+// 3 pass E (corrector gradient), 4 recover combined slack step + pass G, 5 violation (+ largest multiplier),
+// 6 dual information (sigmu = scale of the multipliers, first_iter = Farkas mode: cost gradient left out)
 // ---------------------------------------------------------------------------------------
-struct PairAcc { IpStat st; IpAff af; double rmax, worst, rd0; };
+struct PairAcc { IpStat st; IpAff af; double rmax, worst, rd0; MDualAcc du; };
 
 template <int MODE>
 MQ_FN void m_pair_stage(const MCtx &k, int i, const MStep &sc, double sigmu, bool first_iter, PairAcc &acc) {
@@ -506,7 +523,24 @@ MQ_FN void m_pair_stage(const MCtx &k, int i, const MStep &sc, double sigmu, boo
         }
         if (MODE == 5) {
           acc.worst = fmax(acc.worst, gz - r.rhs);
-          if (S) { acc.worst = fmax(acc.worst, sv - cap); acc.worst = fmax(acc.worst, -sv); }
+          acc.st.lmax = fmax(acc.st.lmax, pw[q].y);
+          if (S) { acc.worst = fmax(acc.worst, sv - cap); acc.worst = fmax(acc.worst, -sv); acc.st.lmax = fmax(acc.st.lmax, fmax(pw[4 + 2 * sk].y, pw[5 + 2 * sk].y)); }
+          continue;
+        }
+        if (MODE == 6) {
+          const double scale = sigmu; const bool farkas = first_iter;
+          const double lam = fmax(pw[q].y, 0.0) * scale;
+          acc.du.hl += lam * r.rhs; acc.du.lgz += lam * gz; acc.du.mag += lam * fabs(r.rhs);
+          double *gd = k.DZ + (long)i * nz;
+          for (int t = 0; t < 6; ++t) { gd[8 * a + t] += r.ca[t] * lam; gd[8 * b + t] += r.cb[t] * lam; }
+          if (S) {   // the slack is a boxed variable of its own: gradient (cost) qs sigma - lam + lam_hi - lam_lo, range within [0, cap]
+            const double lh = fmax(pw[4 + 2 * sk].y, 0.0) * scale, ll = fmax(pw[5 + 2 * sk].y, 0.0) * scale;
+            acc.du.hl += lh * cap; acc.du.lgz += lh * sv - ll * sv; acc.du.mag += lh * cap;
+            const double gs = (farkas ? 0.0 : qs * sv) - lam + lh - ll;
+            const double range = farkas ? cap : fmax(fmax(cap - sv, sv), 0.0);
+            acc.du.usum += fabs(gs) * range;
+            if (!farkas) acc.du.fz += p.w_slack * sv * sv;
+          }
           continue;
         }
         const double dxa = dot6m(r.ca, dai + 8 * a) + dot6m(r.cb, dai + 8 * b);   // coefficient part of g.dza
@@ -782,7 +816,60 @@ MQ_FN void m_riccati_forward(const MCtx &k, double *dst) {
   }
 }
 
-struct MQpResult { int status, iters; double obj; long rows; };
+// status: 0 optimal (or, with converged == 0, a feasible point), 1 proven infeasible (empty box or Farkas certificate),
+// 4 unknown (no convergence, no feasible point, no certificate).  lb: valid lower bound of the relaxation (obj if converged,
+// else the Lagrangian bound of the last multipliers).
+struct MQpResult { int status, iters, converged; double obj, lb; long rows; };
+
+// Dual information of the current iterate; same mathematics as dual_check of node_qp.cuh (costate recursion per car, the
+// pair rows couple the cars only through the stage gradients; the pair slacks are boxed variables).  Uses DZ as scratch (dead between pass A and the second forward sweep, and after the last iteration).
+MQ_FN bool m_dual_check(const MCtx &k, bool farkas, double lmax, double *lb) {
+  const DevProb &p = *k.p;
+  const double *D = k.D;
+  const int N = k.N, C = k.C, nz = k.nz, P = k.P;
+  const double scale = farkas ? 1.0 / lmax : 1.0;
+  PairAcc acc; acc.du.hl = 0.0; acc.du.lgz = 0.0; acc.du.mag = 0.0; acc.du.fz = 0.0; acc.du.usum = 0.0;
+  PFOR(itc, C * N) {
+    const int c = itc / N, i = itc % N;
+    MPassDual v; v.rows = k.rows + (long)c * k.kmaxc * N; v.N = N; v.i = i; v.scale = scale; v.y = k.Z + (long)i * nz + 8 * c; v.acc = &acc.du;
+    for (int t = 0; t < 8; ++t) v.gl[t] = 0.0;
+    m_car_rows(k, c, i, v);
+    const double *cst = D + p.o_cost + 16 * (c * N + i);
+    double *gi = k.DZ + (long)i * nz + 8 * c;
+    for (int t = 0; t < 8; ++t) {
+      gi[t] = v.gl[t] + (farkas ? 0.0 : cst[t] * v.y[t] + cst[8 + t]);
+      if (!farkas) acc.du.fz += (0.5 * cst[t] * v.y[t] + cst[8 + t]) * v.y[t];
+    }
+  }
+  k.sync();
+  if (P > 0) { MStep s0; s0.alpha = 0.0; s0.sigmu = 0.0; s0.pending = false; PFOR(i, N) m_pair_stage<6>(k, i, s0, scale, farkas, acc); k.sync(); }
+  // costate recursion of every car (the dynamics are block diagonal over the cars)
+  double px = 0.0;
+  PFOR(c, C) {
+    const double ts = p.ts, c2 = p.c2, c3 = p.c3;
+    const double Ulo = p.total_min_jerk, Uhi = p.total_max_jerk, Uabs = fmax(fabs(Ulo), fabs(Uhi));
+    double pn[6];
+    for (int t = 0; t < 6; ++t) pn[t] = k.DZ[(long)(N - 1) * nz + 8 * c + t];
+    for (int i = N - 2; i >= 0; --i) {
+      const double *g = k.DZ + (long)i * nz + 8 * c, *z = k.Z + (long)i * nz + 8 * c;
+      for (int ax = 0; ax < 2; ++ax) {
+        const double pp = pn[3 * ax], pv = pn[3 * ax + 1], pa = pn[3 * ax + 2];
+        pn[3 * ax] = g[3 * ax] + pp;
+        pn[3 * ax + 1] = g[3 * ax + 1] + ts * pp + pv;
+        pn[3 * ax + 2] = g[3 * ax + 2] + c2 * pp + ts * pv + pa;
+        const double rho = g[6 + ax] + c3 * pp + c2 * pv + ts * pa;
+        const double range = farkas ? Uabs : fmax(fmax(Uhi - z[6 + ax], z[6 + ax] - Ulo), 0.0);
+        acc.du.usum += fabs(rho) * range;
+      }
+    }
+    for (int t = 0; t < 6; ++t) px += pn[t] * D[p.o_x0 + 6 * c + t];
+  }
+  const double hl = k.rsum(acc.du.hl), lgz = k.rsum(acc.du.lgz), mag = k.rsum(acc.du.mag), fz = k.rsum(acc.du.fz), usum = k.rsum(acc.du.usum);
+  const double pi0x0 = k.rsum(px);
+  if (farkas) return (hl - pi0x0 + usum) < -1e-10 * (mag + fabs(pi0x0) + usum) - 1e-13;
+  *lb = fz + p.cost_const - (hl - lgz) - usum - 1e-12 * (fabs(fz) + fabs(hl) + fabs(lgz) + usum);
+  return false;
+}
 
 // Solves the node QP of k.dec (k.jeff filled).  On success Z holds the optimal stage vectors
 // and sig[..][SG_VAL] the slacks.
@@ -790,7 +877,7 @@ MQ_FN MQpResult m_solve_node_qp(const MCtx &k) {
   const DevProb &p = *k.p;
   const double *D = k.D;
   const int N = k.N, C = k.C, nz = k.nz, P = k.P, nxx = k.nxx;
-  MQpResult res; res.status = 1; res.iters = 0; res.obj = 0.0; res.rows = 0;
+  MQpResult res; res.status = 1; res.iters = 0; res.converged = 0; res.obj = 0.0; res.lb = -MQM_INF; res.rows = 0;
 
   // trivially infeasible boxes
   int bad = 0;
@@ -892,7 +979,8 @@ MQ_FN MQpResult m_solve_node_qp(const MCtx &k) {
     res.rows += m;
     const double mu = (m > 0) ? musum / m : 0.0;
     if (rpn <= 1e-9 && rdn <= 1e-8 * (1.0 + cn) && mu <= 1e-10) { status = 0; break; }
-    if (lmax > 1e13 || !(musum == musum)) { status = 1; break; }
+    if (lmax > 1e13 || !(musum == musum)) { status = 2; break; }   // diverged: infeasible if the multipliers certify it (below)
+    if (it >= 3 && rpn > 1e-5 && lmax > 1.0 + cn && m_dual_check(k, true, lmax, nullptr)) { status = 1; break; }   // early exit of infeasible relaxations
     // ---- predictor --------------------------------------------------------------------------
     m_riccati_factor(k);
     m_riccati_forward(k, k.DZA);
@@ -955,19 +1043,23 @@ MQ_FN MQpResult m_solve_node_qp(const MCtx &k) {
     if (alpha < 1e-6) { if (++stall >= 5) { status = 2; break; } } else stall = 0;
   }
   res.iters = it;
-  if (status != 0) {
-    // not converged: infeasible only if the primal point violates its rows
-    PairAcc acc; acc.worst = 0.0;
+  res.converged = (status == 0);
+  if (status == 2) {
+    // not converged.  A primal feasible point is still usable (upper bound + Lagrangian lower bound); a violated one
+    // closes the node only with a Farkas certificate, otherwise the outcome is "unknown"
+    PairAcc acc; acc.worst = 0.0; acc.st.lmax = 0.0;
     PFOR(itc, C * N) {
       const int c = itc / N, i = itc % N;
-      MPassViol v; v.worst = 0.0; v.y = k.Z + (long)i * nz + 8 * c;
+      MPassViol v; v.rows = k.rows + (long)c * k.kmaxc * N; v.N = N; v.i = i; v.worst = 0.0; v.lmax = 0.0; v.y = k.Z + (long)i * nz + 8 * c;
       m_car_rows(k, c, i, v);
-      acc.worst = fmax(acc.worst, v.worst);
+      acc.worst = fmax(acc.worst, v.worst); acc.st.lmax = fmax(acc.st.lmax, v.lmax);
     }
     if (P > 0) { PFOR(i, N) m_pair_stage<5>(k, i, sc, 0.0, false, acc); }
-    int nan = !(acc.worst == acc.worst);
-    const double worst = k.rmax(acc.worst);
-    status = (worst > 1e-7 || k.rany(nan)) ? 1 : 0;
+    int nan = !(acc.worst == acc.worst) || !(acc.st.lmax == acc.st.lmax);
+    const double worst = k.rmax(acc.worst), lmx = k.rmax(acc.st.lmax);
+    if (k.rany(nan) || !(lmx < MQM_INF)) status = 4;
+    else if (worst <= 1e-7) { status = 0; m_dual_check(k, false, 1.0, &res.lb); }
+    else status = (lmx > 0.0 && m_dual_check(k, true, lmx, nullptr)) ? 1 : 4;
   }
   res.status = status;
   if (status == 0) {
@@ -981,6 +1073,7 @@ MQ_FN MQpResult m_solve_node_qp(const MCtx &k) {
     PFOR(e, P * N * 4) { const double sv = k.sig[e * SG_SIZE + SG_VAL]; o += p.w_slack * sv * sv; }
     o = k.rsum(o);
     res.obj = o + p.cost_const;
+    if (res.converged) res.lb = res.obj;
   }
   return res;
 }

@@ -83,7 +83,7 @@ struct MiqpB200Solver {
   DevBuf<int> b_suspslot, b_suspcnt;
   DevBuf<int2> b_meta, b_work;
   DevBuf<unsigned long long> b_uid, b_keybuf, b_incuid, b_stats, b_prof;
-  DevBuf<int> b_open, b_opencnt, b_free, b_freecnt, b_sel, b_selcnt, b_done, b_lock, b_ctrl;
+  DevBuf<int> b_open, b_opencnt, b_free, b_freecnt, b_sel, b_selcnt, b_done, b_lock, b_ctrl, b_overflow;
   int smem_per_warp = 0, warps_per_cta = 4, ctas = 0, wide_ctas = 0;
   // CTA-per-node kernel for plans with several cars
   int n_single = 0, n_multi = 0, multi_threads = 64, multi_ctas = 0, multi_use_smem = 1;
@@ -97,7 +97,7 @@ struct MiqpB200Solver {
   DVec h_x;   // page-locked: D2H target of the solution vectors
   std::vector<double> h_viol, h_obj, h_bb, h_ub;
   std::vector<unsigned long long> h_stats;
-  std::vector<int> h_done;
+  std::vector<int> h_done, h_overflow;
   int single_maxN = 2;
   size_t pool_budget = 0;
 };
@@ -258,13 +258,13 @@ void setup_bnb(MiqpB200Solver *s) {
   st.sel_per_plan = KS;
   // pool capacity per plan
   int cap = s->opt.pool_capacity;
+  // warm start of the children from the parent's relaxed optimum (single-car nodes): N x 8 doubles per node
+  st.warm_mu = 10.0; st.zp_stride = 0;   // profiles/r1k: with parked relaxations 84.2 -> 76.9 ms (2048 plans), 8.6 -> 7.7 iterations per node
+  st.tau_k = 1.0;   // profiles/r1k: 9.45 -> 8.6 interior-point iterations per node
+  if (const char *e = getenv("MIQP_TAU_K")) st.tau_k = atof(e);
+  if (const char *e = getenv("MIQP_WARM_MU")) st.warm_mu = atof(e);
+  if (st.warm_mu > 0.0 && s->n_single > 0) st.zp_stride = s->single_maxN * 8;
   if (cap <= 0) {
-    // warm start of the children from the parent's relaxed optimum (single-car nodes): N x 8 doubles per node
-    st.warm_mu = 10.0; st.zp_stride = 0;   // profiles/r1k: with parked relaxations 84.2 -> 76.9 ms (2048 plans), 8.6 -> 7.7 iterations per node
-    st.tau_k = 1.0;   // profiles/r1k: 9.45 -> 8.6 interior-point iterations per node
-    if (const char *e = getenv("MIQP_TAU_K")) st.tau_k = atof(e);
-    if (const char *e = getenv("MIQP_WARM_MU")) st.warm_mu = atof(e);
-    if (st.warm_mu > 0.0 && s->n_single > 0) st.zp_stride = s->single_maxN * 8;
     const size_t node_bytes = (size_t)st.ndec_stride + 48 + (size_t)8 * st.zp_stride;
     // pool budget: a third of the free HBM, at most 48 GiB (B200: 180 GB per GPU)
     if (s->pool_budget == 0) {   // asked once per solver: cudaMemGetInfo costs about a millisecond
@@ -316,8 +316,9 @@ void setup_bnb(MiqpB200Solver *s) {
   s->b_incz.ensure((size_t)count * st.zstride); st.inc_z = s->b_incz.p;
   s->b_incdec.ensure((size_t)count * st.ndec_stride); st.inc_dec = s->b_incdec.p;
   s->b_incuid.ensure(count); st.inc_uid = s->b_incuid.p;
-  s->b_stats.ensure((size_t)3 * count);
-  st.stat_nodes = s->b_stats.p; st.stat_iters = s->b_stats.p + count; st.stat_rows = s->b_stats.p + 2 * count;
+  s->b_stats.ensure((size_t)4 * count);
+  st.stat_nodes = s->b_stats.p; st.stat_iters = s->b_stats.p + count; st.stat_rows = s->b_stats.p + 2 * count; st.stat_uncert = s->b_stats.p + 3 * count;
+  s->b_overflow.ensure(count); st.overflow = s->b_overflow.p;
   s->b_work.ensure(st.work_cap); st.work = s->b_work.p;
   s->b_work2.ensure(st.work_cap); st.work2 = s->b_work2.p;
   s->b_ctrl.ensure(8);
@@ -380,7 +381,7 @@ void miqp_b200_destroy(MiqpB200Solver *s) {
   s->b_pruned.release(); s->b_incz.release(); s->b_meta.release(); s->b_work.release();
   s->b_uid.release(); s->b_keybuf.release(); s->b_incuid.release(); s->b_stats.release(); s->b_open.release();
   s->b_opencnt.release(); s->b_free.release(); s->b_freecnt.release(); s->b_sel.release(); s->b_selcnt.release();
-  s->b_zpool.release(); s->b_susp0.release(); s->b_susp1.release(); s->b_suspslot.release(); s->b_suspcnt.release(); s->b_done.release(); s->b_lock.release(); s->b_ctrl.release(); s->b_multi_ws.release(); s->b_work2.release();
+  s->b_zpool.release(); s->b_susp0.release(); s->b_susp1.release(); s->b_suspslot.release(); s->b_suspcnt.release(); s->b_done.release(); s->b_overflow.release(); s->b_lock.release(); s->b_ctrl.release(); s->b_multi_ws.release(); s->b_work2.release();
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   if (s->evr0) cudaEventDestroy(s->evr0);
@@ -559,7 +560,6 @@ int miqp_b200_batch_run(MiqpB200Solver *s, float *device_ms) {
       CK(cudaEventElapsedTime(&ms, s->evr0, s->evr1));
       node_ms += ms;
       if (s->opt.verbose > 1) fprintf(stderr, "[miqp_b200] round %ld: work %d active %d err %d node kernel %.3f ms\n", rounds, ctrl[0], ctrl[2], ctrl[3], ms);
-      if (ctrl[3]) return fail(s, MIQP_B200_ERR_RESOURCE, "node pool exhausted; raise MiqpB200Options.pool_capacity");
       if (ctrl[2] == 0) break;  // every plan finished
       const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
       if (el > tlim) { s->timed_out = true; break; }
@@ -594,16 +594,17 @@ int miqp_b200_batch_fetch(MiqpB200Solver *s, double *const *x_out, MiqpB200Solve
     const long ncols = s->pk.total_cols;
     const auto tf0 = std::chrono::steady_clock::now();
     s->h_x.resize(ncols); s->h_viol.resize(count); s->h_obj.resize(count); s->h_bb.resize(count); s->h_ub.resize(count);
-    s->h_stats.resize((size_t)3 * count); s->h_done.resize(count);
+    s->h_stats.resize((size_t)4 * count); s->h_done.resize(count); s->h_overflow.resize(count);
     CK(cudaMemcpyAsync(s->h_x.data(), s->d_x.p, sizeof(double) * ncols, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaMemcpyAsync(s->h_viol.data(), s->d_viol.p, sizeof(double) * count, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaMemcpyAsync(s->h_obj.data(), s->d_obj.p, sizeof(double) * count, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaMemcpyAsync(s->h_bb.data(), s->d_bb.p, sizeof(double) * count, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaMemcpyAsync(s->h_ub.data(), s->st.ub, sizeof(double) * count, cudaMemcpyDeviceToHost, s->stream));
-    CK(cudaMemcpyAsync(s->h_stats.data(), s->b_stats.p, sizeof(unsigned long long) * 3 * count, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(s->h_stats.data(), s->b_stats.p, sizeof(unsigned long long) * 4 * count, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaMemcpyAsync(s->h_done.data(), s->st.done, sizeof(int) * count, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(s->h_overflow.data(), s->st.overflow, sizeof(int) * count, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
-    s->stats.d2h_bytes = (long)(sizeof(double) * (ncols + 4 * count) + sizeof(unsigned long long) * 3 * count + sizeof(int) * count);
+    s->stats.d2h_bytes = (long)(sizeof(double) * (ncols + 4 * count) + sizeof(unsigned long long) * 4 * count + 2 * sizeof(int) * count);
     long nodes = 0, iters = 0, rows = 0;
     if (x_out) {   // scatter of the solution vectors into the caller's buffers: a few host threads for large batches
       const int nthr = (ncols * (long)sizeof(double) > (8L << 20)) ? 4 : 1;
@@ -630,6 +631,8 @@ int miqp_b200_batch_fetch(MiqpB200Solver *s, double *const *x_out, MiqpB200Solve
       in.seconds = s->last_seconds;
       in.nodes = (long)s->h_stats[k]; in.qp_iters = (long)s->h_stats[count + k]; in.rounds = s->stats.rounds;
       in.best_bound = s->h_bb[k];
+      in.uncertified = (long)s->h_stats[3 * (size_t)count + k];
+      in.pool_exhausted = s->h_overflow[k];
       if (have) {
         // every open or pruned node may lie above the incumbent: report min(bound, incumbent) like CPLEX's best bound
         if (in.best_bound > s->h_ub[k]) in.best_bound = s->h_ub[k];

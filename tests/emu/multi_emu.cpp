@@ -105,10 +105,12 @@ extern "C" int emu_multi_solve(const MiqpB200Problem *q, double gap_tol, double 
     iters += out.iters;
     if (verbose > 1) fprintf(stderr, "emu node %ld depth %d what %d obj %.6f kind %d c%d i%d q%d viol %.3g open %zu ub %.6f iters %d\n", nodes, nd.depth, out.what, out.obj, sh.br.kind, sh.br.c, sh.br.i, sh.br.q, sh.br.viol, open.size(), ub, out.iters);
     if (out.what == MN_INFEASIBLE) continue;
+    if (out.what == MN_UNKNOWN) { pruned_lb = std::min(pruned_lb, nd.bound); if (verbose) fprintf(stderr, "emu uncertified node\n"); continue; }
     if (out.what == MN_PRUNED) { pruned_lb = std::min(pruned_lb, out.obj); continue; }
     if (out.what == MN_INCUMBENT) {
-      if (out.obj < ub) {
-        ub = out.obj; cmp.have_inc = true;
+      if (!out.converged) pruned_lb = std::min(pruned_lb, out.obj);
+      if (out.fval < ub) {
+        ub = out.fval; cmp.have_inc = true;
         for (int c = 0; c < p.C; ++c) for (int i = 0; i < p.N; ++i) for (int t = 0; t < 8; ++t) traj_out[(c * p.N + i) * 8 + t] = k.Z[(long)i * k.nz + 8 * c + t];
         for (int e = 0; e < p.P * p.N * 4; ++e) sig_out[e] = k.sig[e * SG_SIZE + SG_VAL];
         memcpy(dec_out, k.dec, nds);
