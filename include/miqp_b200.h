@@ -99,11 +99,10 @@ typedef struct MiqpB200SolveInfo {
   int status;            /* MIQP_B200_SUCCESS / FAILED_NO_SOLUT / FAILED_TIMEOUT */
   int proven;            /* 1 if gap <= gap_tol was reached */
   double objective, best_bound, gap; /* gap = |best_bound-objective| / (1e-10+|objective|) */
-  double seconds;        /* from the start of the batch to the end of this plan's search, device clock (%globaltimer) */
+  double seconds;        /* wall time of the batch this plan was solved in */
   double max_violation;  /* of the returned vector against the full big-M model, device-evaluated */
-  long nodes, qp_iters, rounds;   /* rounds: select / solve rounds of this plan's own search (plans do not share rounds) */
+  long nodes, qp_iters, rounds;
   long uncertified;      /* node relaxations closed without optimum, feasible point or Farkas certificate; their bounds stay in best_bound */
-  int root_violations;   /* disjunctions that the root relaxation violates (the scheduler's hardness estimate of the plan) */
   int pool_exhausted;    /* 1: the node pool of this plan ran out (children were dropped, their bound stays in best_bound; result not proven) */
 } MiqpB200SolveInfo;
 

@@ -66,7 +66,7 @@ class CSolveInfo(C.Structure):
     _fields_ = [("status", C.c_int), ("proven", C.c_int), ("objective", C.c_double),
                 ("best_bound", C.c_double), ("gap", C.c_double), ("seconds", C.c_double),
                 ("max_violation", C.c_double), ("nodes", C.c_long), ("qp_iters", C.c_long),
-                ("rounds", C.c_long), ("uncertified", C.c_long), ("root_violations", C.c_int), ("pool_exhausted", C.c_int)]
+                ("rounds", C.c_long), ("uncertified", C.c_long), ("pool_exhausted", C.c_int)]
 
 
 class COptions(C.Structure):
@@ -95,7 +95,6 @@ class SolveInfo:
     rounds: int
     uncertified: int = 0
     pool_exhausted: int = 0
-    root_violations: int = 0
 
 
 def library_path() -> str:
@@ -378,4 +377,4 @@ class Solver:
     @staticmethod
     def _info(i: CSolveInfo) -> SolveInfo:
         return SolveInfo(i.status, bool(i.proven), i.objective, i.best_bound, i.gap, i.seconds,
-                         i.max_violation, i.nodes, i.qp_iters, i.rounds, i.uncertified, i.pool_exhausted, i.root_violations)
+                         i.max_violation, i.nodes, i.qp_iters, i.rounds, i.uncertified, i.pool_exhausted)

@@ -23,9 +23,25 @@
 #include "kernels.cuh"
 #include "node_qp.cuh"
 #include "bnb_common.cuh"
-#include "sched.cuh"
 
 namespace miqp {
+
+// priority key, smaller = earlier.  Without incumbent the search dives: the children created in the
+// last round come first (least violated alternative first, then bound); if the dive died (no
+// newborn node) it restarts from the best bound.  Deepest-first backtracking is deliberately NOT
+// used: it gets trapped below a wrong early decision (seen on 3 of 512 config-2 plans: 20k+ nodes
+// instead of ~40).  With an incumbent: best bound first, then deepest.
+__device__ __forceinline__ unsigned long long node_key(double bound, int depth, int rank, unsigned long long uid, bool have_inc, bool newborn) {
+  unsigned long long d = 1023 - (unsigned long long)(depth > 1023 ? 1023 : depth);  // 10 bits
+  unsigned long long r = (unsigned long long)(rank + 1 > 127 ? 127 : rank + 1);      // 7 bits
+  unsigned long long b = ordered_bits(bound) >> 24;                                   // 40 bits
+  unsigned long long u = uid & 127ULL;                                                // 7 bits
+  if (have_inc) return (b << 24) | (d << 14) | (r << 7) | u;
+  if (newborn) return (r << 47) | (b << 7) | u;
+  return (1ULL << 63) | (b << 17) | (d << 7) | u;
+}
+__device__ __forceinline__ int meta_rank(int my) { return (my & 0xff) - 1; }
+__device__ __forceinline__ int meta_birth(int my) { return my >> 8; }
 
 // ---------------------------------------------------------------------------------------
 // init
@@ -59,22 +75,7 @@ __global__ void bnb_init_kernel(BnbState st, const DevProb *probs, const unsigne
     st.done[s] = 0; st.lock[s] = 0;
     st.stat_nodes[s] = 0; st.stat_iters[s] = 0; st.stat_rows[s] = 0; st.stat_uncert[s] = 0; st.overflow[s] = 0;
     st.inc_uid[s] = ~0ULL;
-    // per-plan rounds (sched.cuh)
-    st.rd_base[s] = 0; st.rd_end[s] = 0; st.rd_next[s] = 0; st.rd_left[s] = 0; st.rd_round[s] = 0; st.t_done[s] = 0ULL;
-    st.rank_of[s] = s; st.order[s] = s; st.score[s] = 0;
-    if (s == 0) { *st.t_start = global_ns(); *st.stop = 0; }
-  }
-  // plans left per class, empty ready bitmaps
-  if (s == 0) {
-    int n1 = 0;
-    for (int k = tid; k < st.count; k += nt) n1 += (probs[k].C > 1 || st.force_multi) ? 1 : 0;
-    for (int o = 16; o > 0; o >>= 1) n1 += __shfl_xor_sync(0xffffffffu, n1, o);
-    __shared__ int part[32];
-    if ((tid & 31) == 0) part[tid >> 5] = n1;
-    __syncthreads();
-    if (tid == 0) { int m = 0; for (int k = 0; k < (nt >> 5); ++k) m += part[k]; st.plans_left[1] = m; st.plans_left[0] = st.count - m; }
-    for (int k = tid; k < PRIO_BUCKETS * ((st.count + 31) / 32); k += nt) { st.ready[0][k] = 0u; st.ready[1][k] = 0u; }
-    for (int k = tid; k < 2 * PRIO_BUCKETS; k += nt) st.bucket_cnt[k] = 0;
+    if (s == 0) { *st.active_prev = 0; *st.work_cnt = 0; *st.work_next = 0; *st.active = 0; *st.err = 0; *st.work_cnt2 = 0; *st.work_next2 = 0; }
   }
 }
 
@@ -83,15 +84,170 @@ void launch_bnb_init(const BnbState &st, const DevProb *probs, const unsigned ch
 }
 
 // ---------------------------------------------------------------------------------------
-// first round of every plan (the later ones are started by the node kernels themselves, sched.cuh)
+// select
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) bnb_select_all_kernel(BnbState st, const DevProb *probs) {
-  __shared__ SelSmem sm;
-  plan_select(st, probs, blockIdx.x, sm);
+constexpr int SEL_THREADS = 256;
+
+__device__ __forceinline__ int block_excl_scan(int flag, int *warp_tot /*[8]*/, int &total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned bal = __ballot_sync(FULL, flag);
+  int pre = __popc(bal & ((1u << lane) - 1));
+  if (lane == 0) warp_tot[wid] = __popc(bal);
+  __syncthreads();
+  int off = 0; total = 0;
+  for (int k = 0; k < SEL_THREADS / 32; ++k) { int t = warp_tot[k]; if (k < wid) off += t; total += t; }
+  __syncthreads();
+  return off + pre;
 }
 
-void launch_bnb_select_all(const BnbState &st, const DevProb *probs, cudaStream_t s) {
-  bnb_select_all_kernel<<<st.count, 128, 0, s>>>(st, probs);
+__global__ void __launch_bounds__(SEL_THREADS) bnb_select_kernel(BnbState st, const DevProb *probs, int round) {
+  const int s = blockIdx.x;
+  const int tid = threadIdx.x;
+  __shared__ int warp_tot[SEL_THREADS / 32];
+  __shared__ int s_out, s_free, s_tie, s_wbase, s_nsusp;
+  __shared__ int hist[256];
+  __shared__ double s_pruned[SEL_THREADS / 32];
+  __shared__ unsigned long long s_prefix; __shared__ int s_remaining;
+  if (st.done[s]) return;
+  const DevProb &p = probs[s];
+  const long pb = (long)s * st.cap;
+  const int KS = st.sel_per_plan;   // stride of sel_idx = largest number of nodes a plan may take per round
+  // 1. release the slots processed in the last round
+  const int nsel_prev = st.sel_cnt[s];
+  const int free0 = st.free_cnt[s];
+  // (a parked relaxation keeps its node slot: it is back in the open list and continues this round)
+  if (tid == 0) {
+    int f = free0;
+    for (int k = 0; k < nsel_prev; ++k) { const int sl = st.sel_idx[(long)s * KS + k]; if (!st.susp_slot || st.susp_slot[pb + sl] < 0) st.free_stack[pb + f++] = sl; }
+    s_free = f; s_out = 0; s_tie = 0; s_nsusp = 0;
+  }
+  // 2. cutoff snapshot
+  const double ub = st.ub[s];
+  const bool have_inc = ub < MQ_INF;
+  const double cutoff = have_inc ? ub - p.gap_tol * fabs(ub) : MQ_INF;
+  // nodes taken this round: one dive head per plan until an incumbent exists; afterwards the base
+  // count, raised when few plans are still active so that the resident warps stay busy
+  int K = st.sel_dive;
+  const int act = *st.active_prev > 0 ? *st.active_prev : st.count;
+  const int fill = st.nwarps / act;
+  if (have_inc) {
+    K = st.sel_base;
+    if (fill > K) K = fill;
+    if (K > KS) K = KS;
+  } else {
+    if (st.dive_fill > 0) { const int kd = fill / st.dive_fill; if (kd > K) K = kd; }
+    // still no incumbent long after the typical plan has finished its dive: a hard plan, widen its beam
+    if (st.dive_patience > 0 && round > st.dive_patience) { const int kp = (round - st.dive_patience) * st.dive_growth; if (kp > K) K = kp; }
+    if (K > KS) K = KS;
+  }
+  __syncthreads();
+  // 3. prune by bound, compute keys, compact in place
+  const int n0 = st.open_cnt[s];
+  double pruned = MQ_INF;
+  for (int base = 0; base < n0; base += SEL_THREADS) {
+    const int idx = base + tid;
+    int slot = -1, keep = 0; unsigned long long key = 0;
+    if (idx < n0) {
+      slot = st.open_idx[pb + idx];
+      const double b = st.bound[pb + slot];
+      keep = (b < cutoff);
+      const bool parked = st.susp_slot && st.susp_slot[pb + slot] >= 0;
+      if (parked && !keep) st.susp_slot[pb + slot] = -1;                 // pruned while parked
+      if (parked && keep) { key = 0ULL; atomicAdd(&s_nsusp, 1); }        // continues first: its state is only kept for one round
+      else if (keep) { int2 m = st.meta[pb + slot]; key = node_key(b, m.x, meta_rank(m.y), st.uid[pb + slot], have_inc, meta_birth(m.y) == round - 1); }
+      else { pruned = fmin(pruned, b); int pos = atomicAdd(&s_free, 1); st.free_stack[pb + pos] = slot; }
+    }
+    int total; const int rank = block_excl_scan(keep, warp_tot, total);
+    const int out0 = s_out;
+    if (keep) { st.open_idx[pb + out0 + rank] = slot; st.keybuf[pb + out0 + rank] = key; }
+    __syncthreads();
+    if (tid == 0) s_out = out0 + total;
+    __syncthreads();
+  }
+  pruned = warp_min(pruned);
+  if ((tid & 31) == 0) s_pruned[tid >> 5] = pruned;
+  __syncthreads();
+  const int n1 = s_out;
+  if (tid == 0) {
+    double pm = st.pruned_lb[s];
+    for (int k = 0; k < SEL_THREADS / 32; ++k) pm = fmin(pm, s_pruned[k]);
+    st.pruned_lb[s] = pm;
+  }
+  // a plan whose frontier stays large after pruning is a hard one: let it run wide even while the easy
+  // plans still fill the machine (its sequential depth, not the node count, is what ends the batch)
+  K += s_nsusp; if (K > KS) K = KS;   // parked relaxations do not take the place of new nodes
+  if (have_inc && st.wide_div > 0) { int kw = n1 / st.wide_div; if (kw > KS) kw = KS; if (kw > K) K = kw; }
+  // 4. threshold key of the K best
+  unsigned long long T = ~0ULL; int remaining = n1;  // take everything
+  if (n1 > K) {
+    if (tid == 0) { s_prefix = 0ULL; s_remaining = K; }
+    __syncthreads();
+    for (int pass = 0; pass < 8; ++pass) {
+      const int shift = 56 - 8 * pass;
+      hist[tid] = 0;
+      __syncthreads();
+      const unsigned long long prefix = s_prefix;
+      const unsigned long long himask = (pass == 0) ? 0ULL : (~0ULL << (shift + 8));
+      for (int idx = tid; idx < n1; idx += SEL_THREADS) {
+        const unsigned long long key = st.keybuf[pb + idx];
+        if ((key & himask) == prefix) atomicAdd(&hist[(int)((key >> shift) & 255ULL)], 1);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int rem = s_remaining, b = 0;
+        while (b < 255 && hist[b] < rem) { rem -= hist[b]; ++b; }
+        s_remaining = rem;  // how many to take from bucket b at this digit
+        s_prefix = prefix | ((unsigned long long)b << shift);
+      }
+      __syncthreads();
+    }
+    T = s_prefix; remaining = s_remaining;
+  }
+  // 5. hand the selected nodes to the work list, keep the rest
+  __syncthreads();   // every thread has read n1 = s_out (no barrier in between when n1 <= K; racecheck finding)
+  if (tid == 0) s_out = 0;
+  __syncthreads();
+  int nsel_total = 0;
+  for (int base = 0; base < n1; base += SEL_THREADS) {
+    const int idx = base + tid;
+    int slot = -1, sel = 0, keep = 0; unsigned long long key = 0;
+    if (idx < n1) {
+      slot = st.open_idx[pb + idx]; key = st.keybuf[pb + idx];
+      if (key < T) sel = 1;
+      else if (key == T) sel = (atomicAdd(&s_tie, 1) < remaining);
+      keep = !sel;
+    }
+    int tsel; const int rsel = block_excl_scan(sel, warp_tot, tsel);
+    int tkeep; const int rkeep = block_excl_scan(keep, warp_tot, tkeep);
+    const int out0 = s_out;
+    if (sel) st.sel_idx[(long)s * KS + nsel_total + rsel] = slot;
+    if (keep) { st.open_idx[pb + out0 + rkeep] = slot; st.keybuf[pb + out0 + rkeep] = key; }
+    nsel_total += tsel;
+    __syncthreads();
+    if (tid == 0) s_out = out0 + tkeep;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    st.open_cnt[s] = s_out;
+    st.sel_cnt[s] = nsel_total;
+    st.free_cnt[s] = s_free;
+    st.cutoff[s] = cutoff;
+    if (nsel_total == 0) st.done[s] = 1;  // frontier exhausted (everything pruned or solved)
+    else { atomicAdd(st.active, 1); s_wbase = atomicAdd((p.C > 1 || st.force_multi) ? st.work_cnt2 : st.work_cnt, nsel_total); }
+  }
+  __syncthreads();
+  if (nsel_total > 0) {
+    const int wb = s_wbase;
+    int2 *wl = (p.C > 1 || st.force_multi) ? st.work2 : st.work;   // plans with several cars go to the CTA-per-node kernel
+    for (int k = tid; k < nsel_total; k += SEL_THREADS) wl[wb + k] = make_int2(s, st.sel_idx[(long)s * KS + k]);
+  }
+}
+
+__global__ void bnb_round_reset_kernel(BnbState st) { if (st.susp_cnt) *st.susp_cnt = 0; *st.active_prev = *st.active; *st.work_cnt = 0; *st.work_next = 0; *st.active = 0; *st.work_cnt2 = 0; *st.work_next2 = 0; }
+
+void launch_bnb_select(const BnbState &st, const DevProb *probs, int round, cudaStream_t s) {
+  bnb_round_reset_kernel<<<1, 1, 0, s>>>(st);
+  bnb_select_kernel<<<st.count, SEL_THREADS, 0, s>>>(st, probs, round);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -144,7 +300,7 @@ __device__ __forceinline__ double edge_violation(const double *et, const double 
 }
 
 // returns number of undecided disjunctions; fills w.imp and br
-__device__ __forceinline__ int scan_node(const WarpCtx &w, Branch &br, Fallback &fb, int &nviol) {
+__device__ __forceinline__ int scan_node(const WarpCtx &w, Branch &br, Fallback &fb) {
   const DevProb &p = *w.p;
   const int lane = w.lane, N = w.N, O = p.O, E = p.E, L = p.L;
   const double tol = 1e-6;
@@ -172,7 +328,7 @@ __device__ __forceinline__ int scan_node(const WarpCtx &w, Branch &br, Fallback 
   // phase 2: region chain (all lanes redundantly; the frozen alternative inherits the region)
   br.kind = 0; br.viol = tol; br.ord = 0x7fffffff; br.i = 0; br.o = 0; br.pt = 0;
   fb.ord = 0x7fffffff; fb.kind = 0; fb.i = 0; fb.o = 0; fb.pt = 0;
-  int und = 0, nv2 = 0, nv3 = 0;   // violated disjunctions: mode chain (all lanes), points (per lane)
+  int und = 0;
   {
     int jp = w.I[p.o_initreg] - 1;
     int root_undec = -1;
@@ -193,7 +349,6 @@ __device__ __forceinline__ int scan_node(const WarpCtx &w, Branch &br, Fallback 
           j = (best == MODE_FROZEN) ? jp : (best >> 2);
           root_undec = (best == MODE_FROZEN && root_undec >= 0) ? root_undec : i;
           branch_offer(br, bv, i * ord_stride, 1, i, 0, 0);
-          nv2 += (bv > tol);
         } else {
           j = jp;  // decided frozen, but its region is only implied: blame the chain root
           branch_offer(br, vfz, i * ord_stride, 1, root_undec, 0, 0);
@@ -232,7 +387,6 @@ __device__ __forceinline__ int scan_node(const WarpCtx &w, Branch &br, Fallback 
           if (v < bv) { bv = v; best = e; }
         }
         if (E > 1) w.imp[p.off_env + i * 5 + pt] = (unsigned char)best;
-        nv3 += (bv > tol);
         if (pt > 0 && !region_decided) branch_offer(mine, bv, i * ord_stride + 1 + pt, 1, mode_blame, 0, 0);
         else branch_offer(mine, bv, i * ord_stride + 1 + pt, 2, i, 0, pt);
       }
@@ -251,7 +405,6 @@ __device__ __forceinline__ int scan_node(const WarpCtx &w, Branch &br, Fallback 
         }
         if (ne == 0) { bv = -1.0; best = 0; }
         w.imp[p.off_obs + (o * N + i) * 5 + pt] = (unsigned char)best;
-        nv3 += (bv > tol);
         if (pt > 0 && !region_decided) branch_offer(mine, bv, i * ord_stride + 6 + o * 5 + pt, 1, mode_blame, 0, 0);
         else branch_offer(mine, bv, i * ord_stride + 6 + o * 5 + pt, 3, i, o, pt);
       }
@@ -271,7 +424,6 @@ __device__ __forceinline__ int scan_node(const WarpCtx &w, Branch &br, Fallback 
     fb_offer(fb, oo, ok, oi, ob, op);
   }
   und += warp_sum_i(und3);
-  nviol = nv2 + warp_sum_i(nv3);
   __syncwarp();
   return und;
 }
@@ -351,12 +503,6 @@ __device__ __forceinline__ void copy_bytes16(unsigned char *dst, const unsigned 
   for (int k = lane; k < nbytes / 16; k += 32) d4[k] = s4[k];
 }
 
-__device__ __forceinline__ void copy_bytes16_cg(unsigned char *dst, const unsigned char *src, int nbytes, int lane) {   // source written by another CTA
-  const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
-  uint4 *d4 = reinterpret_cast<uint4 *>(dst);
-  for (int k = lane; k < nbytes / 16; k += 32) d4[k] = __ldcg(s4 + k);
-}
-
 __device__ __forceinline__ void effective_regions(const WarpCtx &w) {
   const DevProb &p = *w.p;
   if (w.lane == 0) {
@@ -395,10 +541,10 @@ int node_kernel_smem_per_warp(int maxN, int kmax, int ndec_stride) { return node
 // round time is then the latency of its slowest node, and the wider team shortens the row passes.
 template <int NW>
 __global__ void __launch_bounds__(NW * 32, NW == 4 ? NODE_TEAMS_PER_SM : 1) bnb_nodes_kernel(BnbState st, const DevProb *probs, const double *dblob,
-                                                                                            const int *iblob, int smem_per_node, int maxN) {
+                                                                                            const int *iblob, int smem_per_node, int maxN, int round) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double s_red[32];
-  __shared__ SelSmem s_sel;
+  __shared__ int s_wi;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   unsigned char *base = smem_raw;
   const NodeSmem L = node_smem_layout(maxN, st.kmax, st.ndec_stride);
@@ -418,17 +564,16 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? NODE_TEAMS_PER_SM : 1) bnb_
   w.dec = base + L.off_dec;
   w.imp = w.dec + st.ndec_stride;
   unsigned char *alts = w.imp + st.ndec_stride;
-  int cur = -1;   // plan of the node this CTA is working on
+  const int nwork = *reinterpret_cast<volatile int *>(st.work_cnt);
 
   for (;;) {
-    __threadfence();   // children, incumbent, counters of the previous node: visible before its completion is reported
     __syncthreads();   // warp 0 has finished the previous node (scan, children) before its shared memory is reused
-    if (cur >= 0) complete_item(st, probs, cur, s_sel);   // may run the plan's next round boundary (sched.cuh)
-    const int2 item = acquire_item(st, 0, s_sel);
-    cur = item.x;
-    if (cur < 0) break;
+    if (threadIdx.x == 0) s_wi = atomicAdd(st.work_next, 1);
+    __syncthreads();
+    const int wi = s_wi;
+    if (wi >= nwork) break;
+    const int2 item = st.work[wi];
     const int s = item.x, slot = item.y;
-    const int round = ldg2(&st.rd_round[s]);
     const DevProb &p = probs[s];
     const long pb = (long)s * st.cap;
     w.p = &p; w.N = p.N;
@@ -436,7 +581,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? NODE_TEAMS_PER_SM : 1) bnb_
     w.sgmul = 65536 / w.sg + 1; w.NP = team_row_stride(p.N, w.sg); w.kmax = st.kmax;
     double pen = 0.0;
     if (wid == 0) {
-      copy_bytes16_cg(w.dec, st.dec + (pb + slot) * st.ndec_stride, st.ndec_stride, lane);
+      copy_bytes16(w.dec, st.dec + (pb + slot) * st.ndec_stride, st.ndec_stride, lane);
       __syncwarp();
       effective_regions(w);
       // constant cost of SOFT obstacle decisions
@@ -454,16 +599,33 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? NODE_TEAMS_PER_SM : 1) bnb_
     const long long pt0 = clock64();
 #endif
     const double *zw = st.zpool ? st.zpool + (pb + slot) * (long)st.zp_stride : nullptr;
-    if (zw) { const double z0 = ldg2(zw); if (!(z0 == z0)) zw = nullptr; }   // NaN marks a node without parent optimum
-    SuspendIO sio;   // relaxations are not parked: a slow one only delays the next round of its own plan
-    sio.resume = nullptr; sio.pool = nullptr; sio.counter = nullptr; sio.nslots = 0; sio.stride = 0; sio.budget = 0;
+    if (zw && !(zw[0] == zw[0])) zw = nullptr;   // NaN marks a node without parent optimum
+    SuspendIO sio;
+    sio.resume = nullptr; sio.pool = nullptr; sio.counter = st.susp_cnt; sio.nslots = st.susp_slots; sio.stride = st.susp_stride; sio.budget = st.susp_budget;
+    if (st.susp_slot) {
+      const int ss = st.susp_slot[pb + slot];
+      if (ss >= 0) sio.resume = st.susp_pool[(round + 1) & 1] + (long)ss * st.susp_stride;   // parked by the previous round
+      sio.pool = st.susp_pool[round & 1];
+    }
     QpResult r = solve_node_qp(w, e1, e2, zw, st.warm_mu, sio);
+    if (r.status == 3) {
+      // parked: the node stays open (its bound still counts) and continues in the next round
+      if (threadIdx.x == 0) {
+        st.susp_slot[pb + slot] = r.susp_index;
+        const int opos = atomicAdd(&st.open_cnt[s], 1);
+        st.open_idx[pb + opos] = slot;
+        atomicAdd(&st.stat_iters[s], (unsigned long long)r.iters);
+        atomicAdd(&st.stat_rows[s], (unsigned long long)r.rows);
+      }
+      continue;
+    }
+    if (threadIdx.x == 0 && st.susp_slot) st.susp_slot[pb + slot] = -1;
     if (wid != 0) continue;
     // ---- warp 0: bookkeeping, scan of the relaxed optimum, children ----
-    const double nbound = ldg2(&st.bound[pb + slot]);
-    const int2 nmeta = ldg2(&st.meta[pb + slot]);
-    const unsigned long long nuid = ldg2(&st.uid[pb + slot]);
-    const double cutoff = ldg2(&st.cutoff[s]);
+    const double nbound = st.bound[pb + slot];
+    const int2 nmeta = st.meta[pb + slot];
+    const unsigned long long nuid = st.uid[pb + slot];
+    const double cutoff = st.cutoff[s];
 #ifdef MQ_PROF
     if (lane == 0) {
       atomicAdd(&st.prof[r.iters > 100 ? 100 : r.iters], 1ULL);
@@ -500,9 +662,8 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? NODE_TEAMS_PER_SM : 1) bnb_
     if (lane == 0 && !r.converged) atomicAdd(&st.prof[149], 1ULL);
 #endif
 
-    Branch br; Fallback fb; int nviol = 0;
-    const int und = scan_node(w, br, fb, nviol);
-    if (lane == 0 && nmeta.x == 0) st.score[s] = nviol;   // root: disjunctions that the relaxed optimum violates (hardness estimate)
+    Branch br; Fallback fb;
+    const int und = scan_node(w, br, fb);
     if (br.kind == 0 && und > 0 && !r.converged) {
       // The stalled point satisfies an alternative of every disjunction without being the optimum of the relaxation.  The
       // node is still replaced by the completion `imp` alone (branching on the hundreds of disjunctions that a trajectory
@@ -583,7 +744,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? NODE_TEAMS_PER_SM : 1) bnb_
     ok = __shfl_sync(FULL, ok, 0); fbase = __shfl_sync(FULL, fbase, 0); opos = __shfl_sync(FULL, opos, 0);
     if (!ok) continue;
     for (int a = 0; a < nalt; ++a) {
-      const int cs = ldg2(&st.free_stack[pb + fbase + a]);
+      const int cs = st.free_stack[pb + fbase + a];
       unsigned char *dst = st.dec + (pb + cs) * st.ndec_stride;
       copy_bytes16(dst, src, st.ndec_stride, lane);
       if (st.zpool) {   // the child starts its interior-point solve from this node's relaxed optimum
@@ -598,6 +759,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? NODE_TEAMS_PER_SM : 1) bnb_
         st.meta[pb + cs] = make_int2(nmeta.x >= (1 << 20) ? nmeta.x : nmeta.x + 1, (round << 8) | (rank + 1));
         st.uid[pb + cs] = mix64(nuid * 0x9e3779b97f4a7c15ULL + (unsigned long long)(a + 1));
         st.open_idx[pb + opos + a] = cs;
+        if (st.susp_slot) st.susp_slot[pb + cs] = -1;
       }
     }
     __syncwarp();
@@ -617,11 +779,11 @@ int node_kernel_max_ctas(int smem_per_cta, int threads) {
 }
 
 int launch_bnb_nodes(const BnbState &st, const DevProb *probs, const double *dblob, const int *iblob,
-                     int smem_per_node, int warps_per_cta, int ctas, int maxN, cudaStream_t s) {
+                     int smem_per_node, int warps_per_cta, int ctas, int maxN, int round, cudaStream_t s) {
   if (warps_per_cta == NODE_TEAM_WARPS_WIDE)
-    bnb_nodes_kernel<NODE_TEAM_WARPS_WIDE><<<ctas, warps_per_cta * 32, (size_t)smem_per_node, s>>>(st, probs, dblob, iblob, smem_per_node, maxN);
+    bnb_nodes_kernel<NODE_TEAM_WARPS_WIDE><<<ctas, warps_per_cta * 32, (size_t)smem_per_node, s>>>(st, probs, dblob, iblob, smem_per_node, maxN, round);
   else
-    bnb_nodes_kernel<NODE_TEAM_WARPS><<<ctas, warps_per_cta * 32, (size_t)smem_per_node, s>>>(st, probs, dblob, iblob, smem_per_node, maxN);
+    bnb_nodes_kernel<NODE_TEAM_WARPS><<<ctas, warps_per_cta * 32, (size_t)smem_per_node, s>>>(st, probs, dblob, iblob, smem_per_node, maxN, round);
   return (int)cudaGetLastError();
 }
 

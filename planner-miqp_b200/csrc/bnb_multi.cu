@@ -9,7 +9,6 @@
 #include "kernels.cuh"
 #include "bnb_common.cuh"
 #include "bnb_multi_core.cuh"
-#include "sched.cuh"
 
 namespace miqp {
 
@@ -20,39 +19,37 @@ long multi_workspace_bytes(int C, int N, int P, int kmax, int ndec_stride) {
 }
 
 __global__ void __launch_bounds__(MULTI_MAX_THREADS) bnb_nodes_multi_kernel(BnbState st, const DevProb *probs, const double *dblob,
-                                                                            const int *iblob, double *gws, long ws_bytes, int use_smem) {
+                                                                            const int *iblob, double *gws, long ws_bytes, int use_smem, int round) {
   extern __shared__ __align__(16) unsigned char smem_multi[];
   __shared__ MShared sh;
-  __shared__ SelSmem s_sel;
   __shared__ int s_i[4];
   const int tid = threadIdx.x, nthr = blockDim.x;
   double *ws = use_smem ? reinterpret_cast<double *>(smem_multi)
                         : reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(gws) + (size_t)blockIdx.x * ws_bytes);
+  const int nwork = *reinterpret_cast<volatile int *>(st.work_cnt2);
   MCtx k;
   k.D = dblob; k.I = iblob; k.tid = tid; k.nthr = nthr;
-  int cur = -1;   // plan of the node this CTA is working on
 
   for (;;) {
-    __threadfence();   // children, incumbent, counters of the previous node: visible before its completion is reported
+    if (tid == 0) s_i[0] = atomicAdd(st.work_next2, 1);
     __syncthreads();
-    if (cur >= 0) complete_item(st, probs, cur, s_sel);   // may run the plan's next round boundary (sched.cuh)
-    const int2 item = acquire_item(st, 1, s_sel);
-    cur = item.x;
-    if (cur < 0) break;
+    const int wi = s_i[0];
+    __syncthreads();
+    if (wi >= nwork) break;
+    const int2 item = st.work2[wi];
     const int s = item.x, slot = item.y;
-    const int round = ldg2(&st.rd_round[s]);
     const DevProb &p = probs[s];
     const long pb = (long)s * st.cap;
     multi_bind(k, &p, ws, st.ndec_stride);
     {
       const uint4 *s4 = reinterpret_cast<const uint4 *>(st.dec + (pb + slot) * st.ndec_stride);
       uint4 *d4 = reinterpret_cast<uint4 *>(k.dec);
-      for (int e = tid; e < st.ndec_stride / 16; e += nthr) d4[e] = __ldcg(s4 + e);
+      for (int e = tid; e < st.ndec_stride / 16; e += nthr) d4[e] = s4[e];
     }
-    const double nbound = ldg2(&st.bound[pb + slot]);
-    const int2 nmeta = ldg2(&st.meta[pb + slot]);
-    const unsigned long long nuid = ldg2(&st.uid[pb + slot]);
-    const double cutoff = ldg2(&st.cutoff[s]);
+    const double nbound = st.bound[pb + slot];
+    const int2 nmeta = st.meta[pb + slot];
+    const unsigned long long nuid = st.uid[pb + slot];
+    const double cutoff = st.cutoff[s];
     __syncthreads();
 
     const MNodeOut out = m_process_node(k, &sh, nbound, cutoff, p.ndec_pad);
@@ -115,7 +112,7 @@ __global__ void __launch_bounds__(MULTI_MAX_THREADS) bnb_nodes_multi_kernel(BnbS
     if (ok) {
       const unsigned char *src = out.from_imp ? k.imp : k.dec;
       for (int a = 0; a < nalt; ++a) {
-        const int cs = ldg2(&st.free_stack[pb + fbase + a]);
+        const int cs = st.free_stack[pb + fbase + a];
         unsigned char *dst = st.dec + (pb + cs) * st.ndec_stride;
         const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
         uint4 *d4 = reinterpret_cast<uint4 *>(dst);
@@ -146,8 +143,8 @@ int multi_kernel_max_ctas(int smem_bytes, int threads) {
 }
 
 int launch_bnb_nodes_multi(const BnbState &st, const DevProb *probs, const double *dblob, const int *iblob,
-                           double *gws, long ws_bytes, int use_smem, int threads, int ctas, cudaStream_t s) {
-  bnb_nodes_multi_kernel<<<ctas, threads, use_smem ? (size_t)ws_bytes : 0, s>>>(st, probs, dblob, iblob, gws, ws_bytes, use_smem);
+                           double *gws, long ws_bytes, int use_smem, int threads, int ctas, int round, cudaStream_t s) {
+  bnb_nodes_multi_kernel<<<ctas, threads, use_smem ? (size_t)ws_bytes : 0, s>>>(st, probs, dblob, iblob, gws, ws_bytes, use_smem, round);
   return (int)cudaGetLastError();
 }
 

@@ -824,7 +824,7 @@ __device__ __forceinline__ QpResult solve_node_qp(const WarpCtx &w, const PhiEnt
     if (act) {
       if (zwarm) {   // the parent's relaxed optimum (satisfies the dynamics, violates the rows this node adds)
 #pragma unroll
-        for (int t = 0; t < 8; ++t) v.y[t] = __ldcg(zwarm + i * 8 + t);   // written by the CTA that solved the parent
+        for (int t = 0; t < 8; ++t) v.y[t] = zwarm[i * 8 + t];
       } else {
         const double t = i * p.ts;
 #pragma unroll

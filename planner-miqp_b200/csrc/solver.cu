@@ -79,11 +79,9 @@ struct MiqpB200Solver {
   // bnb state buffers
   BnbState st;
   DevBuf<unsigned char> b_dec, b_incdec;
-  DevBuf<double> b_bound, b_ub, b_cutoff, b_pruned, b_incz, b_zpool, b_dbg, b_tlimit;
-  DevBuf<int> b_sched;                  // rd_base, rd_end, rd_next, rd_left, rd_round, rank_of, order [7][count]
-  DevBuf<unsigned> b_ready;             // two bitmaps
-  DevBuf<unsigned long long> b_times;   // t_start, t_done[count]
-  DevBuf<int2> b_meta;
+  DevBuf<double> b_bound, b_ub, b_cutoff, b_pruned, b_incz, b_zpool, b_dbg, b_susp0, b_susp1;
+  DevBuf<int> b_suspslot, b_suspcnt;
+  DevBuf<int2> b_meta, b_work;
   DevBuf<unsigned long long> b_uid, b_keybuf, b_incuid, b_stats, b_prof;
   DevBuf<int> b_open, b_opencnt, b_free, b_freecnt, b_sel, b_selcnt, b_done, b_lock, b_ctrl, b_overflow;
   int smem_per_warp = 0, warps_per_cta = 4, ctas = 0, wide_ctas = 0;
@@ -91,11 +89,7 @@ struct MiqpB200Solver {
   int n_single = 0, n_multi = 0, multi_threads = 64, multi_ctas = 0, multi_use_smem = 1;
   long multi_ws_bytes = 0;
   DevBuf<double> b_multi_ws;
-  cudaStream_t stream2 = nullptr;   // watchdog: writes the stop flag while the persistent kernels run
-  cudaEvent_t evn0 = nullptr, evn1 = nullptr, evm1 = nullptr;
-  int *h_one = nullptr;             // page-locked constant 1
-  std::vector<unsigned long long> h_times;
-  std::vector<int> h_rounds, h_score;
+  DevBuf<int2> b_work2;
   bool uploaded = false, ran = false;
   double last_seconds = 0.0;
   bool timed_out = false;
@@ -216,7 +210,7 @@ void setup_bnb(MiqpB200Solver *s) {
   }
   st.kmax = std::max(kmax1, 1);
   s->single_maxN = std::max(maxN1, 2);
-  int teams = 0; s->ctas = 0; s->multi_ctas = 0;   // node relaxations in flight
+  st.nwarps = 0; s->ctas = 0; s->multi_ctas = 0;
   if (s->n_single > 0) {
     s->smem_per_warp = node_kernel_smem_per_warp(s->single_maxN, st.kmax, st.ndec_stride);   // per node (one team)
     s->warps_per_cta = NODE_TEAM_WARPS;
@@ -228,7 +222,9 @@ void setup_bnb(MiqpB200Solver *s) {
       const int wide_per_sm = node_kernel_max_ctas(s->smem_per_warp, NODE_TEAM_WARPS_WIDE * 32);
       if (wide_per_sm > 0) s->wide_ctas = wide_per_sm * s->num_sms;
     }
-    teams += s->ctas;
+    int fm = 1;
+    if (const char *e = getenv("MIQP_FILL_MULT")) fm = std::max(1, atoi(e));
+    st.nwarps += 2 * s->num_sms * fm;   // the round-width rules are tuned for two teams per SM, whatever the launch uses
   }
   if (s->n_multi > 0) {
     s->multi_threads = (maxCm <= 2) ? 64 : 128;
@@ -240,28 +236,26 @@ void setup_bnb(MiqpB200Solver *s) {
     }
     s->multi_ctas = per_sm * s->num_sms;
     if (!s->multi_use_smem) s->b_multi_ws.ensure((size_t)s->multi_ctas * (size_t)s->multi_ws_bytes / 8 + 16);
-    teams += s->multi_ctas;
+    st.nwarps += s->multi_ctas;
   }
-  // Nodes per plan per round (sched.cuh:round_width): a function of the batch size and of the plan's own round number
-  // only, so that a plan's search does not depend on its neighbours.  Base width: the machine's share of one plan (every
-  // extra node per round is speculative); a plan still searching after `dive_patience` rounds widens by `dive_growth`
-  // nodes per round, up to KS.
+  // nodes per plan per round.  Base count: enough to fill the resident warps once (every extra node
+  // per round is speculative: 37 -> 45 -> 53 nodes per config-2 plan at 1 / 3 / 5); one dive head
+  // per plan until an incumbent exists; up to KS when few plans are still active.
   int K = s->opt.nodes_per_round;
-  if (K <= 0) { K = teams / std::max(count, 1); if (K < 1) K = 1; if (K > 64) K = 64; }
+  if (K <= 0) { K = (st.nwarps + count - 1) / count; if (K < 1) K = 1; if (K > 64) K = 64; }
   st.sel_base = K;
-  st.sel_dive = std::max(1, std::min(8, teams / std::max(count, 1)));   // several dive heads only when teams would idle
-  st.dive_patience = 14; st.inc_patience = 24; st.dive_growth = 8;
+  st.sel_dive = std::max(1, std::min(8, st.nwarps / std::max(count, 1)));   // several dive heads only when warps would idle
+  st.dive_fill = 2;   // A/B on 2048 config-2 plans (profiles/r1i, r1k): one dive head 347 ms / 120 rounds; widened dive 143 ms / 53 rounds
+  if (const char *e = getenv("MIQP_DIVE_FILL")) st.dive_fill = atoi(e);
+  st.wide_div = 0;
+  if (const char *e = getenv("MIQP_WIDE_DIV")) st.wide_div = atoi(e);
+  st.dive_patience = 14; st.dive_growth = 8;   // profiles/r1k: batch 1024 139 -> 80 ms, batch 2048 unchanged (144 ms, 53 -> 38 rounds)
   if (const char *e = getenv("MIQP_DIVE_PATIENCE")) st.dive_patience = atoi(e);
-  if (const char *e = getenv("MIQP_INC_PATIENCE")) st.inc_patience = atoi(e);
   if (const char *e = getenv("MIQP_DIVE_GROWTH")) st.dive_growth = atoi(e);
-  st.teams = teams;
-  st.width_mode = 1;
-  if (const char *e = getenv("MIQP_WIDTH_MODE")) st.width_mode = atoi(e);
-  int kscap = 256;
+  int kscap = 64;
   if (const char *e = getenv("MIQP_KS")) kscap = std::max(1, atoi(e));
-  const int KS = std::max(K, kscap);
+  int KS = std::max(K, std::min(kscap, std::max(1, st.nwarps)));
   st.sel_per_plan = KS;
-  st.max_rounds = s->opt.max_rounds;
   // pool capacity per plan
   int cap = s->opt.pool_capacity;
   // warm start of the children from the parent's relaxed optimum (single-car nodes): N x 8 doubles per node
@@ -286,9 +280,23 @@ void setup_bnb(MiqpB200Solver *s) {
   }
   if (cap < 4 * KS + 64) cap = 4 * KS + 64;
   st.cap = cap;
+  st.work_cap = count * KS;
   const size_t nodes = (size_t)count * cap;
   s->b_dec.ensure(nodes * st.ndec_stride); st.dec = s->b_dec.p;
   s->b_bound.ensure(nodes); st.bound = s->b_bound.p;
+  // parked relaxations (single-car nodes): iteration budget per round, two state pools written alternately
+  st.susp_budget = 8;   // profiles/r1k: cold starts 10 was best (129 -> 86 ms); with the warm start 6 / 7 / 8 / 10 / 12: 88 / 83 / 69 / 77 / 88 ms per 2048 plans
+  if (const char *e = getenv("MIQP_SUSP_BUDGET")) st.susp_budget = atoi(e);
+  st.susp_slot = nullptr; st.susp_cnt = nullptr; st.susp_pool[0] = st.susp_pool[1] = nullptr; st.susp_slots = 0; st.susp_stride = 0;
+  if (st.susp_budget > 0 && s->n_single > 0) {
+    const int np = s->single_maxN + 7;
+    st.susp_stride = (8 + (long)s->single_maxN * 35 + 1 + 2L * (st.kmax + 1) * np + 1) & ~1L;   // SUSP_HDR + V + (s, lambda) records, 16-byte aligned
+    st.susp_slots = std::min(st.work_cap, 4096);
+    s->b_susp0.ensure((size_t)st.susp_slots * st.susp_stride); s->b_susp1.ensure((size_t)st.susp_slots * st.susp_stride);
+    st.susp_pool[0] = s->b_susp0.p; st.susp_pool[1] = s->b_susp1.p;
+    s->b_suspslot.ensure(nodes); st.susp_slot = s->b_suspslot.p;
+    s->b_suspcnt.ensure(1); st.susp_cnt = s->b_suspcnt.p;
+  }
   st.zpool = nullptr;
   if (st.zp_stride > 0) { s->b_zpool.ensure(nodes * (size_t)st.zp_stride); st.zpool = s->b_zpool.p; }
   s->b_meta.ensure(nodes); st.meta = s->b_meta.p;
@@ -311,21 +319,13 @@ void setup_bnb(MiqpB200Solver *s) {
   s->b_stats.ensure((size_t)4 * count);
   st.stat_nodes = s->b_stats.p; st.stat_iters = s->b_stats.p + count; st.stat_rows = s->b_stats.p + 2 * count; st.stat_uncert = s->b_stats.p + 3 * count;
   s->b_overflow.ensure(count); st.overflow = s->b_overflow.p;
+  s->b_work.ensure(st.work_cap); st.work = s->b_work.p;
+  s->b_work2.ensure(st.work_cap); st.work2 = s->b_work2.p;
   s->b_ctrl.ensure(8);
   s->b_prof.ensure(256); st.prof = s->b_prof.p;
   s->b_dbg.ensure((size_t)(1024 + 8) * 512); st.dbg = s->b_dbg.p;
-  st.plans_left = s->b_ctrl.p; st.stop = s->b_ctrl.p + 2;
-  s->b_sched.ensure((size_t)8 * count);
-  st.rd_base = s->b_sched.p; st.rd_end = st.rd_base + count; st.rd_next = st.rd_end + count; st.rd_left = st.rd_next + count;
-  st.rd_round = st.rd_left + count; st.rank_of = st.rd_round + count; st.order = st.rank_of + count; st.score = st.order + count;
-  const size_t nwords = ((size_t)count + 31) / 32;
-  s->b_ready.ensure(2 * 32 * nwords + 64); st.ready[0] = s->b_ready.p; st.ready[1] = s->b_ready.p + 32 * nwords;
-  st.bucket_cnt = reinterpret_cast<int *>(s->b_ready.p + 2 * 32 * nwords);
-  st.prio_mode = 1;
-  if (const char *e = getenv("MIQP_PRIO")) st.prio_mode = atoi(e);
-  s->b_times.ensure((size_t)count + 1); st.t_start = s->b_times.p; st.t_done = s->b_times.p + 1;
-  s->b_tlimit.ensure(count); st.tlimit = s->b_tlimit.p;
-  CK(cudaMemcpyAsync(st.tlimit, s->time_limits.data(), sizeof(double) * count, cudaMemcpyHostToDevice, s->stream));
+  st.work_cnt = s->b_ctrl.p; st.work_next = s->b_ctrl.p + 1; st.active = s->b_ctrl.p + 2; st.err = s->b_ctrl.p + 3;
+  st.work_cnt2 = s->b_ctrl.p + 4; st.work_next2 = s->b_ctrl.p + 5; st.active_prev = s->b_ctrl.p + 6;
   s->d_x.ensure(std::max<long>(pk.total_cols, 1));
   s->d_viol.ensure(count); s->d_obj.ensure(count); s->d_bb.ensure(count);
 }
@@ -363,9 +363,6 @@ int miqp_b200_create(const MiqpB200Options *opt, MiqpB200Solver **out) {
     CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&s->ev0)); CK(cudaEventCreate(&s->ev1));
     CK(cudaEventCreate(&s->evr0)); CK(cudaEventCreate(&s->evr1));
-    CK(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
-    CK(cudaEventCreate(&s->evn0)); CK(cudaEventCreate(&s->evn1)); CK(cudaEventCreate(&s->evm1));
-    CK(cudaHostAlloc(&s->h_one, sizeof(int), cudaHostAllocDefault)); *s->h_one = 1;
   } catch (const std::exception &ex) {
     fprintf(stderr, "miqp_b200: %s\n", ex.what());
     delete s;
@@ -381,15 +378,10 @@ void miqp_b200_destroy(MiqpB200Solver *s) {
   s->d_probs.release(); s->d_dblob.release(); s->d_iblob.release(); s->d_x.release(); s->d_viol.release();
   s->d_obj.release(); s->d_bb.release(); s->d_warm.release(); s->d_haswarm.release();
   s->b_dec.release(); s->b_incdec.release(); s->b_bound.release(); s->b_ub.release(); s->b_cutoff.release();
-  s->b_pruned.release(); s->b_incz.release(); s->b_meta.release();
+  s->b_pruned.release(); s->b_incz.release(); s->b_meta.release(); s->b_work.release();
   s->b_uid.release(); s->b_keybuf.release(); s->b_incuid.release(); s->b_stats.release(); s->b_open.release();
   s->b_opencnt.release(); s->b_free.release(); s->b_freecnt.release(); s->b_sel.release(); s->b_selcnt.release();
-  s->b_zpool.release(); s->b_sched.release(); s->b_ready.release(); s->b_times.release(); s->b_tlimit.release(); s->b_done.release(); s->b_overflow.release(); s->b_lock.release(); s->b_ctrl.release(); s->b_multi_ws.release();
-  if (s->h_one) cudaFreeHost(s->h_one);
-  if (s->evn0) cudaEventDestroy(s->evn0);
-  if (s->evn1) cudaEventDestroy(s->evn1);
-  if (s->evm1) cudaEventDestroy(s->evm1);
-  if (s->stream2) cudaStreamDestroy(s->stream2);
+  s->b_zpool.release(); s->b_susp0.release(); s->b_susp1.release(); s->b_suspslot.release(); s->b_suspcnt.release(); s->b_done.release(); s->b_overflow.release(); s->b_lock.release(); s->b_ctrl.release(); s->b_multi_ws.release(); s->b_work2.release();
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   if (s->evr0) cudaEventDestroy(s->evr0);
@@ -532,66 +524,59 @@ int miqp_b200_batch_run(MiqpB200Solver *s, float *device_ms) {
     const auto t0 = std::chrono::steady_clock::now();
     double tlim = 0.0;
     for (double t : s->time_limits) tlim = std::max(tlim, t);
-    long launches = 0, node_launches = 0;
+    long launches = 0, node_launches = 0, rounds = 0;
+    double node_ms = 0.0;
     CK(cudaMemsetAsync(s->b_prof.p, 0, 256 * sizeof(unsigned long long), s->stream));
+    if (s->st.susp_slot) CK(cudaMemsetAsync(s->st.susp_slot, 0xff, sizeof(int) * (size_t)s->st.count * s->st.cap, s->stream));
     CK(cudaEventRecord(s->ev0, s->stream));
     launch_bnb_init(s->st, s->d_probs.p, s->any_warm ? s->d_warm.p : nullptr, s->any_warm ? s->d_haswarm.p : nullptr, s->stream);
-    launch_bnb_select_all(s->st, s->d_probs.p, s->stream);   // first round of every plan; the later ones start on the device
-    launches += 2;
+    ++launches;
     s->timed_out = false;
-    CK(cudaEventRecord(s->evn0, s->stream));
-    if (s->n_single > 0) {
-      // fewer single-car plans than wide teams fit: latency matters, not throughput
-      const bool wide = s->wide_ctas > 0 && s->n_single * 8 <= s->wide_ctas;
-      int rc = launch_bnb_nodes(s->st, s->d_probs.p, s->d_dblob.p, s->d_iblob.p, s->smem_per_warp,
-                                wide ? NODE_TEAM_WARPS_WIDE : s->warps_per_cta, wide ? s->wide_ctas : s->ctas, s->single_maxN, s->stream);
-      if (rc != 0) throw std::runtime_error(std::string("node kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
-      ++launches; ++node_launches;
+    int ctrl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (;;) {
+      launch_bnb_select(s->st, s->d_probs.p, (int)rounds + 1, s->stream);
+      launches += 2;
+      CK(cudaEventRecord(s->evr0, s->stream));
+      if (s->n_single > 0) {
+        // fewer single-car nodes than wide teams fit (work count of the last round as the estimate): latency matters, not throughput
+        const bool wide = s->wide_ctas > 0 && rounds > 0 && ctrl[0] > 0 && ctrl[0] <= s->wide_ctas;
+        int rc = launch_bnb_nodes(s->st, s->d_probs.p, s->d_dblob.p, s->d_iblob.p, s->smem_per_warp,
+                                  wide ? NODE_TEAM_WARPS_WIDE : s->warps_per_cta, wide ? s->wide_ctas : s->ctas, s->single_maxN,
+                                  (int)rounds + 1, s->stream);
+        if (rc != 0) throw std::runtime_error(std::string("node kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
+        ++launches; ++node_launches;
+      }
+      if (s->n_multi > 0) {
+        int rc = launch_bnb_nodes_multi(s->st, s->d_probs.p, s->d_dblob.p, s->d_iblob.p, s->b_multi_ws.p, s->multi_ws_bytes,
+                                        s->multi_use_smem, s->multi_threads, s->multi_ctas, (int)rounds + 1, s->stream);
+        if (rc != 0) throw std::runtime_error(std::string("multi-car node kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
+        ++launches; ++node_launches;
+      }
+      CK(cudaEventRecord(s->evr1, s->stream));
+      ++rounds;
+      CK(cudaMemcpyAsync(ctrl, s->b_ctrl.p, sizeof ctrl, cudaMemcpyDeviceToHost, s->stream));
+      CK(cudaStreamSynchronize(s->stream));
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, s->evr0, s->evr1));
+      node_ms += ms;
+      if (s->opt.verbose > 1) fprintf(stderr, "[miqp_b200] round %ld: work %d active %d err %d node kernel %.3f ms\n", rounds, ctrl[0], ctrl[2], ctrl[3], ms);
+      if (ctrl[2] == 0) break;  // every plan finished
+      const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      if (el > tlim) { s->timed_out = true; break; }
+      if (s->opt.max_rounds > 0 && rounds >= s->opt.max_rounds) { s->timed_out = true; break; }
     }
-    CK(cudaEventRecord(s->evn1, s->stream));
-    if (s->n_multi > 0) {
-      int rc = launch_bnb_nodes_multi(s->st, s->d_probs.p, s->d_dblob.p, s->d_iblob.p, s->b_multi_ws.p, s->multi_ws_bytes,
-                                      s->multi_use_smem, s->multi_threads, s->multi_ctas, s->stream);
-      if (rc != 0) throw std::runtime_error(std::string("multi-car node kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
-      ++launches; ++node_launches;
-    }
-    CK(cudaEventRecord(s->evm1, s->stream));
     launch_bnb_finish(s->st, s->d_probs.p, s->d_dblob.p, s->d_iblob.p, s->d_x.p, s->d_bb.p, s->stream);
     CK(cudaMemsetAsync(s->d_viol.p, 0, sizeof(double) * count, s->stream));
     launch_evaluate(s->d_probs.p, s->d_dblob.p, s->d_iblob.p, count, s->pk.max_rows, s->d_x.p, s->d_viol.p, s->d_obj.p, s->stream);
     launches += 2;
     CK(cudaGetLastError());
     CK(cudaEventRecord(s->ev1, s->stream));
-    // The time limits are enforced on the device, per plan, at the plan's round boundaries (%globaltimer).  The host
-    // only keeps a watchdog: well past the largest limit it raises the stop flag, which ends every plan at its next
-    // round boundary.
-    {
-      double watchdog = tlim + 2.0 + 0.1 * tlim;
-      if (const char *e = getenv("MIQP_WATCHDOG_SECONDS")) watchdog = atof(e);
-      bool flagged = false;
-      int spins = 0;
-      for (;;) {
-        const cudaError_t q = cudaEventQuery(s->ev1);
-        if (q == cudaSuccess) break;
-        if (q != cudaErrorNotReady) CK(q);
-        const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        if (!flagged && el > watchdog) {
-          CK(cudaMemcpyAsync(s->st.stop, s->h_one, sizeof(int), cudaMemcpyHostToDevice, s->stream2));
-          flagged = true; s->timed_out = true;
-        }
-        if (++spins > 2000) std::this_thread::sleep_for(std::chrono::microseconds(el > 0.05 ? 200 : 20));   // the first milliseconds are polled hot: single-plan latency
-      }
-    }
     CK(cudaStreamSynchronize(s->stream));
-    float node_ms = 0.f, multi_ms = 0.f;
-    CK(cudaEventElapsedTime(&node_ms, s->evn0, s->evn1));
-    CK(cudaEventElapsedTime(&multi_ms, s->evn1, s->evm1));
-    node_ms += multi_ms;
     float total_ms = 0.f;
     CK(cudaEventElapsedTime(&total_ms, s->ev0, s->ev1));
     if (device_ms) *device_ms = total_ms;
     s->last_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    s->stats.launches = launches; s->stats.node_kernel_launches = node_launches; s->stats.rounds = 0;   // rounds: filled by batch_fetch (largest per-plan count)
+    s->stats.launches = launches; s->stats.node_kernel_launches = node_launches; s->stats.rounds = rounds;
     s->stats.node_kernel_ms = node_ms; s->stats.total_ms = total_ms;
     s->ran = true;
   } catch (const std::exception &ex) {
@@ -610,11 +595,6 @@ int miqp_b200_batch_fetch(MiqpB200Solver *s, double *const *x_out, MiqpB200Solve
     const auto tf0 = std::chrono::steady_clock::now();
     s->h_x.resize(ncols); s->h_viol.resize(count); s->h_obj.resize(count); s->h_bb.resize(count); s->h_ub.resize(count);
     s->h_stats.resize((size_t)4 * count); s->h_done.resize(count); s->h_overflow.resize(count);
-    s->h_times.resize((size_t)count + 1); s->h_rounds.resize(count);
-    CK(cudaMemcpyAsync(s->h_times.data(), s->b_times.p, sizeof(unsigned long long) * ((size_t)count + 1), cudaMemcpyDeviceToHost, s->stream));
-    CK(cudaMemcpyAsync(s->h_rounds.data(), s->st.rd_round, sizeof(int) * count, cudaMemcpyDeviceToHost, s->stream));
-    s->h_score.resize(count);
-    CK(cudaMemcpyAsync(s->h_score.data(), s->st.score, sizeof(int) * count, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaMemcpyAsync(s->h_x.data(), s->d_x.p, sizeof(double) * ncols, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaMemcpyAsync(s->h_viol.data(), s->d_viol.p, sizeof(double) * count, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaMemcpyAsync(s->h_obj.data(), s->d_obj.p, sizeof(double) * count, cudaMemcpyDeviceToHost, s->stream));
@@ -624,8 +604,7 @@ int miqp_b200_batch_fetch(MiqpB200Solver *s, double *const *x_out, MiqpB200Solve
     CK(cudaMemcpyAsync(s->h_done.data(), s->st.done, sizeof(int) * count, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaMemcpyAsync(s->h_overflow.data(), s->st.overflow, sizeof(int) * count, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
-    s->stats.d2h_bytes = (long)(sizeof(double) * (ncols + 4 * count) + sizeof(unsigned long long) * (5 * count + 1) + 3 * sizeof(int) * count);
-    s->stats.rounds = 0;
+    s->stats.d2h_bytes = (long)(sizeof(double) * (ncols + 4 * count) + sizeof(unsigned long long) * 4 * count + 2 * sizeof(int) * count);
     long nodes = 0, iters = 0, rows = 0;
     if (x_out) {   // scatter of the solution vectors into the caller's buffers: a few host threads for large batches
       const int nthr = (ncols * (long)sizeof(double) > (8L << 20)) ? 4 : 1;
@@ -649,14 +628,11 @@ int miqp_b200_batch_fetch(MiqpB200Solver *s, double *const *x_out, MiqpB200Solve
       MiqpB200SolveInfo &in = infos[k];
       std::memset(&in, 0, sizeof in);
       const bool have = std::isfinite(s->h_ub[k]);
-      // time from the start of the batch to the plan's last round boundary, on the device clock
-      in.seconds = (s->h_times[1 + k] > s->h_times[0]) ? 1e-9 * (double)(s->h_times[1 + k] - s->h_times[0]) : s->last_seconds;
-      in.nodes = (long)s->h_stats[k]; in.qp_iters = (long)s->h_stats[count + k]; in.rounds = s->h_rounds[k];
-      s->stats.rounds = std::max<long>(s->stats.rounds, s->h_rounds[k]);
+      in.seconds = s->last_seconds;
+      in.nodes = (long)s->h_stats[k]; in.qp_iters = (long)s->h_stats[count + k]; in.rounds = s->stats.rounds;
       in.best_bound = s->h_bb[k];
       in.uncertified = (long)s->h_stats[3 * (size_t)count + k];
       in.pool_exhausted = s->h_overflow[k];
-      in.root_violations = s->h_score[k];
       if (have) {
         // every open or pruned node may lie above the incumbent: report min(bound, incumbent) like CPLEX's best bound
         if (in.best_bound > s->h_ub[k]) in.best_bound = s->h_ub[k];
@@ -668,7 +644,7 @@ int miqp_b200_batch_fetch(MiqpB200Solver *s, double *const *x_out, MiqpB200Solve
         in.proven = (in.gap <= p.gap_tol + 1e-15) ? 1 : 0;
       } else {
         // no incumbent: the reference reports FAILED_TIMEOUT only for the time-limit status
-        in.status = (s->h_done[k] == 3 || s->h_done[k] == 0) ? MIQP_B200_FAILED_TIMEOUT : MIQP_B200_FAILED_NO_SOLUT;
+        in.status = (s->timed_out && !s->h_done[k]) ? MIQP_B200_FAILED_TIMEOUT : MIQP_B200_FAILED_NO_SOLUT;
         in.objective = NAN; in.gap = NAN; in.max_violation = NAN;
       }
     }

@@ -42,9 +42,6 @@ for sh in a.shards:
           f"uncertified {sum(i.uncertified for i in infos)}, pool exhausted {sum(i.pool_exhausted for i in infos)}, "
           f"hardest (seed, nodes): {[(sh * a.batch + int(k), int(n[k])) for k in hard]}", flush=True)
     print("   nodes of the first 32 plans:", [int(v) for v in n[:32]], "rounds:", [int(v) for v in r[:32]])
-    sc = np.array([i.root_violations for i in infos])
-    print("   hardness estimate vs nodes: corr", round(float(np.corrcoef(sc, n)[0, 1]), 3), "score of the 12 hardest:", [int(sc[k]) for k in np.argsort(-n)[:12]],
-          "score percentiles 50/90/99:", np.percentile(sc, [50, 90, 99]).tolist(), "rank of the 12 hardest by score:", [int((sc > sc[k]).sum()) for k in np.argsort(-n)[:12]])
     sec = np.array([i.seconds for i in infos]) * 1e3
     print("   finish time (ms) of the plans at rank 10%..100%:", [round(float(sec[int(q * (a.batch - 1))]), 1) for q in np.linspace(0.1, 1.0, 10)])
     late = np.argsort(-sec)[:8]
