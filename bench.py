@@ -6,7 +6,8 @@ dynamic-occupancy obstacle, N=40 steps, 32 fitted regions, reference default set
 (planner-miqp_b200/scenarios.py:obstacle_scenario, seeds rank*B .. rank*B+B-1).
 
 One step = one pass of the hot path over one batch: every plan is solved to a proven
-relative gap <= 1e-4 by the device branch and bound.
+relative gap <= 1e-4 by the device branch and bound.  The scenario seeds rotate from step to
+step (--shards distinct batches per rank); per-shard step times are reported.
   value : plans/s, whole job, batch already resident in HBM when the timed region starts
           (miqp_b200_batch_run; CUDA events on the solver stream, max over ranks)
   e2e   : plans/s through the C ABI with host buffers (miqp_b200_solve_batch: pack + H2D +
@@ -130,6 +131,13 @@ def cpu_oracle_rate(plans, threads: int):
     return len(plans) / dt, dt, ok
 
 
+def bench_config(B: int) -> dict:
+    """The `config` object of both arms (the reference arm times bounded samples of the same workload)."""
+    return {"workload": WORKLOAD, "plans_per_gpu_per_step": B, "gap": GAP,
+            "seeds": "rank r, step k: shard (r + k * n_gpus) mod shards; shard s = scenario seeds s*B .. s*B+B-1",
+            "cache": "L2 flushed between steps (256 MiB write)"}
+
+
 def run_reference(args):
     """Reference arm: the CPU implementation of the path (the oracle port; CPLEX 12.10 is
     proprietary and absent) on all host cores, same workload/metric."""
@@ -150,14 +158,52 @@ def run_reference(args):
         "impl": "reference", "metric": "MIQP plans/sec at 1e-4 gap", "value": value, "unit": "plans/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "plans_per_step": sample, "gap": GAP},
+        "config": bench_config(args.batch),
         "cpu_baseline": {"value": value, "unit": "plans/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} plans of the workload per step, one oracle solve per host thread"},
+                         "sample": f"every step solves the first {sample} plans of shard 0 of the workload (a bounded sample of the "
+                                   f"{args.batch}-plan batch), one oracle solve per host thread; ms_per_step is the time of the sample"},
         "e2e": {"value": value, "unit": "plans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
     return 0
+
+
+def replan_leg(solver, scenarios: int, cycles: int):
+    """Config 2 as BASELINE.json names it: warm-started replanning.  `scenarios` config-2 scenarios are planned, then
+    re-planned `cycles - 1` times in a receding horizon (state <- step 1 of the plan, obstacle predictions advance by one
+    step, MIP start = previous solution shifted by one step: reference src/miqp_planner.cpp:787-1051,
+    src/cplex_wrapper.cpp:494-639).  Timed: the C-ABI call on host buffers (pack + H2D + solve + D2H) of every cycle."""
+    from planner_miqp_b200.scenarios import obstacle_scenario, advance_obstacle_scenario
+    from planner_miqp_b200.results import shift_warmstart
+    builders = [obstacle_scenario(k) for k in range(scenarios)]
+    plans = [b.build() for b in builders]
+    warm = None
+    t_cold = t_warm = 0.0
+    nodes_cold = nodes_warm = 0
+    proven = 0
+    for c in range(cycles):
+        prep = solver.prepare(plans, gap_tol=GAP, time_limit=600.0, warm=warm)
+        t0 = time.perf_counter()
+        xs, infos = solver.solve_prepared(prep)
+        dt = time.perf_counter() - t0
+        st = solver.run_stats()
+        proven += sum(1 for i in infos if i.status == 0 and i.proven)
+        if c == 0:
+            t_cold, nodes_cold = dt, st["nodes"]
+        else:
+            t_warm += dt; nodes_warm += st["nodes"]
+        if c + 1 < cycles:
+            warm = [shift_warmstart(p, x) if i.status == 0 else None for p, x, i in zip(plans, xs, infos)]
+            builders = [advance_obstacle_scenario(b, p, x) if i.status == 0 else b for b, p, x, i in zip(builders, plans, xs, infos)]
+            plans = [b.build() for b in builders]
+    return {"scenarios": scenarios, "cycles": cycles,
+            "cold_plans_per_s": scenarios / t_cold, "warm_plans_per_s": scenarios * (cycles - 1) / t_warm if cycles > 1 else None,
+            "all_cycles_plans_per_s": scenarios * cycles / (t_cold + t_warm),
+            "nodes_per_plan_cold": nodes_cold / scenarios, "nodes_per_plan_warm": nodes_warm / (scenarios * max(cycles - 1, 1)),
+            "proven_optimal": proven, "plans": scenarios * cycles,
+            "timed": "miqp_b200_solve_batch on host buffers per cycle (pack + H2D + solve + D2H); the shift of the previous "
+                     "solution and the scenario update run on the host between the cycles, untimed"}
 
 
 def main():
@@ -166,10 +212,13 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=2048, help="plans per GPU per step")
+    ap.add_argument("--shards", type=int, default=3, help="distinct scenario shards a rank cycles through (seeds rotate per step)")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--nodes-per-round", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=48)
     ap.add_argument("--latency-plans", type=int, default=16)
+    ap.add_argument("--replan-scenarios", type=int, default=256)
+    ap.add_argument("--replan-cycles", type=int, default=8)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -183,14 +232,18 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the MIQP backend has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL_DEBUG=VERSION prints there)
+        os.environ.setdefault("NCCL_DEBUG", "INFO")     # communicator lines go to stderr (fd 1 is redirected there, see emit())
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     import planner_miqp_b200 as P
     B = args.batch
-    plans = make_plans(rank * B, B)
-    N = plans[0].N
+    S = max(1, min(args.shards, args.steps))
+    shard_ids = [rank + k * world for k in range(S)]          # rank r: shards r, r + world, ...
     solver = P.Solver(device=local_rank, nodes_per_round=args.nodes_per_round)
+    shard_plans = {sid: make_plans(sid * B, B) for sid in shard_ids}
+    prepared = {sid: solver.prepare(shard_plans[sid], gap_tol=GAP, time_limit=600.0) for sid in shard_ids}
+    plans = shard_plans[shard_ids[0]]
+    N = plans[0].N
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
     def barrier():
@@ -200,37 +253,52 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ------------------------------------------------------
-    solver.upload(plans, gap_tol=GAP, time_limit=600.0)
-    for _ in range(args.warmup):
+    # every step solves another shard of the workload: upload (untimed; the batch is resident in HBM when the timed
+    # region of the step starts), L2 flush, then the device solve, timed with CUDA events on the solver stream
+    for k in range(args.warmup):
+        solver.upload_prepared(prepared[shard_ids[k % S]])
         flush.fill_(1)
         solver.run()
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
-    dev_ms, node_ms, launches, stats_acc = [], 0.0, 0, None
+    dev_ms, node_ms, launches = [], 0.0, 0
+    per_shard = {sid: [] for sid in shard_ids}
+    nodes_tot = iters_tot = rows_tot = 0
+    n_ok = 0
+    uncert = pool_ex = 0
+    worst_viol = 0.0
     t_wall0 = time.perf_counter()
-    for _ in range(args.steps):
+    for k in range(args.steps):
+        sid = shard_ids[k % S]
+        solver.upload_prepared(prepared[sid])
         flush.fill_(1)
         torch.cuda.synchronize()
         ms = solver.run()
-        dev_ms.append(ms)
+        dev_ms.append(ms); per_shard[sid].append(ms)
         st = solver.run_stats()
         node_ms += st["node_kernel_ms"]; launches += st["launches"]
+        if k < S:      # results of every distinct shard are fetched and checked once (outside the device-timed region)
+            xs, infos = solver.fetch()
+            stf = solver.run_stats()
+            nodes_tot += stf["nodes"]; iters_tot += stf["qp_iters"]; rows_tot += stf["rows_visited"]
+            n_ok += sum(1 for i in infos if i.status == 0 and i.proven)
+            uncert += sum(i.uncertified for i in infos); pool_ex += sum(i.pool_exhausted for i in infos)
+            worst_viol = max([worst_viol] + [i.max_violation for i in infos if i.status == 0])
+            if sid == shard_ids[0]:
+                infos0, st0 = infos, dict(stf)
+                st0["node_kernel_ms"] = st["node_kernel_ms"]
     barrier()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
-    xs, infos = solver.fetch()
-    st = solver.run_stats()
-    n_ok = sum(1 for i in infos if i.status == 0 and i.proven)
-    worst_viol = max((i.max_violation for i in infos if i.status == 0), default=float("nan"))
     total_ms = sum(dev_ms)
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
-        ok_t = torch.tensor([n_ok], dtype=torch.int64, device="cuda")
+        ok_t = torch.tensor([n_ok, uncert, pool_ex], dtype=torch.int64, device="cuda")
         dist.all_reduce(ok_t)
-        n_ok_all = int(ok_t.item())
+        n_ok_all, uncert, pool_ex = (int(v) for v in ok_t.tolist())
     else:
         n_ok_all = n_ok
     value = world * B * args.steps / (total_ms * 1e-3)
@@ -238,16 +306,15 @@ def main():
     # ---- end to end through the C ABI with host buffers ------------------------------------
     # the caller holds the batch as MiqpB200Problem structs over host arrays and receives every
     # solution vector in host arrays; timed: the C-ABI call (flatten + H2D + device solve + D2H)
-    prepared = solver.prepare(plans, gap_tol=GAP, time_limit=600.0)
-    for _ in range(2):
-        solver.solve_prepared(prepared)
+    for k in range(2):
+        solver.solve_prepared(prepared[shard_ids[k % S]])
     barrier()
     e2e_s = 0.0
-    for _ in range(args.steps):
+    for k in range(args.steps):
         flush.fill_(1)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        xs, infos2 = solver.solve_prepared(prepared)
+        solver.solve_prepared(prepared[shard_ids[k % S]])
         e2e_s += time.perf_counter() - t0
     barrier()
     st2 = solver.run_stats()
@@ -262,7 +329,8 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel (bnb_nodes_kernel) --------------------------------
+    # ---- roofline of the dominant kernel (bnb_nodes_kernel), first shard ----------------------
+    st = st0
     fp64_peak = solver.measure_fp64_peak()
     flops = algorithmic_flops(st, N)
     node_ms_last = st["node_kernel_ms"]
@@ -281,13 +349,21 @@ def main():
         "kernel": "bnb_nodes_kernel", "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
         "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": traffic,
         "peak_source": "DFMA micro-benchmark in this run (MEASURED_PEAKS.json has no FP64 figure)",
-        "kernel_share_of_step": node_ms / total_ms if total_ms else None,
+        "kernel_share_of_step": node_ms / sum(dev_ms) if dev_ms else None,
         "note": "latency-bound FP64 kernel (one CTA of four warps per node relaxation, sequential Riccati recursion on one warp); see DESIGN.md section 4",
         "hbm": {"achieved": hbm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": hbm_gbs / peaks["hbm_gbs"] if peaks["hbm_gbs"] else None, "peak_source": peaks["source"]},
         "nodes_per_s": st["nodes"] / (node_ms_last * 1e-3) if node_ms_last > 0 else None,
         "ipm_iters_per_node": st["qp_iters"] / max(st["nodes"], 1),
     }
+    # assembly kernel: HBM-write bound; bytes = CSR values + column indices + two row bounds + row pointers
+    asm_ms, asm_rows, asm_nnz = solver.assemble_batch(plans, repeats=5)
+    asm_bytes = 12.0 * asm_nnz + 16.0 * asm_rows + 8.0 * (asm_rows + B)
+    asm_gbs = asm_bytes / (asm_ms * 1e-3) / 1e9 if asm_ms > 0 else 0.0
+    roofline["assembly"] = {"kernel": "assemble_rows_kernel", "bound": "hbm", "achieved": asm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                            "frac": asm_gbs / peaks["hbm_gbs"] if peaks["hbm_gbs"] else None, "ms_per_batch": asm_ms,
+                            "plans": B, "rows": asm_rows, "nnz": asm_nnz, "bytes": asm_bytes, "peak_source": peaks["source"],
+                            "assemblies_per_s": B / (asm_ms * 1e-3) if asm_ms > 0 else None}
 
     # ---- single-plan latency ----------------------------------------------------------------
     lat_e2e, lat_dev = [], []
@@ -297,6 +373,9 @@ def main():
         lat_e2e.append(1e3 * (time.perf_counter() - t0))
         lat_dev.append(solver.run_stats()["total_ms"])
 
+    # ---- config 2 as named: warm-started replanning ---------------------------------------------
+    replan = replan_leg(solver, min(args.replan_scenarios, B), args.replan_cycles) if args.replan_scenarios > 0 else None
+
     # ---- CPU baseline (rank 0, bounded sample, one core) --------------------------------------
     sample = min(args.cpu_sample, B)
     cpu_rate, cpu_dt, cpu_ok = cpu_oracle_rate(plans[:sample], 1)
@@ -305,15 +384,17 @@ def main():
     mism = 0
     for k in range(min(8, sample)):
         xo, io = O.solve(plans[k], gap_tol=GAP, time_limit=60.0)
-        if io.status != infos[k].status or (io.status == 0 and abs(io.objective - infos[k].objective) > 1e-4 * max(abs(io.objective), 1e-9)):
+        if io.status != infos0[k].status or (io.status == 0 and abs(io.objective - infos0[k].objective) > 1e-4 * max(abs(io.objective), 1e-9)):
             mism += 1
 
+    shard_ms = {str(sid): {"min": min(v), "mean": sum(v) / len(v), "max": max(v), "steps": len(v)} for sid, v in per_shard.items() if v}
+    cfg = bench_config(B)
+    cfg["nodes_per_plan_per_round"] = args.nodes_per_round or "auto"
     line = {
         "metric": "MIQP plans/sec at 1e-4 gap", "value": value, "unit": "plans/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "plans_per_gpu_per_step": B, "gap": GAP, "cache": "L2 flushed between steps (256 MiB write)",
-                   "nodes_per_plan_per_round": args.nodes_per_round or "auto"},
+        "config": cfg,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "plans/s", "h2d_bytes_per_step": st2["h2d_bytes"], "d2h_bytes_per_step": st2["d2h_bytes"],
                 "ms_per_step": 1e3 * e2e_s / args.steps,
@@ -323,10 +404,12 @@ def main():
         "cpu_baseline": {"value": cpu_rate, "unit": "plans/s", "cores": 1, "kind": "port",
                          "sample": f"first {sample} plans of the batch, oracle/miqp_oracle_bnb.c, {cpu_dt:.1f} s"},
         "latency_p50_ms": {"e2e": statistics.median(lat_e2e), "device": statistics.median(lat_dev), "plans": len(lat_e2e)},
-        "solved": {"proven_optimal": n_ok_all, "plans": world * B, "worst_violation": worst_viol,
-                   "oracle_mismatches_in_sample": mism, "nodes_per_plan": st["nodes"] / B, "rounds": st["rounds"],
-                   "nodes_closed_without_certificate": sum(i.uncertified for i in infos),
-                   "plans_with_exhausted_pool": sum(i.pool_exhausted for i in infos)},
+        "shard_ms_rank0": shard_ms,
+        "replan": replan,
+        "solved": {"proven_optimal": n_ok_all, "plans": world * B * S, "worst_violation": worst_viol,
+                   "oracle_mismatches_in_sample": mism, "nodes_per_plan": nodes_tot / (B * S), "rounds": st["rounds"],
+                   "nodes_closed_without_certificate": uncert, "plans_with_exhausted_pool": pool_ex,
+                   "note": "every distinct shard is fetched and checked once; counts are summed over ranks and shards"},
         "wall_s_timed_region": t_wall,
     }
     emit(line)

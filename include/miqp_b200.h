@@ -132,6 +132,12 @@ int miqp_b200_sizes(MiqpB200Solver *s, const MiqpB200Problem *p, MiqpB200Sizes *
 int miqp_b200_assemble(MiqpB200Solver *s, const MiqpB200Problem *p, long *rowptr, int *cols,
                        double *vals, double *lo, double *hi);
 
+/* Row instantiation of a whole batch into device-resident CSR buffers (kept by the solver), `repeats` timed passes after one
+ * untimed pass: average kernel time in ms (CUDA events), total rows and structural non-zeros.  What opl.generate()
+ * (reference src/cplex_wrapper.cpp:98) does per plan, measured for the roofline of the assembly kernel. */
+int miqp_b200_assemble_batch(MiqpB200Solver *s, const MiqpB200Problem *problems, int count, int repeats,
+                             float *device_ms, long *rows, long *nnz_struct);
+
 /* objective and max violation (rows, bounds, integrality) of a full column vector */
 int miqp_b200_evaluate(MiqpB200Solver *s, const MiqpB200Problem *p, const double *x,
                        double *objective, double *max_violation);

@@ -20,7 +20,7 @@ _ip = C.POINTER(C.c_int)
 DECLARED_SYMBOLS = [
     "miqp_b200_version", "miqp_b200_default_options", "miqp_b200_create", "miqp_b200_destroy",
     "miqp_b200_last_error", "miqp_b200_layout", "miqp_b200_sizes", "miqp_b200_assemble",
-    "miqp_b200_evaluate", "miqp_b200_solve_batch", "miqp_b200_batch_upload", "miqp_b200_batch_run",
+    "miqp_b200_evaluate", "miqp_b200_assemble_batch", "miqp_b200_solve_batch", "miqp_b200_batch_upload", "miqp_b200_batch_run",
     "miqp_b200_batch_fetch", "miqp_b200_run_stats", "miqp_b200_measure_fp64_peak",
     "miqp_b200_debug_profile", "miqp_b200_debug_traces",
 ]
@@ -276,6 +276,16 @@ class Solver:
             vals.ctypes.data_as(_dp), lo.ctypes.data_as(_dp), hi.ctypes.data_as(_dp)), "miqp_b200_assemble")
         return rowptr, cols, vals, lo, hi
 
+    def assemble_batch(self, plans, repeats: int = 5):
+        """Row instantiation of a batch on the device (buffers stay in HBM): (ms per pass, rows, structural nnz)."""
+        keep = []
+        arr = (CProblem * len(plans))(*[to_c(p, keep=keep) for p in plans])
+        ms, rows, nnz = C.c_float(), C.c_long(), C.c_long()
+        f = self._lib.miqp_b200_assemble_batch
+        f.argtypes = [C.c_void_p, C.POINTER(CProblem), C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_long), C.POINTER(C.c_long)]
+        self._check(f(self._h, arr, len(plans), int(repeats), C.byref(ms), C.byref(rows), C.byref(nnz)), "miqp_b200_assemble_batch")
+        return ms.value, rows.value, nnz.value
+
     def evaluate(self, p, x):
         keep = []
         cp = to_c(p, keep=keep)
@@ -339,6 +349,11 @@ class Solver:
         arr, warm_arr, ncols, keep = self._pack(problems, gap_tol, time_limit, warm)
         self._check(self._lib.miqp_b200_batch_upload(self._h, arr, n, warm_arr), "miqp_b200_batch_upload")
         self._batch = (n, ncols)
+
+    def upload_prepared(self, b):
+        """miqp_b200_batch_upload of a batch built by prepare() (no Python-side packing)."""
+        self._check(self._lib.miqp_b200_batch_upload(self._h, b["arr"], b["n"], b["warm"]), "miqp_b200_batch_upload")
+        self._batch = (b["n"], [len(x) for x in b["xs"]])
 
     def run(self) -> float:
         ms = C.c_float()

@@ -674,9 +674,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? NODE_TEAMS_PER_SM : 1) bnb_
     if (br.kind == 0 && und == 0) {
       // every disjunction decided and satisfied: incumbent candidate
       if (lane == 0 && !r.converged) atomic_min_double(&st.pruned_lb[s], obj);   // the leaf's optimum may lie below the stalled point, not below obj
-      if (lane == 0) { while (atomicCAS(&st.lock[s], 0, 1) != 0) {} }
-      __syncwarp();
-      __threadfence();
+      warp_lock(&st.lock[s], lane);
       const double cur = *reinterpret_cast<volatile double *>(&st.ub[s]);
       const unsigned long long cuid = *reinterpret_cast<volatile unsigned long long *>(&st.inc_uid[s]);
       const double inc = fval > obj ? fval : obj;   // value of the stored point (never below the node's bound)
@@ -689,8 +687,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? NODE_TEAMS_PER_SM : 1) bnb_
         __syncwarp();
         if (lane == 0) { st.ub[s] = inc; st.inc_uid[s] = nuid; }
       }
-      __syncwarp();
-      if (lane == 0) { __threadfence(); atomicExch(&st.lock[s], 0); }
+      warp_unlock(&st.lock[s], lane);
       continue;
     }
     // children

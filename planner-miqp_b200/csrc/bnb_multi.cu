@@ -65,10 +65,9 @@ __global__ void __launch_bounds__(MULTI_MAX_THREADS) bnb_nodes_multi_kernel(BnbS
     }
     if (out.what == MN_PRUNED) { if (tid == 0) atomic_min_double(&st.pruned_lb[s], out.obj); continue; }
     if (out.what == MN_INCUMBENT) {
+      if (tid < 32) warp_lock(&st.lock[s], tid);   // (warp 0 waits converged; the other warps wait at the barrier below)
       if (tid == 0) {
         if (!out.converged) atomic_min_double(&st.pruned_lb[s], out.obj);   // the leaf's optimum may lie below the stalled point, not below obj
-        while (atomicCAS(&st.lock[s], 0, 1) != 0) {}
-        __threadfence();
         const double cur = *reinterpret_cast<volatile double *>(&st.ub[s]);
         const unsigned long long cuid = *reinterpret_cast<volatile unsigned long long *>(&st.inc_uid[s]);
         s_i[1] = (out.fval < cur || (out.fval == cur && nuid < cuid)) ? 1 : 0;

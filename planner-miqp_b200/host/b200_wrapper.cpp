@@ -10,6 +10,8 @@
 #include <iomanip>
 #include <limits>
 #include <sstream>
+#include <cstdlib>
+#include <initializer_list>
 
 namespace miqp {
 namespace planner {
@@ -269,6 +271,161 @@ B200Wrapper::B200Wrapper(const B200Wrapper &o)
 B200Wrapper &B200Wrapper::operator=(const B200Wrapper &o) { debugPath_ = o.debugPath_; return *this; }
 B200Wrapper::~B200Wrapper() { if (solver_) miqp_b200_destroy(solver_); }
 
+void B200Wrapper::overrideSolverSettingsDataSource(std::shared_ptr<ModelParameters> o) {
+  if (!o) return;
+  if (!parameters_) parameters_ = std::make_shared<ModelParameters>();
+  parameters_->max_solution_time = o->max_solution_time;
+  parameters_->relative_mip_gap_tolerance = o->relative_mip_gap_tolerance;
+  parameters_->mipdisplay = o->mipdisplay; parameters_->mipemphasis = o->mipemphasis;
+  parameters_->relobjdif = o->relobjdif; parameters_->cutpass = o->cutpass; parameters_->probe = o->probe;
+  parameters_->repairtries = o->repairtries; parameters_->rinsheur = o->rinsheur; parameters_->varsel = o->varsel;
+  parameters_->mircuts = o->mircuts; parameters_->parallelmode = o->parallelmode;
+}
+
+// ---- column names, .mst, .lp -------------------------------------------------------------------------------------------
+std::vector<std::string> ColumnNames(const MiqpB200Layout &l) {
+  std::vector<std::string> n((size_t)l.ncols);
+  auto idx = [](std::initializer_list<int> v) { std::string s; for (int k : v) s += "(" + std::to_string(k + 1) + ")"; return s; };
+  static const char *core[12] = {"u_x", "u_y", "pos_x", "vel_x", "acc_x", "pos_y", "vel_y", "acc_y",
+                                 "pos_x_front_UB", "pos_x_front_LB", "pos_y_front_UB", "pos_y_front_LB"};
+  static const char *nwe[5] = {"notWithinEnvironmentRear", "notWithinEnvironmentFrontUbUb", "notWithinEnvironmentFrontLbUb",
+                               "notWithinEnvironmentFrontUbLb", "notWithinEnvironmentFrontLbLb"};
+  static const char *rcna[5] = {"region_change_not_allowed_x_positive", "region_change_not_allowed_y_positive",
+                                "region_change_not_allowed_x_negative", "region_change_not_allowed_y_negative",
+                                "region_change_not_allowed_combined"};
+  const int C = l.C, N = l.N, R = l.R, O = l.O, L = l.L, E = l.E, K = l.K;
+  for (int b = 0; b < 12; ++b) for (int c = 0; c < C; ++c) for (int i = 0; i < N; ++i) n[((size_t)b * C + c) * N + i] = core[b] + idx({c, i});
+  for (int k = 0; k < 5; ++k) for (int c = 0; c < C; ++c) for (int e = 0; e < E; ++e) for (int i = 0; i < N; ++i)
+    n[l.base_nwe + (((size_t)k * C + c) * E + e) * N + i] = nwe[k] + idx({c, e, i});
+  for (int c = 0; c < C; ++c) for (int i = 0; i < N; ++i) for (int j = 0; j < R; ++j) n[l.base_ar + ((size_t)c * N + i) * R + j] = "active_region" + idx({c, i, j});
+  for (int k = 0; k < 5; ++k) for (int c = 0; c < C; ++c) for (int i = 0; i < N; ++i) n[l.base_rcna + ((size_t)k * C + c) * N + i] = rcna[k] + idx({c, i});
+  for (int c = 0; c < C; ++c) for (int o = 0; o < O; ++o) for (int i = 0; i < N; ++i) {
+    for (int e = 0; e < L; ++e) {
+      n[l.base_dcc + (((size_t)c * O + o) * N + i) * L + e] = "deltacc" + idx({c, o, i, e});
+      for (int f = 0; f < 4; ++f) n[l.base_dcf + ((((size_t)c * O + o) * N + i) * L + e) * 4 + f] = "deltacc_front" + idx({c, o, i, e, f});
+    }
+    n[l.base_so + ((size_t)c * O + o) * N + i] = "slackvarsObstacle" + idx({c, o, i});
+    for (int f = 0; f < 4; ++f) n[l.base_sof + (((size_t)c * O + o) * N + i) * 4 + f] = "slackvarsObstacle_front" + idx({c, o, i, f});
+  }
+  for (int a = 0; a < K; ++a) for (int b = 0; b < K; ++b) for (int i = 0; i < N; ++i) {
+    for (int q = 0; q < 16; ++q) n[l.base_c2c + (((size_t)a * K + b) * N + i) * 16 + q] = "car2car_collision" + idx({a, b, i, q});
+    for (int q = 0; q < 4; ++q) n[l.base_sv + (((size_t)a * K + b) * N + i) * 4 + q] = "slackvars" + idx({a, b, i, q});
+  }
+  return n;
+}
+
+bool WriteMst(const std::string &path, const MiqpB200Layout &l, const std::vector<double> &x) {
+  if ((int)x.size() != l.ncols) return false;
+  std::ofstream f(path);
+  if (!f) return false;
+  const std::vector<std::string> names = ColumnNames(l);
+  f << "<?xml version = \"1.0\" encoding=\"UTF-8\" standalone=\"yes\"?>\n<CPLEXSolutions version=\"1.2\">\n <CPLEXSolution version=\"1.2\">\n"
+    << "  <header\n    problemName=\"cplexmodel\"\n    solutionName=\"m1\"\n    solutionIndex=\"0\"\n    MIPStartEffortLevel=\"0\"\n    writeLevel=\"2\"/>\n  <variables>\n";
+  f << std::setprecision(17);
+  for (int k = 0; k < l.ncols; ++k) f << "   <variable name=\"" << names[k] << "\" index=\"" << k << "\" value=\"" << x[k] << "\"/>\n";
+  f << "  </variables>\n </CPLEXSolution>\n</CPLEXSolutions>\n";
+  return (bool)f;
+}
+
+bool ReadMst(const std::string &path, int ncols, std::vector<double> &x) {
+  std::ifstream f(path);
+  if (!f) return false;
+  std::vector<double> v((size_t)ncols, 0.0);
+  std::string line; int seen = 0;
+  while (std::getline(f, line)) {
+    const size_t pi = line.find("index=\""), pv = line.find("value=\"");
+    if (line.find("<variable") == std::string::npos || pi == std::string::npos || pv == std::string::npos) continue;
+    const int k = std::atoi(line.c_str() + pi + 7);
+    if (k < 0 || k >= ncols) return false;
+    v[k] = std::strtod(line.c_str() + pv + 7, nullptr);
+    ++seen;
+  }
+  if (seen != ncols) return false;
+  x.swap(v);
+  return true;
+}
+
+bool B200Wrapper::writeMIPStarts(const std::string &mstfile) const { return haveLast_ && WriteMst(mstfile, lastLayout_, lastX_); }
+
+bool B200Wrapper::readMIPStarts(const std::string &mstfile) {
+  if (!parameters_) return false;
+  FlatProblem fp; MiqpB200Layout l;
+  try { Flatten(*parameters_, precision_, fp); } catch (const std::exception &) { return false; }
+  if (miqp_b200_layout(&fp.p, &l) != MIQP_B200_OK) return false;
+  std::vector<double> x;
+  if (!ReadMst(mstfile, l.ncols, x)) return false;
+  lastX_.swap(x); lastLayout_ = l; haveLast_ = true;
+  return true;
+}
+
+bool B200Wrapper::exportModel(const std::string &lpfile) {
+  error_.clear();
+  if (!parameters_) { error_ = "resetParameters() has not been called"; return false; }
+  FlatProblem fp; MiqpB200Layout l; MiqpB200Sizes sz;
+  try { Flatten(*parameters_, source_ == DATFILE ? 0 : precision_, fp); } catch (const std::exception &ex) { error_ = ex.what(); return false; }
+  if (miqp_b200_layout(&fp.p, &l) != MIQP_B200_OK) { error_ = "malformed ModelParameters"; return false; }
+  if (!EnsureSolver()) return false;
+  if (miqp_b200_sizes(solver_, &fp.p, &sz) != MIQP_B200_OK) { error_ = miqp_b200_last_error(solver_); return false; }
+  std::vector<long> rowptr((size_t)sz.nrows + 1);
+  std::vector<int> cols((size_t)sz.nnz_struct);
+  std::vector<double> vals((size_t)sz.nnz_struct), lo((size_t)sz.nrows), hi((size_t)sz.nrows);
+  if (miqp_b200_assemble(solver_, &fp.p, rowptr.data(), cols.data(), vals.data(), lo.data(), hi.data()) != MIQP_B200_OK) {
+    error_ = miqp_b200_last_error(solver_); return false;
+  }
+  std::ofstream f(lpfile);
+  if (!f) { error_ = "cannot write " + lpfile; return false; }
+  const std::vector<std::string> names = ColumnNames(l);
+  const MiqpB200Problem &p = fp.p;
+  const int C = l.C, N = l.N;
+  f << std::setprecision(15);
+  f << "\\ENCODING=ISO-8859-1\n\\Problem name: cplexmodel\n\\ rows " << sz.nrows << ", non-zeros " << sz.nnz << ", columns " << l.ncols
+    << " (" << sz.nbin << " binary)\n\nMinimize\n obj:";
+  // objective_function.mod:7-19: sum w (v - ref)^2 + w a^2 + w u^2 + W_obs slackObs^2 + W_slack slackvars^2
+  const double *w[8] = {p.w_jerk_x, p.w_jerk_y, p.w_pos_x, p.w_vel_x, p.w_acc_x, p.w_pos_y, p.w_vel_y, p.w_acc_y};   // per core block 0..7
+  const double *ref[8] = {nullptr, nullptr, p.x_ref, p.vx_ref, nullptr, p.y_ref, p.vy_ref, nullptr};
+  double konst = 0.0; int terms = 0;
+  auto brk = [&]() { if (++terms % 6 == 0) f << "\n     "; };
+  for (int b = 0; b < 8; ++b) for (int c = 0; c < C; ++c) for (int i = 0; i < N; ++i) {
+    const double wt = w[b][c], r = ref[b] ? ref[b][(size_t)c * N + i] : 0.0;
+    konst += wt * r * r;
+    const double lin = -2.0 * wt * r;
+    if (lin != 0.0) { f << (lin < 0 ? " - " : " + ") << std::fabs(lin) << " " << names[((size_t)b * C + c) * N + i]; brk(); }
+  }
+  f << " + " << konst << " objconst\n      + [";
+  terms = 0;
+  auto quad = [&](int col, double q) { if (q != 0.0) { f << " + " << 2.0 * q << " " << names[col] << " ^2"; brk(); } };
+  for (int b = 0; b < 8; ++b) for (int c = 0; c < C; ++c) for (int i = 0; i < N; ++i) quad((b * C + c) * N + i, w[b][c]);
+  for (int k = l.base_so; k < l.base_c2c; ++k) quad(k, p.w_slack_obs);
+  for (int k = l.base_sv; k < l.ncols; ++k) quad(k, p.w_slack);
+  f << " ] / 2\nSubject To\n";
+  for (long r = 0; r < sz.nrows; ++r) {
+    f << " c" << r + 1 << ":";
+    int nt = 0;
+    for (long k = rowptr[r]; k < rowptr[r + 1]; ++k) {
+      if (vals[k] == 0.0) continue;
+      f << (vals[k] < 0 ? " - " : " + ") << std::fabs(vals[k]) << " " << names[cols[k]];
+      if (++nt % 5 == 0) f << "\n     ";
+    }
+    if (nt == 0) f << " 0 objconst";
+    const bool flo = std::isfinite(lo[r]), fhi = std::isfinite(hi[r]);
+    if (flo && fhi && lo[r] == hi[r]) f << " = " << lo[r];
+    else if (fhi && !flo) f << " <= " << hi[r];
+    else if (flo && !fhi) f << " >= " << lo[r];
+    else { error_ = "ranged row in the model"; return false; }
+    f << "\n";
+  }
+  f << "Bounds\n objconst = 1\n";
+  for (int k = 0; k < l.base_nwe; ++k) f << " " << names[k] << " free\n";                         // decision_variables.mod:10-26
+  for (int k = l.base_so; k < l.base_c2c; ++k) f << " 0 <= " << names[k] << " <= 1\n";            // :46-47
+  for (int k = l.base_sv; k < l.ncols; ++k) f << " 0 <= " << names[k] << " <= " << p.maximum_slack << "\n";   // :53
+  f << "Binaries\n";
+  int nb = 0;
+  for (int k = l.base_nwe; k < l.base_so; ++k) { f << " " << names[k]; if (++nb % 6 == 0) f << "\n"; }
+  for (int k = l.base_c2c; k < l.base_sv; ++k) { f << " " << names[k]; if (++nb % 6 == 0) f << "\n"; }
+  f << "\nEnd\n";
+  return (bool)f;
+}
+
 void B200Wrapper::setDevice(int ordinal) {
   if (ordinal == device_) return;
   device_ = ordinal;
@@ -284,7 +441,7 @@ void B200Wrapper::setLastSolutionWarmstart(WarmstartType type) {
   useLastSolution_ = true;
   if (type != LAST_SOLUTION_WARMSTART) useRecedingWarm_ = true;
 }
-void B200Wrapper::deleteLastSolutionWarmstartFile() { haveLast_ = false; }
+void B200Wrapper::deleteLastSolutionWarmstartFile() { haveLast_ = false; std::remove(tmpWarmstartFile_.c_str()); }
 
 bool B200Wrapper::EnsureSolver() {
   if (solver_) return true;
@@ -325,6 +482,11 @@ bool B200Wrapper::Prepare(double timestamp, Prepared &pr) {
     // it is handed over as "undecided" so that the start is a partial assignment the search completes
     Pack(pr.layout, *recedingWarm_, true, pr.warm);
     pr.have_warm = true;
+  } else if (useLastSolution_ && !haveLast_ && ReadMst(tmpWarmstartFile_, pr.layout.ncols, lastX_)) {
+    // the MIP start of a previous solve (possibly by another wrapper or process) comes back from the warm-start file, as
+    // in the reference (src/cplex_wrapper.cpp:128-138)
+    lastLayout_ = pr.layout; haveLast_ = true;
+    pr.warm = lastX_; pr.have_warm = true;
   } else if (useLastSolution_ && haveLast_ && lastLayout_.ncols == pr.layout.ncols && lastLayout_.C == pr.layout.C &&
              lastLayout_.E == pr.layout.E && lastLayout_.O == pr.layout.O) {
     pr.warm = lastX_; pr.have_warm = true;
@@ -333,6 +495,11 @@ bool B200Wrapper::Prepare(double timestamp, Prepared &pr) {
     std::ostringstream fn;
     fn << std::setprecision(15) << debugPath_ << "/" << debugPrefix_ << "parameters_" << timestamp << ".txt";
     if (WriteParametersDat(pr.flat.p, *parameters_, fn.str())) lastParameterFile_ = fn.str();
+    if (debugPrint_) {   // lpexport_<t>.lp next to the parameter dump (src/cplex_wrapper.cpp:151-154)
+      std::ostringstream ln;
+      ln << std::setprecision(15) << debugPath_ << "/" << debugPrefix_ << "lpexport_" << timestamp << ".lp";
+      exportModel(ln.str());
+    }
   }
   return true;
 }
@@ -355,7 +522,13 @@ OptimizationStatus B200Wrapper::Finish(const Prepared &pr, const MiqpB200SolveIn
     props_.proven_gap = info.proven != 0; props_.NrSolutionPool = 1;
     Unpack(pr.layout, x, *results_);
     lastX_.assign(x, x + pr.layout.ncols); lastLayout_ = pr.layout; haveLast_ = true;
+    if (useLastSolution_) WriteMst(tmpWarmstartFile_, lastLayout_, lastX_);   // cplex.writeMIPStarts, src/cplex_wrapper.cpp:206-209
     if (debugPrint_ && !debugPath_.empty()) {
+      if (useLastSolution_) {
+        std::ostringstream wn;
+        wn << std::setprecision(15) << debugPath_ << "/" << debugPrefix_ << "warmstartsolution_" << timestamp << ".mst";
+        WriteMst(wn.str(), lastLayout_, lastX_);
+      }
       std::ostringstream fn;
       fn << std::setprecision(15) << debugPath_ << "/" << debugPrefix_ << "solution_" << timestamp << ".txt";
       std::ofstream f(fn.str());

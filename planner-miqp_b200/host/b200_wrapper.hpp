@@ -42,6 +42,12 @@ void Unpack(const MiqpB200Layout &l, const double *x, RawResults &r);
 void Pack(const MiqpB200Layout &l, const RawResults &r, bool relax_last_step, std::vector<double> &x);
 // OPL .dat dialect of the reference's parameter dumps (readable by oracle/dat_io.py)
 bool WriteParametersDat(const MiqpB200Problem &p, const ModelParameters &m, const std::string &path);
+// names of the columns in decision_variables.mod order, OPL style with 1-based indices: pos_x(1)(2), active_region(1)(2)(32), ...
+std::vector<std::string> ColumnNames(const MiqpB200Layout &l);
+// CPLEX MIP-start file (.mst, XML) of a full column vector / back; what cplex.writeMIPStarts / readMIPStarts exchange
+// (reference src/cplex_wrapper.cpp:128-138, 206-209)
+bool WriteMst(const std::string &path, const MiqpB200Layout &l, const std::vector<double> &x);
+bool ReadMst(const std::string &path, int ncols, std::vector<double> &x);
 
 class B200Wrapper {
  public:
@@ -58,6 +64,9 @@ class B200Wrapper {
   ~B200Wrapper();
 
   void resetParameters(std::shared_ptr<ModelParameters> parameters) { parameters_ = parameters; }
+  // copies only the solver options (time limit, gap, CPLEX emphasis switches) into the bound parameters
+  // (reference src/cplex_wrapper.cpp:893, src/model_input_data_source.cpp:282-296)
+  void overrideSolverSettingsDataSource(std::shared_ptr<ModelParameters> parameters);
   // DATFILE source: the OPL .dat file is read at every callCplex (host/dat_reader.hpp); values are taken as written
   void setParameterDatFileAbsolute(const char *datfile) { datFile_ = datfile; }
   void setParameterDatFileRelative(const char *datfile) { datFile_ = modPath_ + datfile; }
@@ -73,7 +82,13 @@ class B200Wrapper {
   void setDebugOutputFilePath(const std::string &path) { debugPath_ = path; }
   void setDebugOutputFilePrefix(const std::string &prefix) { debugPrefix_ = prefix; }
   std::string getDebugOutputParameterFilePath() const { return lastParameterFile_; }
-  std::string getTmpWarmstartFile() const { return "/tmp/warmstart_debug_res.mst"; }
+  std::string getTmpWarmstartFile() const { return tmpWarmstartFile_; }
+  void setTmpWarmstartFile(const std::string &path) { tmpWarmstartFile_ = path; }   // (the reference's path is fixed: src/cplex_wrapper.hpp:104)
+  // CPLEX LP file of the big-M model of the bound parameters, rows instantiated on the device in OPL order
+  // (cplex.exportModel, reference src/cplex_wrapper.cpp:151-154); exact-zero coefficients are dropped as CPLEX does
+  bool exportModel(const std::string &lpfile);
+  bool writeMIPStarts(const std::string &mstfile) const;   // last solution
+  bool readMIPStarts(const std::string &mstfile);          // becomes the "last solution" MIP start
   void setCollectModelStatistics(bool in) { collectSizes_ = in; }   // rows / non-zeros cost one more device pass
   void setDevice(int ordinal);
 
@@ -106,6 +121,7 @@ class B200Wrapper {
   std::string debugPath_, debugPrefix_, lastParameterFile_, error_;
   ParameterSource source_ = CPPINPUTS;
   std::string modPath_, datFile_;
+  std::string tmpWarmstartFile_ = "/tmp/warmstart_debug_res.mst";
   // MIP starts
   std::shared_ptr<RawResults> recedingWarm_;
   bool useRecedingWarm_ = false, useLastSolution_ = false;

@@ -92,6 +92,31 @@ static void cpu_part() {
   CHECK(same);
   miqp::planner::cplex::Pack(l, r, true, y);
   CHECK(std::isnan(y[l.base_ar + 19 * 16]) && !std::isnan(y[l.base_ar + 18 * 16]) && !std::isnan(y[19]));
+  // column names in OPL style, .mst round trip (cplex.writeMIPStarts / readMIPStarts, src/cplex_wrapper.cpp:128-138, 206-209)
+  const std::vector<std::string> names = miqp::planner::cplex::ColumnNames(l);
+  CHECK((int)names.size() == l.ncols && names[0] == "u_x(1)(1)" && names[2 * 2 * 20 + 20 + 3] == "pos_x(2)(4)");
+  CHECK(names[l.base_ar + (1 * 20 + 2) * 16 + 5] == "active_region(2)(3)(6)" && names[l.base_rcna + 4 * 2 * 20] == "region_change_not_allowed_combined(1)(1)");
+  CHECK(names[l.base_c2c + 17] == "car2car_collision(1)(1)(2)(2)" && names[l.ncols - 1] == "slackvars(1)(1)(20)(4)");
+  const std::string mst = "/tmp/miqp_b200_test_roundtrip.mst";
+  CHECK(miqp::planner::cplex::WriteMst(mst, l, x));
+  std::vector<double> xr;
+  CHECK(miqp::planner::cplex::ReadMst(mst, l.ncols, xr) && xr == x);
+  CHECK(!miqp::planner::cplex::ReadMst(mst, l.ncols - 1, xr) && !miqp::planner::cplex::ReadMst("/nonexistent.mst", l.ncols, xr));
+  {   // a wrapper bound to the same parameters takes the file as its "last solution" MIP start and writes it back unchanged
+    CplexWrapper w2(12);
+    w2.resetParameters(p);
+    CHECK(!w2.writeMIPStarts("/tmp/miqp_b200_test_none.mst"));      // nothing solved or read yet
+    CHECK(w2.readMIPStarts(mst) && w2.getSolutionVector() == x);
+    CHECK(w2.writeMIPStarts("/tmp/miqp_b200_test_roundtrip2.mst") && miqp::planner::cplex::ReadMst("/tmp/miqp_b200_test_roundtrip2.mst", l.ncols, xr) && xr == x);
+    w2.setTmpWarmstartFile("/tmp/miqp_b200_test_tmpws.mst");
+    CHECK(w2.getTmpWarmstartFile() == "/tmp/miqp_b200_test_tmpws.mst");
+    // overrideSolverSettingsDataSource copies the solver options only (src/model_input_data_source.cpp:282-296)
+    auto o = std::make_shared<ModelParameters>();
+    o->max_solution_time = 3.5f; o->relative_mip_gap_tolerance = 0.02f; o->mipemphasis = 1; o->parallelmode = -1; o->NumSteps = 7;
+    const int steps = p->NumSteps;
+    w2.overrideSolverSettingsDataSource(o);
+    CHECK(p->max_solution_time == 3.5f && p->relative_mip_gap_tolerance == 0.02f && p->mipemphasis == 1 && p->parallelmode == -1 && p->NumSteps == steps);
+  }
 }
 
 static std::string g_root;   // repository root (argv[2])
@@ -190,6 +215,27 @@ static void gpu_part() {
     fixture.setParameterDatFileAbsolute((g_root + "/tests/golden/cplexmodel_testcase.dat").c_str());
     CHECK(fixture.callCplex(0.0) == SUCCESS);
     CHECK(std::fabs(fixture.getSolutionProperties().objective - 9.57603) <= 0.1 * 9.57603);   // the file asks for a 10 % gap
+  }
+  // .lp export of the reference fixture (cplex.exportModel, src/cplex_wrapper.cpp:151-154): the device-instantiated rows as a
+  // CPLEX LP file; tests/test_gpu_lp_export.py parses it and compares it with the oracle's rows
+  {
+    CplexWrapper fx("", "cplexmodel.mod", CplexWrapper::DATFILE, 12);
+    fx.setParameterDatFileAbsolute((g_root + "/tests/golden/cplexmodel_testcase.dat").c_str());
+    fx.setLastSolutionWarmstart(LAST_SOLUTION_WARMSTART);
+    fx.setTmpWarmstartFile("/tmp/miqp_b200_hostapi_ws.mst");
+    fx.deleteLastSolutionWarmstartFile();
+    CHECK(fx.callCplex(0.0) == SUCCESS);
+    CHECK(fx.exportModel("/tmp/miqp_b200_hostapi_testcase.lp"));
+    // LAST_SOLUTION_WARMSTART wrote the solution to the warm-start file; a fresh wrapper starts from it
+    std::vector<double> xr;
+    CHECK(miqp::planner::cplex::ReadMst("/tmp/miqp_b200_hostapi_ws.mst", (int)fx.getSolutionVector().size(), xr) && xr == fx.getSolutionVector());
+    CplexWrapper fy("", "cplexmodel.mod", CplexWrapper::DATFILE, 12);
+    fy.setParameterDatFileAbsolute((g_root + "/tests/golden/cplexmodel_testcase.dat").c_str());
+    fy.setLastSolutionWarmstart(LAST_SOLUTION_WARMSTART);
+    fy.setTmpWarmstartFile("/tmp/miqp_b200_hostapi_ws.mst");
+    CHECK(fy.callCplex(1.0) == SUCCESS);
+    CHECK(std::fabs(fy.getSolutionProperties().objective - fx.getSolutionProperties().objective) <= 0.1 * 9.57603);
+    CHECK(fy.getSolutionProperties().NrNodes <= fx.getSolutionProperties().NrNodes);   // the MIP start is an incumbent from the first round on
   }
   // batched dispatch
   MiqpPlanner p1(sc, map), p2(sc, map);
