@@ -444,9 +444,10 @@ int miqp_b200_assemble_batch(MiqpB200Solver *s, const MiqpB200Problem *problems,
     s->uploaded = false;
     upload_packed(s);
     const long rows = s->pk.total_rows, nnz = s->pk.total_nnz;
-    s->a_rowptr.ensure(rows + 1); s->a_cols.ensure(std::max<long>(nnz, 1)); s->a_vals.ensure(std::max<long>(nnz, 1));
-    s->a_lo.ensure(rows + 1); s->a_hi.ensure(rows + 1); s->a_cnt.ensure(1);
-    CK(cudaMemsetAsync(s->a_cnt.p, 0, sizeof(unsigned long long), s->stream));
+    // every plan owns nrows + 1 row pointers and its own non-zero counter (formulation.cu:assemble_rows_kernel)
+    s->a_rowptr.ensure(rows + count); s->a_cols.ensure(std::max<long>(nnz, 1)); s->a_vals.ensure(std::max<long>(nnz, 1));
+    s->a_lo.ensure(rows + count); s->a_hi.ensure(rows + count); s->a_cnt.ensure(count);
+    CK(cudaMemsetAsync(s->a_cnt.p, 0, sizeof(unsigned long long) * count, s->stream));
     const int reps = std::max(repeats, 1);
     // one untimed pass (first touch of the output pages), then `reps` timed ones
     launch_assemble_rows(s->d_probs.p, s->d_dblob.p, s->d_iblob.p, count, s->pk.max_rows, s->a_rowptr.p, s->a_cols.p, s->a_vals.p,
