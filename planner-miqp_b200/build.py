@@ -54,9 +54,35 @@ def build_host(force: bool = False) -> str:
     return CAPI_LIB
 
 
+def pymodule_path() -> str:
+    import sysconfig
+    return os.path.join(HERE, "miqp" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def build_pymodule(force: bool = False) -> str:
+    """pybind11 module `miqp` (host/python_module.cpp): the Python surface of the reference's test module
+    (python/bindings/python_module.cpp) over the host classes, linked against libmiqp_planner_c_api.so."""
+    import pybind11
+    import sysconfig
+    out = pymodule_path()
+    src = os.path.join(HOST, "python_module.cpp")
+    newest = max(os.path.getmtime(CAPI_LIB), max(os.path.getmtime(os.path.join(HOST, f)) for f in os.listdir(HOST) if f.endswith((".hpp", ".cpp"))))
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= newest:
+        return out
+    cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-Wall", "-Wno-comment", "-fvisibility=hidden",
+           "-I" + pybind11.get_include(), "-I" + sysconfig.get_paths()["include"], src, "-o", out,
+           "-L" + HERE, "-lmiqp_planner_c_api", "-lmiqp_b200", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("pybind module build failed")
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_src():
         build_host(force=False)
+        build_pymodule(force=False)
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
@@ -80,6 +106,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         sys.stderr.write("\n".join(log))
     build_host(force=True)
+    build_pymodule(force=True)
     return LIB
 
 

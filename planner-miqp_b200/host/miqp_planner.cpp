@@ -1,5 +1,6 @@
 // miqp_planner.cpp -- see miqp_planner.hpp.  Reference: src/miqp_planner.cpp.
 #include "miqp_planner.hpp"
+#include "convexified_map.hpp"
 
 #include <algorithm>
 #include <array>
@@ -68,6 +69,7 @@ MiqpPlanner::MiqpPlanner(const MiqpPlanner &o)
       egoCarIdx_(o.egoCarIdx_), referenceGenerator_(o.referenceGenerator_),
       referenceGeneratorLongerHorizon_(o.referenceGeneratorLongerHorizon_), mapCells_(o.mapCells_), activeCells_(o.activeCells_),
       mapPolygon_(o.mapPolygon_), obstaclesRoi_(o.obstaclesRoi_), cplexWrapper_(o.cplexWrapper_) {
+  mapRejected_ = o.mapRejected_;
   cplexWrapper_.resetParameters(parameters_);
 }
 
@@ -251,21 +253,26 @@ bool MiqpPlanner::UpdateConvexifiedMap(const MatrixXd &polygon) {
   }
   if (v.rows() < 3) return false;
   if (SignedArea(v) < 0) v = Reversed(v);
-  if (!IsConvexCcw(v)) {
-    std::fprintf(stderr, "[miqp_planner] non-convex map polygons need the Voronoi decomposition of the reference "
-                         "(common/map/convexified_map.cpp), which this build does not contain; pass convex cells instead\n");
+  // convex polygons are one cell; non-convex ones are decomposed into convex cells whose boundary edges are moved inwards
+  // by the collision radius (host/convexified_map.hpp; the reference: ConvexifiedMap::Convert, common/map/convexified_map.cpp:60-128)
+  miqp::common::map::ConvexifiedMap cm(v, settings_.collisionRadius, settings_.simplificationDistanceMap, settings_.bufferReference);
+  if (!cm.Convert()) {
+    // fail closed: without a valid decomposition Plan() refuses to run instead of planning without road boundaries
+    std::fprintf(stderr, "[miqp_planner] the map polygon could not be decomposed into convex cells (degenerate, self-intersecting "
+                         "or narrower than twice the collision radius)\n");
+    mapCells_.clear(); activeCells_.clear(); mapRejected_ = true;
     return false;
   }
-  MatrixXd cell = ShrinkConvexCcw(v, settings_.collisionRadius);
-  if (cell.rows() < 3) return false;
   mapPolygon_ = polygon;
-  mapCells_.assign(1, cell);
+  mapCells_.clear();
+  for (const auto &kv : cm.GetMapConvexPolygons()) mapCells_.push_back(kv.second);
   activeCells_.clear();
+  mapRejected_ = false;
   return true;
 }
 
 void MiqpPlanner::SetConvexEnvironmentCells(const std::vector<MatrixXd> &cells) {
-  mapCells_.clear(); activeCells_.clear();
+  mapCells_.clear(); activeCells_.clear(); mapRejected_ = false;
   for (MatrixXd v : cells) {
     if (v.rows() < 3) continue;
     if (SignedArea(v) < 0) v = Reversed(v);
@@ -291,6 +298,10 @@ void MiqpPlanner::ResetEnvironment() {
 
 // ---------------------------------------------------------------------------------------
 bool MiqpPlanner::BeginPlan(PlanContext &ctx) {
+  if (mapRejected_) {
+    std::fprintf(stderr, "[miqp_planner] the last map update was rejected: not planning without an environment\n");
+    return false;
+  }
   ModelParameters &p = *parameters_;
   ctx = PlanContext();
   if (p.NumCars <= 0) return false;

@@ -119,6 +119,7 @@ class MiqpPlanner {
   ParameterPreparer parameterPreparer_;
   int egoCarIdx_ = 0;
   std::vector<ReferenceTrajectoryGenerator> referenceGenerator_, referenceGeneratorLongerHorizon_;
+  bool mapRejected_ = false;                        // the last UpdateConvexifiedMap failed: Plan() returns false until a map is accepted
   std::vector<MatrixXd> mapCells_;                  // convex, CCW, shrunk by the collision radius; id = index
   std::map<PolygonId, MatrixXd> activeCells_;       // cells touched by the buffered references in the last Plan()
   MatrixXd mapPolygon_;

@@ -60,6 +60,20 @@ static void cpu_part() {
   MiqpPlanner copy(planner);
   CHECK(copy.GetParameters().get() == p.get());
   CHECK(copy.GetCplexWrapper().getRawResults().get() != planner.GetCplexWrapper().getRawResults().get());
+  {   // non-convex road polygons are decomposed (reference: ConvexifiedMap::Convert); a rejected map makes Plan() fail closed
+    MiqpPlanner mp(s);
+    const double lv[12] = {0, 0, 50, 0, 50, 10, 10, 10, 10, 40, 0, 40};
+    MatrixXd L(6, 2);
+    for (int k = 0; k < 6; ++k) { L(k, 0) = lv[2 * k]; L(k, 1) = lv[2 * k + 1]; }
+    CHECK(mp.UpdateConvexifiedMap(L));
+    const double s0[6] = {5, 4, 0, 5, 0.1, 0};
+    mp.AddCar(s0, Line({5, 5, 45, 5}), 5, 1);
+    MatrixXd degenerate(3, 2);
+    for (int k = 0; k < 3; ++k) { degenerate(k, 0) = k; degenerate(k, 1) = 0; }
+    CHECK(!mp.UpdateConvexifiedMap(degenerate));
+    CHECK(!mp.Plan(0.0));                          // no environment, no plan
+    CHECK(mp.UpdateConvexifiedMap(L));              // accepted again
+  }
   // unknown table combination
   Settings bad = DefaultSettings(); bad.nr_regions = 64;
   threw = false;
