@@ -88,8 +88,10 @@ def test_get_raw_reference():
 def test_update_map_convex_and_non_convex():
     p = PC.CMiqpPlanner()
     assert p.update_map([0, 0, 0, 8, 4, 8, 4, 0, 0, 0])          # c_api, update_map (clockwise rectangle, closed)
-    # an L-shaped road needs the Voronoi decomposition of the reference, which is not part of this build
-    assert not p.update_map([0, 0, 10, 0, 10, 4, 4, 4, 4, 10, 0, 10, 0, 0])
+    # an L-shaped road is decomposed into convex cells (host/convexified_map.hpp; reference ConvexifiedMap::Convert)
+    assert p.update_map([0, 0, 10, 0, 10, 4, 4, 4, 4, 10, 0, 10, 0, 0])
+    # a degenerate polygon is rejected
+    assert not p.update_map([0, 0, 1, 0, 2, 0])
     p.close()
 
 
