@@ -156,6 +156,19 @@ int miqp_b200_batch_upload(MiqpB200Solver *s, const MiqpB200Problem *problems, i
 int miqp_b200_batch_run(MiqpB200Solver *s, float *device_ms);
 int miqp_b200_batch_fetch(MiqpB200Solver *s, double *const *x_out, MiqpB200SolveInfo *infos);
 
+/* The same search in steps, for a caller that shards the FRONTIER of the uploaded plans over several GPUs (one process and one
+ * solver per GPU).  Every rank uploads the same batch and runs the same deterministic ramp-up
+ * (frontier_start, frontier_rounds); frontier_split then keeps, in every open list, the nodes whose uid hashes to this rank.
+ * From there on only incumbent OBJECTIVES travel: frontier_get_ub -> min-allreduce (NCCL, 8 bytes per plan) -> frontier_tighten,
+ * every few rounds.  frontier_finish + batch_fetch return this rank's own incumbent (status FAILED_NO_SOLUT if it has none) and
+ * the best bound of its share; the caller takes the minimum of both over the ranks and broadcasts the winner's vector. */
+int miqp_b200_frontier_start(MiqpB200Solver *s);
+int miqp_b200_frontier_rounds(MiqpB200Solver *s, int nrounds, int *unfinished_plans);
+int miqp_b200_frontier_split(MiqpB200Solver *s, int rank, int world);
+int miqp_b200_frontier_get_ub(MiqpB200Solver *s, double *ub /* [count] */);
+int miqp_b200_frontier_tighten(MiqpB200Solver *s, const double *ub /* [count] */);
+int miqp_b200_frontier_finish(MiqpB200Solver *s, float *device_ms);
+
 /* counters of the last run: kernel launches, node relaxations, IPM iterations, seconds
  * spent in the node kernel (CUDA events on the solver stream) */
 typedef struct MiqpB200RunStats {

@@ -23,6 +23,8 @@ DECLARED_SYMBOLS = [
     "miqp_b200_evaluate", "miqp_b200_assemble_batch", "miqp_b200_solve_batch", "miqp_b200_batch_upload", "miqp_b200_batch_run",
     "miqp_b200_batch_fetch", "miqp_b200_run_stats", "miqp_b200_measure_fp64_peak",
     "miqp_b200_debug_profile", "miqp_b200_debug_traces",
+    "miqp_b200_frontier_start", "miqp_b200_frontier_rounds", "miqp_b200_frontier_split", "miqp_b200_frontier_get_ub",
+    "miqp_b200_frontier_tighten", "miqp_b200_frontier_finish",
 ]
 
 
@@ -367,6 +369,38 @@ class Solver:
         infos = (CSolveInfo * n)()
         self._check(self._lib.miqp_b200_batch_fetch(self._h, xptr, infos), "miqp_b200_batch_fetch")
         return xs, [self._info(i) for i in infos]
+
+    # ---- the search in steps (frontier sharding, sharding.py:solve_frontier_sharded) -----------
+    def frontier_start(self):
+        self._lib.miqp_b200_frontier_start.argtypes = [C.c_void_p]
+        self._check(self._lib.miqp_b200_frontier_start(self._h), "miqp_b200_frontier_start")
+
+    def frontier_rounds(self, nrounds: int) -> int:
+        left = C.c_int()
+        self._lib.miqp_b200_frontier_rounds.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        self._check(self._lib.miqp_b200_frontier_rounds(self._h, int(nrounds), C.byref(left)), "miqp_b200_frontier_rounds")
+        return left.value
+
+    def frontier_split(self, rank: int, world: int):
+        self._lib.miqp_b200_frontier_split.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        self._check(self._lib.miqp_b200_frontier_split(self._h, int(rank), int(world)), "miqp_b200_frontier_split")
+
+    def frontier_get_ub(self) -> np.ndarray:
+        ub = np.zeros(self._batch[0])
+        self._lib.miqp_b200_frontier_get_ub.argtypes = [C.c_void_p, _dp]
+        self._check(self._lib.miqp_b200_frontier_get_ub(self._h, ub.ctypes.data_as(_dp)), "miqp_b200_frontier_get_ub")
+        return ub
+
+    def frontier_tighten(self, ub):
+        ub = np.ascontiguousarray(ub, dtype=np.float64)
+        self._lib.miqp_b200_frontier_tighten.argtypes = [C.c_void_p, _dp]
+        self._check(self._lib.miqp_b200_frontier_tighten(self._h, ub.ctypes.data_as(_dp)), "miqp_b200_frontier_tighten")
+
+    def frontier_finish(self) -> float:
+        ms = C.c_float()
+        self._lib.miqp_b200_frontier_finish.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        self._check(self._lib.miqp_b200_frontier_finish(self._h, C.byref(ms)), "miqp_b200_frontier_finish")
+        return ms.value
 
     def run_stats(self) -> dict:
         st = CRunStats()

@@ -785,6 +785,32 @@ int launch_bnb_nodes(const BnbState &st, const DevProb *probs, const double *dbl
 }
 
 // ---------------------------------------------------------------------------------------
+// frontier sharding over several GPUs: every rank runs the same deterministic ramp-up, then keeps
+// the open nodes whose uid hashes to it; only incumbent objectives travel between the ranks afterwards
+// ---------------------------------------------------------------------------------------
+__global__ void bnb_split_kernel(BnbState st, int rank, int world) {
+  const int s = blockIdx.x;
+  if (threadIdx.x != 0 || st.done[s]) return;   // (open lists are a few hundred entries after the ramp-up: one thread per plan)
+  const long pb = (long)s * st.cap;
+  const int n = st.open_cnt[s];
+  int keep = 0, f = st.free_cnt[s];
+  for (int k = 0; k < n; ++k) {
+    const int slot = st.open_idx[pb + k];
+    if ((int)(mix64(st.uid[pb + slot]) % (unsigned long long)world) == rank) st.open_idx[pb + keep++] = slot;
+    else st.free_stack[pb + f++] = slot;      // another rank owns this subtree: its bound is accounted for there
+  }
+  st.open_cnt[s] = keep; st.free_cnt[s] = f;
+}
+void launch_bnb_split(const BnbState &st, int rank, int world, cudaStream_t s) { bnb_split_kernel<<<st.count, 32, 0, s>>>(st, rank, world); }
+
+// incumbent objectives found elsewhere tighten the cutoff of this rank (the trajectory stays with its owner)
+__global__ void bnb_tighten_kernel(BnbState st, const double *ub) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < st.count && ub[s] < st.ub[s]) st.ub[s] = ub[s];
+}
+void launch_bnb_tighten(const BnbState &st, const double *ub, cudaStream_t s) { bnb_tighten_kernel<<<(st.count + 127) / 128, 128, 0, s>>>(st, ub); }
+
+// ---------------------------------------------------------------------------------------
 // finish: best bound, full column vector of the incumbent (collectRawResults,
 // src/cplex_wrapper.cpp:311-448)
 // ---------------------------------------------------------------------------------------
@@ -815,7 +841,7 @@ __global__ void bnb_finish_kernel(BnbState st, const DevProb *probs, const doubl
   double *x = xall + p.x_base;
   for (int k = tid; k < p.ncols; k += nt) x[k] = 0.0;
   __syncthreads();
-  if (!(ub < MQ_INF)) return;
+  if (!(ub < MQ_INF) || st.inc_uid[s] == ~0ULL) return;   // no incumbent of its own (ub may come from another rank: frontier sharding)
   const int C = p.C, N = p.N, R = p.R, E = p.E, O = p.O, L = p.L;
   const unsigned char *dec = st.inc_dec + (long)s * st.ndec_stride;
   double *z = st.inc_z + (long)s * st.zstride;

@@ -92,6 +92,10 @@ struct MiqpB200Solver {
   DevBuf<double> b_multi_ws;
   DevBuf<int2> b_work2;
   bool uploaded = false, ran = false;
+  long fr_rounds = 0; int fr_ctrl0 = 0;                       // rounds run so far / work items of the last round
+  std::chrono::steady_clock::time_point fr_t0;                // start of the current run (time limit)
+  long fr_launches = 0, fr_node_launches = 0; double fr_node_ms = 0.0;
+  DevBuf<double> d_ubx;                                       // incumbent objectives exchanged between ranks (frontier sharding)
   double last_seconds = 0.0;
   bool timed_out = false;
   MiqpB200RunStats stats;
@@ -99,6 +103,7 @@ struct MiqpB200Solver {
   std::vector<double> h_viol, h_obj, h_bb, h_ub;
   std::vector<unsigned long long> h_stats;
   std::vector<int> h_done, h_overflow;
+  std::vector<unsigned long long> h_incuid;
   int single_maxN = 2;
   size_t pool_budget = 0;
 };
@@ -186,6 +191,49 @@ void pack_batch(MiqpB200Solver *s, const MiqpB200Problem *problems, int count) {
       });
     for (std::thread &t : th) t.join();
   }
+}
+
+// Select / solve rounds of the uploaded batch, starting from the current device state: until every plan is finished, the time
+// limit or round cap is hit, or `max_rounds_now` rounds have run (< 0: no such cap).  Returns the number of unfinished plans.
+int run_rounds(MiqpB200Solver *s, long max_rounds_now, double tlim, long &launches, long &node_launches, double &node_ms) {
+  int ctrl[8] = {s->fr_ctrl0, 0, 1, 0, 0, 0, 0, 0};
+  long done_now = 0;
+  for (;;) {
+    if (max_rounds_now >= 0 && done_now >= max_rounds_now) break;
+    const long rounds = s->fr_rounds;
+    launch_bnb_select(s->st, s->d_probs.p, (int)rounds + 1, s->stream);
+    launches += 2;
+    CK(cudaEventRecord(s->evr0, s->stream));
+    if (s->n_single > 0) {
+      // fewer single-car nodes than wide teams fit (work count of the last round as the estimate): latency matters, not throughput
+      const bool wide = s->wide_ctas > 0 && rounds > 0 && ctrl[0] > 0 && ctrl[0] <= s->wide_ctas;
+      int rc = launch_bnb_nodes(s->st, s->d_probs.p, s->d_dblob.p, s->d_iblob.p, s->smem_per_warp,
+                                wide ? NODE_TEAM_WARPS_WIDE : s->warps_per_cta, wide ? s->wide_ctas : s->ctas, s->single_maxN,
+                                (int)rounds + 1, s->stream);
+      if (rc != 0) throw std::runtime_error(std::string("node kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
+      ++launches; ++node_launches;
+    }
+    if (s->n_multi > 0) {
+      int rc = launch_bnb_nodes_multi(s->st, s->d_probs.p, s->d_dblob.p, s->d_iblob.p, s->b_multi_ws.p, s->multi_ws_bytes,
+                                      s->multi_use_smem, s->multi_threads, s->multi_ctas, (int)rounds + 1, s->stream);
+      if (rc != 0) throw std::runtime_error(std::string("multi-car node kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
+      ++launches; ++node_launches;
+    }
+    CK(cudaEventRecord(s->evr1, s->stream));
+    ++s->fr_rounds; ++done_now;
+    CK(cudaMemcpyAsync(ctrl, s->b_ctrl.p, sizeof ctrl, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    s->fr_ctrl0 = ctrl[0];
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, s->evr0, s->evr1));
+    node_ms += ms;
+    if (s->opt.verbose > 1) fprintf(stderr, "[miqp_b200] round %ld: work %d active %d err %d node kernel %.3f ms\n", s->fr_rounds, ctrl[0], ctrl[2], ctrl[3], ms);
+    if (ctrl[2] == 0) break;  // every plan finished
+    const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - s->fr_t0).count();
+    if (el > tlim) { s->timed_out = true; break; }
+    if (s->opt.max_rounds > 0 && s->fr_rounds >= s->opt.max_rounds) { s->timed_out = true; break; }
+  }
+  return ctrl[2];
 }
 
 void setup_bnb(MiqpB200Solver *s) {
@@ -570,39 +618,9 @@ int miqp_b200_batch_run(MiqpB200Solver *s, float *device_ms) {
     launch_bnb_init(s->st, s->d_probs.p, s->any_warm ? s->d_warm.p : nullptr, s->any_warm ? s->d_haswarm.p : nullptr, s->stream);
     ++launches;
     s->timed_out = false;
-    int ctrl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (;;) {
-      launch_bnb_select(s->st, s->d_probs.p, (int)rounds + 1, s->stream);
-      launches += 2;
-      CK(cudaEventRecord(s->evr0, s->stream));
-      if (s->n_single > 0) {
-        // fewer single-car nodes than wide teams fit (work count of the last round as the estimate): latency matters, not throughput
-        const bool wide = s->wide_ctas > 0 && rounds > 0 && ctrl[0] > 0 && ctrl[0] <= s->wide_ctas;
-        int rc = launch_bnb_nodes(s->st, s->d_probs.p, s->d_dblob.p, s->d_iblob.p, s->smem_per_warp,
-                                  wide ? NODE_TEAM_WARPS_WIDE : s->warps_per_cta, wide ? s->wide_ctas : s->ctas, s->single_maxN,
-                                  (int)rounds + 1, s->stream);
-        if (rc != 0) throw std::runtime_error(std::string("node kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
-        ++launches; ++node_launches;
-      }
-      if (s->n_multi > 0) {
-        int rc = launch_bnb_nodes_multi(s->st, s->d_probs.p, s->d_dblob.p, s->d_iblob.p, s->b_multi_ws.p, s->multi_ws_bytes,
-                                        s->multi_use_smem, s->multi_threads, s->multi_ctas, (int)rounds + 1, s->stream);
-        if (rc != 0) throw std::runtime_error(std::string("multi-car node kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
-        ++launches; ++node_launches;
-      }
-      CK(cudaEventRecord(s->evr1, s->stream));
-      ++rounds;
-      CK(cudaMemcpyAsync(ctrl, s->b_ctrl.p, sizeof ctrl, cudaMemcpyDeviceToHost, s->stream));
-      CK(cudaStreamSynchronize(s->stream));
-      float ms = 0.f;
-      CK(cudaEventElapsedTime(&ms, s->evr0, s->evr1));
-      node_ms += ms;
-      if (s->opt.verbose > 1) fprintf(stderr, "[miqp_b200] round %ld: work %d active %d err %d node kernel %.3f ms\n", rounds, ctrl[0], ctrl[2], ctrl[3], ms);
-      if (ctrl[2] == 0) break;  // every plan finished
-      const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-      if (el > tlim) { s->timed_out = true; break; }
-      if (s->opt.max_rounds > 0 && rounds >= s->opt.max_rounds) { s->timed_out = true; break; }
-    }
+    s->fr_rounds = 0; s->fr_ctrl0 = 0; s->fr_t0 = t0;
+    run_rounds(s, -1, tlim, launches, node_launches, node_ms);
+    rounds = s->fr_rounds;
     launch_bnb_finish(s->st, s->d_probs.p, s->d_dblob.p, s->d_iblob.p, s->d_x.p, s->d_bb.p, s->stream);
     CK(cudaMemsetAsync(s->d_viol.p, 0, sizeof(double) * count, s->stream));
     launch_evaluate(s->d_probs.p, s->d_dblob.p, s->d_iblob.p, count, s->pk.max_rows, s->d_x.p, s->d_viol.p, s->d_obj.p, s->stream);
@@ -632,7 +650,8 @@ int miqp_b200_batch_fetch(MiqpB200Solver *s, double *const *x_out, MiqpB200Solve
     const long ncols = s->pk.total_cols;
     const auto tf0 = std::chrono::steady_clock::now();
     s->h_x.resize(ncols); s->h_viol.resize(count); s->h_obj.resize(count); s->h_bb.resize(count); s->h_ub.resize(count);
-    s->h_stats.resize((size_t)4 * count); s->h_done.resize(count); s->h_overflow.resize(count);
+    s->h_stats.resize((size_t)4 * count); s->h_done.resize(count); s->h_overflow.resize(count); s->h_incuid.resize(count);
+    CK(cudaMemcpyAsync(s->h_incuid.data(), s->st.inc_uid, sizeof(unsigned long long) * count, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaMemcpyAsync(s->h_x.data(), s->d_x.p, sizeof(double) * ncols, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaMemcpyAsync(s->h_viol.data(), s->d_viol.p, sizeof(double) * count, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaMemcpyAsync(s->h_obj.data(), s->d_obj.p, sizeof(double) * count, cudaMemcpyDeviceToHost, s->stream));
@@ -665,7 +684,8 @@ int miqp_b200_batch_fetch(MiqpB200Solver *s, double *const *x_out, MiqpB200Solve
       if (!infos) continue;
       MiqpB200SolveInfo &in = infos[k];
       std::memset(&in, 0, sizeof in);
-      const bool have = std::isfinite(s->h_ub[k]);
+      // (a finite bound without an incumbent of its own: the objective came from another rank, frontier sharding)
+      const bool have = std::isfinite(s->h_ub[k]) && s->h_incuid[k] != ~0ULL;
       in.seconds = s->last_seconds;
       in.nodes = (long)s->h_stats[k]; in.qp_iters = (long)s->h_stats[count + k]; in.rounds = s->stats.rounds;
       in.best_bound = s->h_bb[k];
@@ -701,6 +721,90 @@ int miqp_b200_solve_batch(MiqpB200Solver *s, const MiqpB200Problem *problems, in
   rc = miqp_b200_batch_run(s, nullptr);
   if (rc != MIQP_B200_OK) return rc;
   return miqp_b200_batch_fetch(s, x_out, infos);
+}
+
+// ---- frontier sharding: the round loop in steps, driven by the caller (one process per GPU, NCCL between them) -----------------
+int miqp_b200_frontier_start(MiqpB200Solver *s) {
+  if (!s) return MIQP_B200_ERR_ARG;
+  if (!s->uploaded) return fail(s, MIQP_B200_ERR_ARG, "frontier_start without batch_upload");
+  try {
+    CK(cudaSetDevice(s->opt.device));
+    CK(cudaMemsetAsync(s->b_prof.p, 0, 256 * sizeof(unsigned long long), s->stream));
+    if (s->st.susp_slot) CK(cudaMemsetAsync(s->st.susp_slot, 0xff, sizeof(int) * (size_t)s->st.count * s->st.cap, s->stream));
+    CK(cudaEventRecord(s->ev0, s->stream));
+    launch_bnb_init(s->st, s->d_probs.p, s->any_warm ? s->d_warm.p : nullptr, s->any_warm ? s->d_haswarm.p : nullptr, s->stream);
+    s->fr_rounds = 0; s->fr_ctrl0 = 0; s->fr_t0 = std::chrono::steady_clock::now();
+    s->fr_launches = 1; s->fr_node_launches = 0; s->fr_node_ms = 0.0;
+    s->timed_out = false; s->ran = false;
+    CK(cudaStreamSynchronize(s->stream));
+  } catch (const std::exception &ex) { return fail(s, MIQP_B200_ERR_CUDA, ex.what()); }
+  return MIQP_B200_OK;
+}
+
+int miqp_b200_frontier_rounds(MiqpB200Solver *s, int nrounds, int *unfinished) {
+  if (!s || !s->uploaded) return MIQP_B200_ERR_ARG;
+  try {
+    CK(cudaSetDevice(s->opt.device));
+    double tlim = 0.0;
+    for (double t : s->time_limits) tlim = std::max(tlim, t);
+    const int left = run_rounds(s, nrounds, tlim, s->fr_launches, s->fr_node_launches, s->fr_node_ms);
+    if (unfinished) *unfinished = s->timed_out ? 0 : left;
+  } catch (const std::exception &ex) { return fail(s, MIQP_B200_ERR_CUDA, ex.what()); }
+  return MIQP_B200_OK;
+}
+
+int miqp_b200_frontier_split(MiqpB200Solver *s, int rank, int world) {
+  if (!s || !s->uploaded || world < 1 || rank < 0 || rank >= world) return MIQP_B200_ERR_ARG;
+  try {
+    CK(cudaSetDevice(s->opt.device));
+    launch_bnb_split(s->st, rank, world, s->stream);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s->stream));
+    ++s->fr_launches;
+  } catch (const std::exception &ex) { return fail(s, MIQP_B200_ERR_CUDA, ex.what()); }
+  return MIQP_B200_OK;
+}
+
+int miqp_b200_frontier_get_ub(MiqpB200Solver *s, double *ub) {
+  if (!s || !s->uploaded || !ub) return MIQP_B200_ERR_ARG;
+  if (cudaMemcpy(ub, s->st.ub, sizeof(double) * s->st.count, cudaMemcpyDeviceToHost) != cudaSuccess) return fail(s, MIQP_B200_ERR_CUDA, "copy of the incumbent objectives failed");
+  return MIQP_B200_OK;
+}
+
+int miqp_b200_frontier_tighten(MiqpB200Solver *s, const double *ub) {
+  if (!s || !s->uploaded || !ub) return MIQP_B200_ERR_ARG;
+  try {
+    CK(cudaSetDevice(s->opt.device));
+    s->d_ubx.ensure(s->st.count);
+    CK(cudaMemcpyAsync(s->d_ubx.p, ub, sizeof(double) * s->st.count, cudaMemcpyHostToDevice, s->stream));
+    launch_bnb_tighten(s->st, s->d_ubx.p, s->stream);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s->stream));
+    ++s->fr_launches;
+  } catch (const std::exception &ex) { return fail(s, MIQP_B200_ERR_CUDA, ex.what()); }
+  return MIQP_B200_OK;
+}
+
+int miqp_b200_frontier_finish(MiqpB200Solver *s, float *device_ms) {
+  if (!s || !s->uploaded) return MIQP_B200_ERR_ARG;
+  try {
+    CK(cudaSetDevice(s->opt.device));
+    const int count = s->st.count;
+    launch_bnb_finish(s->st, s->d_probs.p, s->d_dblob.p, s->d_iblob.p, s->d_x.p, s->d_bb.p, s->stream);
+    CK(cudaMemsetAsync(s->d_viol.p, 0, sizeof(double) * count, s->stream));
+    launch_evaluate(s->d_probs.p, s->d_dblob.p, s->d_iblob.p, count, s->pk.max_rows, s->d_x.p, s->d_viol.p, s->d_obj.p, s->stream);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(s->ev1, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    float total_ms = 0.f;
+    CK(cudaEventElapsedTime(&total_ms, s->ev0, s->ev1));
+    if (device_ms) *device_ms = total_ms;
+    s->last_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - s->fr_t0).count();
+    s->stats.launches = s->fr_launches + 2; s->stats.node_kernel_launches = s->fr_node_launches; s->stats.rounds = s->fr_rounds;
+    s->stats.node_kernel_ms = s->fr_node_ms; s->stats.total_ms = total_ms;
+    s->ran = true;
+  } catch (const std::exception &ex) { return fail(s, MIQP_B200_ERR_CUDA, ex.what()); }
+  return MIQP_B200_OK;
 }
 
 int miqp_b200_measure_fp64_peak(MiqpB200Solver *s, double *tflops) {
