@@ -206,8 +206,248 @@ def replan_leg(solver, scenarios: int, cycles: int):
                      "solution and the scenario update run on the host between the cycles, untimed"}
 
 
+WORKLOADS = {
+    "config3": "two-agent cooperative merge, joint MIQP with agent_collision_constraints, N=20, R=16 (BASELINE.json configs[2])",
+    "config4": "randomised 1-4 agent scenarios, N=20, R=16, throughput mode (BASELINE.json configs[3])",
+    "config5": "8-agent intersection, joint MIQP, N=40, R=64, B&B frontier sharded over the GPUs (BASELINE.json configs[4])",
+}
+
+
+def gap_histogram(infos, gap_tol):
+    edges = [gap_tol, 1e-3, 1e-2, 1e-1, 1.0]
+    names = [f"<={gap_tol:g}", "<=1e-3", "<=1e-2", "<=1e-1", "<=1", ">1"]
+    h = {n: 0 for n in names}
+    h["no incumbent"] = 0
+    for i in infos:
+        if i.status != 0 or not (i.gap == i.gap):
+            h["no incumbent"] += 1
+            continue
+        for e, n in zip(edges, names):
+            if i.gap <= e + 1e-15:
+                h[n] += 1
+                break
+        else:
+            h[names[-1]] += 1
+    return h
+
+
+def init_dist():
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the MIQP backend has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "INFO")     # communicator lines go to stderr (fd 1 is redirected there, see emit())
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    return rank, local_rank, world
+
+
+def run_multi_agent_batch(args):
+    """configs 3 and 4: batches of joint multi-agent plans (scenario sharding, no data-path collective).  Multi-agent plans
+    with active collision rows are not proven to 1e-4 within the time limit: the line reports how many
+    were, and the gap histogram of the rest."""
+    import torch
+    import torch.distributed as dist
+    rank, local_rank, world = init_dist()
+    import planner_miqp_b200 as P
+    from planner_miqp_b200.scenarios import two_agent_merge, random_scenario
+    B = args.batch if args.batch_given else (256 if args.workload == "config3" else 512)
+    tl = args.time_limit or 2.0
+    mk = (lambda k: two_agent_merge(k).build()) if args.workload == "config3" else (lambda k: random_scenario(k).build())
+    S = max(1, min(args.shards, args.steps))
+    shard_ids = [rank + k * world for k in range(S)]
+    solver = P.Solver(device=local_rank)
+    prepared = {}
+    plans_of = {}
+    for sid in shard_ids:
+        plans_of[sid] = [mk(sid * B + k) for k in range(B)]
+        prepared[sid] = solver.prepare(plans_of[sid], gap_tol=GAP, time_limit=tl)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(max(args.warmup, 1)):
+        solver.upload_prepared(prepared[shard_ids[k % S]]); flush.fill_(1); solver.run()
+    sampler = ClockSampler(local_rank)
+    barrier(); sampler.start()
+    dev_ms, launches, all_infos, nodes = [], 0, [], 0
+    cars = {}
+    for k in range(args.steps):
+        sid = shard_ids[k % S]
+        solver.upload_prepared(prepared[sid]); flush.fill_(1); torch.cuda.synchronize()
+        dev_ms.append(solver.run())
+        launches += solver.run_stats()["launches"]
+        if k < S:
+            xs, infos = solver.fetch()
+            all_infos += infos
+            nodes += solver.run_stats()["nodes"]
+            for p in plans_of[sid]:
+                cars[p.C] = cars.get(p.C, 0) + 1
+    barrier()
+    clocks = sampler.stop()
+    e2e_s = 0.0
+    for k in range(args.steps):
+        flush.fill_(1); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        solver.solve_prepared(prepared[shard_ids[k % S]])
+        e2e_s += time.perf_counter() - t0
+    st2 = solver.run_stats()
+    barrier()
+    total_ms = sum(dev_ms)
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_s = (float(v) for v in t.tolist())
+    if rank == 0:
+        # parity sample against the oracle: the first plans of shard 0 (same gap, same time limit)
+        from oracle import oracle as O
+        sample = min(args.cpu_sample, 16, B)
+        t0 = time.perf_counter()
+        agree = worse = better = 0
+        for k in range(sample):
+            xo, io = O.solve(plans_of[shard_ids[0]][k], gap_tol=GAP, time_limit=tl)
+            i = all_infos[k]
+            if io.status != 0 or i.status != 0:
+                agree += int(io.status != 0 and i.status != 0); worse += int(io.status == 0 and i.status != 0); better += int(io.status != 0 and i.status == 0)
+            elif abs(io.objective - i.objective) <= max(i.gap, io.gap, GAP) * max(abs(io.objective), 1e-9) + 1e-9:
+                agree += 1
+            elif i.objective < io.objective:
+                better += 1
+            else:
+                worse += 1
+        cpu_dt = time.perf_counter() - t0
+        viols = [i.max_violation for i in all_infos if i.status == 0]
+        line = {
+            "metric": "MIQP plans/sec at 1e-4 gap", "value": world * B * args.steps / (total_ms * 1e-3), "unit": "plans/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.workload], "plans_per_gpu_per_step": B, "gap": GAP, "time_limit_s": tl,
+                       "cars_per_plan_rank0": {str(c): n for c, n in sorted(cars.items())},
+                       "cache": "L2 flushed between steps (256 MiB write)",
+                       "note": "a plan counts when it returns (proven, or time-limited with its incumbent and gap): see `solved`"},
+            "clocks": clocks,
+            "e2e": {"value": world * B * args.steps / e2e_s, "unit": "plans/s", "h2d_bytes_per_step": st2["h2d_bytes"],
+                    "d2h_bytes_per_step": st2["d2h_bytes"], "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": launches,
+            "solved": {"plans_rank0": len(all_infos), "proven_optimal": sum(1 for i in all_infos if i.status == 0 and i.proven),
+                       "with_incumbent": sum(1 for i in all_infos if i.status == 0), "gap_histogram": gap_histogram(all_infos, GAP),
+                       "worst_violation": max(viols) if viols else None, "nodes_per_plan": nodes / max(len(all_infos), 1)},
+            "cpu_baseline": {"value": sample / cpu_dt, "unit": "plans/s", "cores": 1, "kind": "port",
+                             "sample": f"first {sample} plans of shard 0, oracle/miqp_oracle_bnb.c, same gap and time limit, {cpu_dt:.1f} s",
+                             "vs_device_on_sample": {"agree_within_gap": agree, "device_better": better, "device_worse": worse}},
+        }
+        emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_frontier_workload(args):
+    """config 5: ONE joint 8-agent plan per step, its branch-and-bound frontier sharded over the ranks
+    (planner-miqp_b200/sharding.py:solve_frontier_sharded); NCCL carries the incumbent-objective min-all-reduce."""
+    import torch
+    import torch.distributed as dist
+    rank, local_rank, world = init_dist()
+    import planner_miqp_b200 as P
+    from planner_miqp_b200.scenarios import intersection
+    from planner_miqp_b200.sharding import solve_frontier_sharded
+    tl = args.time_limit or 5.0
+    n_cars, steps_h = args.cars, args.horizon
+    solver = P.Solver(device=local_rank)
+    S = max(1, min(args.shards, args.steps))
+    plans = [intersection(k, n_cars=n_cars, nr_steps=steps_h).build() for k in range(S)]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(max(args.warmup, 1)):
+        solve_frontier_sharded(solver, [plans[k % S]], gap_tol=GAP, time_limit=min(tl, 1.0), ramp_rounds=args.ramp_rounds, exchange_every=args.exchange_every)
+    sampler = ClockSampler(local_rank)
+    barrier(); sampler.start()
+    t0 = time.perf_counter()
+    results, launches, dev_ms = [], 0, []
+    for k in range(args.steps):
+        st = {}
+        barrier()
+        t1 = time.perf_counter()
+        xs, infos = solve_frontier_sharded(solver, [plans[k % S]], gap_tol=GAP, time_limit=tl, ramp_rounds=args.ramp_rounds,
+                                           exchange_every=args.exchange_every, stats=st)
+        barrier()
+        dt = time.perf_counter() - t1
+        dev_ms.append(st["device_ms"])
+        rs = solver.run_stats()
+        launches += rs["launches"]
+        results.append((infos[0], st, dt, rs))
+    total_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    dev_total = sum(dev_ms)
+    if world > 1:
+        t = torch.tensor([dev_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_total = float(t.item())
+        own = torch.tensor([float(r[1]["nodes_this_rank"]) for r in results], dtype=torch.float64, device="cuda")
+        gathered = [torch.zeros_like(own) for _ in range(world)]
+        dist.all_gather(gathered, own)
+        nodes_by_rank = [[int(v) for v in g.tolist()] for g in gathered]
+    else:
+        nodes_by_rank = [[int(r[1]["nodes_this_rank"]) for r in results]]
+    if rank == 0:
+        from oracle import oracle as O
+        p0 = plans[0]
+        sz = solver.sizes(p0)
+        nodes = sum(r[0].nodes for r in results)
+        line = {
+            "metric": "MIQP plans/sec at 1e-4 gap", "value": args.steps / (dev_total * 1e-3), "unit": "plans/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": dev_total / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOADS["config5"], "cars": n_cars, "N": steps_h, "R": p0.R, "gap": GAP, "time_limit_s": tl,
+                       "model": {"rows": sz.nrows, "cols": sz.ncols, "binaries": sz.nbin},
+                       "ramp_rounds": args.ramp_rounds, "exchange_every_rounds": args.exchange_every,
+                       "collective": "min-all-reduce of the incumbent objective (8 bytes, in place on the solver's device array) every "
+                                     f"{args.exchange_every} rounds + one sum-all-reduce of the unfinished-plan count; winner's vector once at the end",
+                       "note": "every step ends at the time limit unless the gap is proven: plans/s is 1 / time limit then, and the figures "
+                               "that scale with the GPUs are node relaxations per second and the gap reached (see `solved`)"},
+            "clocks": clocks,
+            "e2e": {"value": args.steps / total_s, "unit": "plans/s", "h2d_bytes_per_step": results[-1][3]["h2d_bytes"],
+                    "d2h_bytes_per_step": results[-1][3]["d2h_bytes"], "ms_per_step": 1e3 * total_s / args.steps},
+            "gpu_launches": launches,
+            "solved": {"per_step": [{"status": r[0].status, "objective": r[0].objective, "best_bound": r[0].best_bound, "gap": r[0].gap,
+                                     "proven": bool(r[0].proven), "nodes_all_ranks": r[0].nodes, "max_violation": r[0].max_violation,
+                                     "exchanges": r[1]["exchanges"], "split": r[1]["split"], "wall_s": r[2]} for r in results],
+                       "node_relaxations_per_s": nodes / (dev_total * 1e-3), "nodes_by_rank_per_step": nodes_by_rank},
+        }
+        if args.cpu_sample > 0:
+            t1 = time.perf_counter()
+            xo, io = O.solve(p0, gap_tol=GAP, time_limit=tl)
+            cdt = time.perf_counter() - t1
+            line["cpu_baseline"] = {"value": 1.0 / cdt, "unit": "plans/s", "cores": 1, "kind": "port",
+                                    "sample": f"plan 0 with the same time limit, oracle/miqp_oracle_bnb.c, {cdt:.1f} s: status {io.status}, "
+                                              f"objective {io.objective}, gap {io.gap}"}
+        emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4", "config5"])
+    ap.add_argument("--time-limit", type=float, default=None, help="per-plan time limit of configs 3-5 (s)")
+    ap.add_argument("--cars", type=int, default=8, help="config5: agents")
+    ap.add_argument("--horizon", type=int, default=40, help="config5: steps")
+    ap.add_argument("--ramp-rounds", type=int, default=8)
+    ap.add_argument("--exchange-every", type=int, default=4)
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
@@ -220,8 +460,13 @@ def main():
     ap.add_argument("--replan-scenarios", type=int, default=256)
     ap.add_argument("--replan-cycles", type=int, default=8)
     args = ap.parse_args()
+    args.batch_given = any(a == "--batch" or a.startswith("--batch=") for a in sys.argv[1:])
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload in ("config3", "config4"):
+        return run_multi_agent_batch(args)
+    if args.workload == "config5":
+        return run_frontier_workload(args)
 
     import torch
     import torch.distributed as dist

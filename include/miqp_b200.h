@@ -159,12 +159,17 @@ int miqp_b200_batch_fetch(MiqpB200Solver *s, double *const *x_out, MiqpB200Solve
 /* The same search in steps, for a caller that shards the FRONTIER of the uploaded plans over several GPUs (one process and one
  * solver per GPU).  Every rank uploads the same batch and runs the same deterministic ramp-up
  * (frontier_start, frontier_rounds); frontier_split then keeps, in every open list, the nodes whose uid hashes to this rank.
- * From there on only incumbent OBJECTIVES travel: frontier_get_ub -> min-allreduce (NCCL, 8 bytes per plan) -> frontier_tighten,
- * every few rounds.  frontier_finish + batch_fetch return this rank's own incumbent (status FAILED_NO_SOLUT if it has none) and
+ * From there on only incumbent OBJECTIVES travel: frontier_get_ub -> min-allreduce (8 bytes per plan) -> frontier_tighten
+ * (host buffers), or an in-place NCCL min-allreduce on frontier_ub_device, every few rounds.  frontier_finish + batch_fetch return this rank's own incumbent (status FAILED_NO_SOLUT if it has none) and
  * the best bound of its share; the caller takes the minimum of both over the ranks and broadcasts the winner's vector. */
 int miqp_b200_frontier_start(MiqpB200Solver *s);
 int miqp_b200_frontier_rounds(MiqpB200Solver *s, int nrounds, int *unfinished_plans);
 int miqp_b200_frontier_split(MiqpB200Solver *s, int rank, int world);
+/* fingerprint of every open list (call on every rank after the ramp-up and compare: the split is only sound if the ramp-ups agree) */
+int miqp_b200_frontier_fingerprint(MiqpB200Solver *s, long long *fp /* [count] */);
+/* device address of the incumbent objectives ([count] doubles on the solver's GPU): an in-place ncclAllReduce(min) on it is the
+ * whole exchange (no host copy); synchronise the communication stream before the next frontier_rounds */
+int miqp_b200_frontier_ub_device(MiqpB200Solver *s, void **ub, int *count);
 int miqp_b200_frontier_get_ub(MiqpB200Solver *s, double *ub /* [count] */);
 int miqp_b200_frontier_tighten(MiqpB200Solver *s, const double *ub /* [count] */);
 int miqp_b200_frontier_finish(MiqpB200Solver *s, float *device_ms);

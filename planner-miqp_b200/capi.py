@@ -24,7 +24,7 @@ DECLARED_SYMBOLS = [
     "miqp_b200_batch_fetch", "miqp_b200_run_stats", "miqp_b200_measure_fp64_peak",
     "miqp_b200_debug_profile", "miqp_b200_debug_traces",
     "miqp_b200_frontier_start", "miqp_b200_frontier_rounds", "miqp_b200_frontier_split", "miqp_b200_frontier_get_ub",
-    "miqp_b200_frontier_tighten", "miqp_b200_frontier_finish",
+    "miqp_b200_frontier_tighten", "miqp_b200_frontier_finish", "miqp_b200_frontier_fingerprint", "miqp_b200_frontier_ub_device",
 ]
 
 
@@ -390,6 +390,19 @@ class Solver:
         self._lib.miqp_b200_frontier_get_ub.argtypes = [C.c_void_p, _dp]
         self._check(self._lib.miqp_b200_frontier_get_ub(self._h, ub.ctypes.data_as(_dp)), "miqp_b200_frontier_get_ub")
         return ub
+
+    def frontier_fingerprint(self) -> np.ndarray:
+        fp = np.zeros(self._batch[0], dtype=np.int64)
+        self._lib.miqp_b200_frontier_fingerprint.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
+        self._check(self._lib.miqp_b200_frontier_fingerprint(self._h, fp.ctypes.data_as(C.POINTER(C.c_longlong))), "miqp_b200_frontier_fingerprint")
+        return fp
+
+    def frontier_ub_device(self):
+        """(device address, count) of the incumbent objectives, for an in-place NCCL min-allreduce"""
+        ptr, n = C.c_void_p(), C.c_int()
+        self._lib.miqp_b200_frontier_ub_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
+        self._check(self._lib.miqp_b200_frontier_ub_device(self._h, C.byref(ptr), C.byref(n)), "miqp_b200_frontier_ub_device")
+        return ptr.value, n.value
 
     def frontier_tighten(self, ub):
         ub = np.ascontiguousarray(ub, dtype=np.float64)

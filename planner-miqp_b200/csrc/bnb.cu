@@ -796,11 +796,25 @@ __global__ void bnb_split_kernel(BnbState st, int rank, int world) {
   int keep = 0, f = st.free_cnt[s];
   for (int k = 0; k < n; ++k) {
     const int slot = st.open_idx[pb + k];
-    if ((int)(mix64(st.uid[pb + slot]) % (unsigned long long)world) == rank) st.open_idx[pb + keep++] = slot;
-    else st.free_stack[pb + f++] = slot;      // another rank owns this subtree: its bound is accounted for there
+    if ((int)(mix64(st.uid[pb + slot]) % (unsigned long long)world) == rank) { st.open_idx[pb + keep++] = slot; continue; }
+    // another rank owns this subtree: its bound is accounted for there.  A parked relaxation is still listed in sel_idx of the
+    // last round: the next select releases its slot once the parking mark is gone (no second push here).
+    if (st.susp_slot && st.susp_slot[pb + slot] >= 0) st.susp_slot[pb + slot] = -1;
+    else st.free_stack[pb + f++] = slot;
   }
   st.open_cnt[s] = keep; st.free_cnt[s] = f;
 }
+// fingerprint of every open list (count and sum of the node uids): the ranks compare them before the split -- the ramp-up has
+// to be identical everywhere, otherwise a subtree could be dropped by every rank
+__global__ void bnb_fingerprint_kernel(BnbState st, unsigned long long *out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= st.count) return;
+  const long pb = (long)s * st.cap;
+  unsigned long long h = (unsigned long long)st.open_cnt[s] * 0x9e3779b97f4a7c15ULL;
+  if (!st.done[s]) for (int k = 0; k < st.open_cnt[s]; ++k) h += mix64(st.uid[pb + st.open_idx[pb + k]]);
+  out[s] = h >> 1;   // (fits a signed 64-bit integer: the caller reduces it with min / max)
+}
+void launch_bnb_fingerprint(const BnbState &st, unsigned long long *out, cudaStream_t s) { bnb_fingerprint_kernel<<<(st.count + 127) / 128, 128, 0, s>>>(st, out); }
 void launch_bnb_split(const BnbState &st, int rank, int world, cudaStream_t s) { bnb_split_kernel<<<st.count, 32, 0, s>>>(st, rank, world); }
 
 // incumbent objectives found elsewhere tighten the cutoff of this rank (the trajectory stays with its owner)

@@ -78,6 +78,7 @@ constexpr int NODE_TEAM_WARPS_WIDE = 8;   // the same for rounds with fewer node
 int launch_bnb_nodes(const BnbState &st, const DevProb *probs, const double *dblob, const int *iblob,
                      int smem_per_warp, int warps_per_cta, int ctas, int maxN, int round, cudaStream_t s);
 void launch_bnb_split(const BnbState &st, int rank, int world, cudaStream_t s);       // frontier sharding: keep this rank's share of every open list
+void launch_bnb_fingerprint(const BnbState &st, unsigned long long *out, cudaStream_t s);   // frontier sharding: open-list fingerprint per plan
 void launch_bnb_tighten(const BnbState &st, const double *ub, cudaStream_t s);      // st.ub = min(st.ub, ub): incumbents of other ranks
 void launch_bnb_finish(const BnbState &st, const DevProb *probs, const double *dblob, const int *iblob,
                        double *xall, double *best_bound, cudaStream_t s);

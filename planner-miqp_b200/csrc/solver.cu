@@ -95,6 +95,7 @@ struct MiqpB200Solver {
   long fr_rounds = 0; int fr_ctrl0 = 0;                       // rounds run so far / work items of the last round
   std::chrono::steady_clock::time_point fr_t0;                // start of the current run (time limit)
   long fr_launches = 0, fr_node_launches = 0; double fr_node_ms = 0.0;
+  DevBuf<unsigned long long> d_fp;                            // open-list fingerprints (frontier sharding)
   DevBuf<double> d_ubx;                                       // incumbent objectives exchanged between ranks (frontier sharding)
   double last_seconds = 0.0;
   bool timed_out = false;
@@ -762,6 +763,27 @@ int miqp_b200_frontier_split(MiqpB200Solver *s, int rank, int world) {
     CK(cudaStreamSynchronize(s->stream));
     ++s->fr_launches;
   } catch (const std::exception &ex) { return fail(s, MIQP_B200_ERR_CUDA, ex.what()); }
+  return MIQP_B200_OK;
+}
+
+int miqp_b200_frontier_fingerprint(MiqpB200Solver *s, long long *fp) {
+  if (!s || !s->uploaded || !fp) return MIQP_B200_ERR_ARG;
+  try {
+    CK(cudaSetDevice(s->opt.device));
+    s->d_fp.ensure(s->st.count);
+    launch_bnb_fingerprint(s->st, s->d_fp.p, s->stream);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(fp, s->d_fp.p, sizeof(long long) * s->st.count, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    ++s->fr_launches;
+  } catch (const std::exception &ex) { return fail(s, MIQP_B200_ERR_CUDA, ex.what()); }
+  return MIQP_B200_OK;
+}
+
+int miqp_b200_frontier_ub_device(MiqpB200Solver *s, void **ub, int *count) {
+  if (!s || !s->uploaded || !ub) return MIQP_B200_ERR_ARG;
+  *ub = s->st.ub;
+  if (count) *count = s->st.count;
   return MIQP_B200_OK;
 }
 

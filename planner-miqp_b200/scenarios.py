@@ -120,6 +120,33 @@ def random_scenario(seed: int, nr_regions=16, nr_steps=20, max_agents=4):
     return b
 
 
+def intersection(seed: int = 0, n_cars: int = 8, nr_steps=40, nr_regions=64, ts=0.25, time_limit=10.0, gap=1e-4):
+    """config 5: n-agent four-way intersection (joint MIQP over all cars, lambda = 0.5), N=40, 64 fitted regions
+    (fitting table 64/10/1: max_velocity_fitting 10 m/s, minimum_region_change_speed 1 m/s).
+
+    Two lanes per road (3.5 m wide, right-hand traffic), cars approach from the four arms -- car c comes from arm c mod 4, the
+    second car of an arm follows 12-16 m behind the first -- 14-24 m before the conflict area at 4-6 m/s, every reference goes
+    straight across.  The crossing order of every conflicting pair is what the collision-side binaries of
+    agent_collision_constraints.mod:38-73 decide; the frontier of that search is what is sharded over the GPUs."""
+    rng = np.random.default_rng(9000 + seed)
+    s = settings_for(nr_regions, nr_steps, ts, gap, time_limit)
+    s.max_velocity_fitting, s.minimum_region_change_speed = 10.0, 1.0
+    b = PlanBuilder(s)
+    lane = 1.75
+    arms = [((-1.0, 0.0), (0.0, -lane)), ((0.0, -1.0), (lane, 0.0)), ((1.0, 0.0), (0.0, lane)), ((0.0, 1.0), (-lane, 0.0))]
+    for c in range(n_cars):
+        (ax, ay), (ox, oy) = arms[c % 4]                  # arm direction (from the centre outwards), lane offset
+        d = rng.uniform(14.0, 24.0) + (c // 4) * rng.uniform(12.0, 16.0)
+        v = rng.uniform(4.0, 6.0)
+        px, py = ax * d + ox, ay * d + oy
+        hx, hy = -ax, -ay                                  # heading: towards the centre
+        ref = [[px - hx * 5.0, py - hy * 5.0], [px + hx * 160.0, py + hy * 160.0]]
+        b.add_car([px, v * hx, 0.0, py, v * hy, 0.0], ref, 5.0, 1.0)
+    r = s.collisionRadius
+    b.add_environment_polygon([[-120 + r, -120 + r], [120 - r, -120 + r], [120 - r, 120 - r], [-120 + r, 120 - r]])
+    return b
+
+
 def advance_obstacle_scenario(builder: PlanBuilder, plan, x) -> PlanBuilder:
     """Next planning cycle of a config-2 scenario (receding horizon): the car state becomes step 1 of
     the solution x, every obstacle prediction moves one step ahead (the last pose is extrapolated
