@@ -153,6 +153,12 @@ int miqp_b200_solve_batch(MiqpB200Solver *s, const MiqpB200Problem *problems, in
  * restarts from the uploaded state) / fetch (D2H). */
 int miqp_b200_batch_upload(MiqpB200Solver *s, const MiqpB200Problem *problems, int count,
                            const double *const *warm);
+/* Receding-horizon replanning (reference: MiqpPlanner::CalculateWarmstart + EnvironmentWarmstart, src/miqp_planner.cpp:787-1115, and the MIP
+ * start of src/cplex_wrapper.cpp:494-639): upload of the NEXT planning cycle of the plans of the previous batch on this solver
+ * (same count, order and shapes; states, references and obstacle predictions advanced by the caller).  The MIP start of every plan
+ * is its previous incumbent shifted by one step ON THE DEVICE -- no solution vector crosses PCIe; plans without a previous
+ * incumbent, or whose shape changed, start cold. */
+int miqp_b200_batch_upload_replan(MiqpB200Solver *s, const MiqpB200Problem *problems, int count);
 int miqp_b200_batch_run(MiqpB200Solver *s, float *device_ms);
 int miqp_b200_batch_fetch(MiqpB200Solver *s, double *const *x_out, MiqpB200SolveInfo *infos);
 
@@ -184,6 +190,12 @@ typedef struct MiqpB200RunStats {
   double pack_ms, upload_ms, fetch_ms; /* host wall time of the last batch: flatten into the staging blobs / H2D + tables + pool setup / D2H + scatter */
 } MiqpB200RunStats;
 int miqp_b200_run_stats(const MiqpB200Solver *s, MiqpB200RunStats *out);
+
+/* Device time over several runs, also of several solvers of one GPU that work concurrently (two batches in flight on two
+ * streams): mark(s, 0) / mark(s, 1) record CUDA events on the solver's stream; elapsed(from, to) = time from mark 0 of `from` to
+ * mark 1 of `to` (both events are waited for). */
+int miqp_b200_mark(MiqpB200Solver *s, int which);
+int miqp_b200_elapsed(MiqpB200Solver *from, MiqpB200Solver *to, float *ms);
 
 /* Diagnostics of the last run (zeros unless the library was built with -DMQ_PROF):
  * out256[0..100] histogram of interior-point iterations per node relaxation, out256[128..131]

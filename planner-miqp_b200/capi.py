@@ -24,7 +24,7 @@ DECLARED_SYMBOLS = [
     "miqp_b200_batch_fetch", "miqp_b200_run_stats", "miqp_b200_measure_fp64_peak",
     "miqp_b200_debug_profile", "miqp_b200_debug_traces",
     "miqp_b200_frontier_start", "miqp_b200_frontier_rounds", "miqp_b200_frontier_split", "miqp_b200_frontier_get_ub",
-    "miqp_b200_frontier_tighten", "miqp_b200_frontier_finish", "miqp_b200_frontier_fingerprint", "miqp_b200_frontier_ub_device",
+    "miqp_b200_frontier_tighten", "miqp_b200_frontier_finish", "miqp_b200_frontier_fingerprint", "miqp_b200_frontier_ub_device", "miqp_b200_batch_upload_replan", "miqp_b200_mark", "miqp_b200_elapsed",
 ]
 
 
@@ -352,6 +352,19 @@ class Solver:
         self._check(self._lib.miqp_b200_batch_upload(self._h, arr, n, warm_arr), "miqp_b200_batch_upload")
         self._batch = (n, ncols)
 
+    def upload_replan(self, problems, gap_tol=None, time_limit=None):
+        """next planning cycle of the previous batch: MIP starts = previous incumbents shifted by one step on the device"""
+        n = len(problems)
+        arr, _, ncols, keep = self._pack(problems, gap_tol, time_limit, None)
+        self._lib.miqp_b200_batch_upload_replan.argtypes = [C.c_void_p, C.POINTER(CProblem), C.c_int]
+        self._check(self._lib.miqp_b200_batch_upload_replan(self._h, arr, n), "miqp_b200_batch_upload_replan")
+        self._batch = (n, ncols)
+
+    def upload_replan_prepared(self, b):
+        self._lib.miqp_b200_batch_upload_replan.argtypes = [C.c_void_p, C.POINTER(CProblem), C.c_int]
+        self._check(self._lib.miqp_b200_batch_upload_replan(self._h, b["arr"], b["n"]), "miqp_b200_batch_upload_replan")
+        self._batch = (b["n"], [len(x) for x in b["xs"]])
+
     def upload_prepared(self, b):
         """miqp_b200_batch_upload of a batch built by prepare() (no Python-side packing)."""
         self._check(self._lib.miqp_b200_batch_upload(self._h, b["arr"], b["n"], b["warm"]), "miqp_b200_batch_upload")
@@ -415,6 +428,17 @@ class Solver:
         self._check(self._lib.miqp_b200_frontier_finish(self._h, C.byref(ms)), "miqp_b200_frontier_finish")
         return ms.value
 
+    def mark(self, which: int):
+        self._lib.miqp_b200_mark.argtypes = [C.c_void_p, C.c_int]
+        self._check(self._lib.miqp_b200_mark(self._h, int(which)), "miqp_b200_mark")
+
+    def elapsed_to(self, other: "Solver") -> float:
+        """device milliseconds from this solver's mark 0 to `other`'s mark 1"""
+        ms = C.c_float()
+        self._lib.miqp_b200_elapsed.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+        self._check(self._lib.miqp_b200_elapsed(self._h, other._h, C.byref(ms)), "miqp_b200_elapsed")
+        return ms.value
+
     def run_stats(self) -> dict:
         st = CRunStats()
         self._check(self._lib.miqp_b200_run_stats(self._h, C.byref(st)), "miqp_b200_run_stats")
@@ -440,3 +464,74 @@ class Solver:
     def _info(i: CSolveInfo) -> SolveInfo:
         return SolveInfo(i.status, bool(i.proven), i.objective, i.best_bound, i.gap, i.seconds,
                          i.max_violation, i.nodes, i.qp_iters, i.rounds, i.uncertified, i.pool_exhausted)
+
+
+class PipelinedSolver:
+    """`depth` solver instances on ONE GPU (own stream, node pool and pinned staging buffers each), fed alternately by host
+    threads, so that consecutive batches overlap:
+
+    * the tail rounds of batch k (a few hard plans, a near-empty GPU, latency-bound) run next to the head rounds of batch
+      k + 1 (every plan active, throughput-bound) -- the persistent node kernels of the two streams share the SMs as their
+      CTAs come and go;
+    * packing + H2D of batch k + 1 and D2H + scatter of batch k - 1 run on the host threads of the idle instance while the
+      other one searches.
+
+    The C calls release the GIL.  Results are identical to Solver.solve_batch (each batch is still one deterministic search).
+    """
+
+    def __init__(self, device: int = 0, depth: int = 2, **kw):
+        self.solvers = [Solver(device=device, **kw) for _ in range(max(1, depth))]
+
+    def close(self):
+        for s in self.solvers:
+            s.close()
+
+    def prepare(self, problems, gap_tol=None, time_limit=None, warm=None):
+        return self.solvers[0].prepare(problems, gap_tol, time_limit, warm)
+
+    def _run_threads(self, jobs, fn, stagger_s):
+        import threading
+        import time as _t
+        depth = len(self.solvers)
+        out, err = [None] * len(jobs), []
+
+        def worker(w):
+            try:
+                if stagger_s > 0 and w > 0:
+                    _t.sleep(stagger_s * w / depth)
+                for k in range(w, len(jobs), depth):
+                    out[k] = fn(self.solvers[w], jobs[k])
+            except Exception as ex:        # surfaced by the caller
+                err.append(ex)
+        ths = [threading.Thread(target=worker, args=(w,)) for w in range(depth)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        if err:
+            raise err[0]
+        return out
+
+    def solve_stream(self, prepared_batches, stagger_s: float = 0.0):
+        """miqp_b200_solve_batch of every prepared batch (host buffers in and out), batch k on instance k mod depth.
+        Two batches that are in flight together must not share their prepared buffers.  Returns [(xs, infos), ...]."""
+        return self._run_threads(list(prepared_batches), lambda s, b: s.solve_prepared(b), stagger_s)
+
+    def upload_resident(self, prepared_batches):
+        """one resident batch per instance (miqp_b200_batch_upload)"""
+        for s, b in zip(self.solvers, prepared_batches):
+            s.upload_prepared(b)
+
+    def run_resident(self, runs: int, stagger_s: float = 0.0):
+        """`runs` searches over the resident batches (miqp_b200_batch_run), run k on instance k mod depth; returns the
+        device time of every run (CUDA events on its own stream; the runs overlap, so their sum exceeds the wall time)."""
+        return self._run_threads(list(range(runs)), lambda s, k: s.run(), stagger_s)
+
+    def timed_resident(self, runs: int, stagger_s: float = 0.0):
+        """run_resident, timed on the device: CUDA events on the solvers' own streams, from the start of the first run to the
+        end of the last one on either stream.  Returns (total device ms, per-run device ms)."""
+        self.solvers[0].mark(0)
+        per_run = self.run_resident(runs, stagger_s)
+        for s in self.solvers:
+            s.mark(1)
+        return max(self.solvers[0].elapsed_to(s) for s in self.solvers), per_run

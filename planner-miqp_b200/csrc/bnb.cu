@@ -825,6 +825,66 @@ __global__ void bnb_tighten_kernel(BnbState st, const double *ub) {
 void launch_bnb_tighten(const BnbState &st, const double *ub, cudaStream_t s) { bnb_tighten_kernel<<<(st.count + 127) / 128, 128, 0, s>>>(st, ub); }
 
 // ---------------------------------------------------------------------------------------
+// receding-horizon warm start on the device (MiqpPlanner::CalculateWarmstart / EnvironmentWarmstart, src/miqp_planner.cpp:787-1115,
+// and the MIP start of src/cplex_wrapper.cpp:494-639): the incumbent of the previous planning cycle is kept as one decision byte per
+// disjunction, so "shift every family by one step, repeat the last column, re-derive the binaries" is a shift of the bytes along the
+// time axis; the last step stays undecided (the repeated column is often infeasible there) and the search completes it.  A region
+// that is no longer reachable in the new cycle (possible_region moves with the car's orientation) leaves its step undecided.
+// One CTA per plan; prev_* are copies of the previous cycle's incumbents, taken before the new batch was set up.
+// ---------------------------------------------------------------------------------------
+__global__ void bnb_shift_warm_kernel(const DevProb *probs, const int *iblob, int count, const unsigned char *prev_dec, int prev_stride,
+                                      const double *prev_ub, const unsigned long long *prev_uid, const int *same_shape,
+                                      unsigned char *warm_dec, int stride, int *has_warm) {
+  const int s = blockIdx.x;
+  if (s >= count) return;
+  const DevProb &p = probs[s];
+  const int *I = iblob;
+  const bool ok = same_shape[s] && prev_ub[s] < MQ_INF && prev_uid[s] != ~0ULL;
+  unsigned char *w = warm_dec + (long)s * stride;
+  for (int e = threadIdx.x; e < stride; e += blockDim.x) w[e] = UNDEC;
+  if (threadIdx.x == 0) has_warm[s] = ok ? 1 : 0;
+  if (!ok) return;
+  __syncthreads();
+  const unsigned char *d = prev_dec + (long)s * prev_stride;
+  const int C = p.C, N = p.N, O = p.O, E = p.E, P = p.P, R = p.R;
+  // mode of (car, step): alternative j*4+h must exist in the new cycle, else another speed half-plane of the same region, else undecided
+  for (int e = threadIdx.x; e < C * (N - 1); e += blockDim.x) {
+    const int c = e / (N - 1), i = e % (N - 1);          // new step i takes old step i + 1
+    if (i == 0) continue;                                 // step 0 is the fixed state
+    unsigned char m = d[p.off_mode + c * N + i + 1];
+    if (m != UNDEC && m != MODE_FROZEN) {
+      const int na = I[p.o_nalt + c]; const int *alts = I + p.o_alt + c * 4 * R;
+      int exact = 0, same_region = -1;
+      for (int a = 0; a < na; ++a) { if (alts[a] == m) exact = 1; else if ((alts[a] >> 2) == (m >> 2) && same_region < 0) same_region = alts[a]; }
+      if (!exact) m = (same_region >= 0) ? (unsigned char)same_region : (unsigned char)UNDEC;
+    }
+    w[p.off_mode + c * N + i] = m;
+  }
+  if (E > 1)
+    for (int e = threadIdx.x; e < C * (N - 1) * 5; e += blockDim.x) {
+      const int pt = e % 5, ci = e / 5, c = ci / (N - 1), i = ci % (N - 1);
+      const unsigned char v = d[p.off_env + (c * N + i + 1) * 5 + pt];
+      w[p.off_env + (c * N + i) * 5 + pt] = (v < E) ? v : (unsigned char)UNDEC;
+    }
+  for (int e = threadIdx.x; e < C * O * (N - 1) * 5; e += blockDim.x) {
+    const int pt = e % 5, r = e / 5, i = r % (N - 1), co = r / (N - 1);
+    unsigned char v = d[p.off_obs + (co * N + i + 1) * 5 + pt];   // the obstacle prediction moves one step ahead with the horizon
+    const int o = co % O;
+    if (v == OBS_SOFT) { if (I[p.o_obs_soft + o] != 1) v = UNDEC; }
+    else if (v != UNDEC && v >= I[p.o_obs_nedges + o * N + i]) v = UNDEC;
+    w[p.off_obs + (co * N + i) * 5 + pt] = v;
+  }
+  for (int e = threadIdx.x; e < P * (N - 1) * 4; e += blockDim.x) {
+    const int q = e % 4, r = e / 4, i = r % (N - 1), pr = r / (N - 1);
+    w[p.off_pair + (pr * N + i) * 4 + q] = d[p.off_pair + (pr * N + i + 1) * 4 + q];
+  }
+}
+void launch_bnb_shift_warm(const DevProb *probs, const int *iblob, int count, const unsigned char *prev_dec, int prev_stride, const double *prev_ub,
+                           const unsigned long long *prev_uid, const int *same_shape, unsigned char *warm_dec, int stride, int *has_warm, cudaStream_t s) {
+  bnb_shift_warm_kernel<<<count, 128, 0, s>>>(probs, iblob, count, prev_dec, prev_stride, prev_ub, prev_uid, same_shape, warm_dec, stride, has_warm);
+}
+
+// ---------------------------------------------------------------------------------------
 // finish: best bound, full column vector of the incumbent (collectRawResults,
 // src/cplex_wrapper.cpp:311-448)
 // ---------------------------------------------------------------------------------------

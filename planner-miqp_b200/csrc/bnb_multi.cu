@@ -59,15 +59,16 @@ __global__ void __launch_bounds__(MULTI_MAX_THREADS) bnb_nodes_multi_kernel(BnbS
       atomicAdd(&st.stat_rows[s], (unsigned long long)out.rows);
     }
     if (out.what == MN_INFEASIBLE) continue;
+    const bool redundant = (nmeta.x & (1 << 21)) != 0;   // heuristic completion (below): never in the bound books
     if (out.what == MN_UNKNOWN) {   // closed without optimum or certificate: its bound stays in the books
-      if (tid == 0) { atomic_min_double(&st.pruned_lb[s], nbound); atomicAdd(&st.stat_uncert[s], 1ULL); }
+      if (tid == 0 && !redundant) { atomic_min_double(&st.pruned_lb[s], nbound); atomicAdd(&st.stat_uncert[s], 1ULL); }
       continue;
     }
-    if (out.what == MN_PRUNED) { if (tid == 0) atomic_min_double(&st.pruned_lb[s], out.obj); continue; }
+    if (out.what == MN_PRUNED) { if (tid == 0 && !redundant) atomic_min_double(&st.pruned_lb[s], out.obj); continue; }
     if (out.what == MN_INCUMBENT) {
       if (tid < 32) warp_lock(&st.lock[s], tid);   // (warp 0 waits converged; the other warps wait at the barrier below)
       if (tid == 0) {
-        if (!out.converged) atomic_min_double(&st.pruned_lb[s], out.obj);   // the leaf's optimum may lie below the stalled point, not below obj
+        if (!out.converged && !redundant) atomic_min_double(&st.pruned_lb[s], out.obj);   // the leaf's optimum may lie below the stalled point, not below obj
         const double cur = *reinterpret_cast<volatile double *>(&st.ub[s]);
         const unsigned long long cuid = *reinterpret_cast<volatile unsigned long long *>(&st.inc_uid[s]);
         s_i[1] = (out.fval < cur || (out.fval == cur && nuid < cuid)) ? 1 : 0;
@@ -97,8 +98,14 @@ __global__ void __launch_bounds__(MULTI_MAX_THREADS) bnb_nodes_multi_kernel(BnbS
     }
     // children (those whose lower bound reaches the cutoff were dropped by m_process_node)
     if (tid == 0 && out.pruned_min < MQM_INF) atomic_min_double(&st.pruned_lb[s], out.pruned_min);
-    const int nalt = out.nalt;
-    if (nalt == 0) continue;
+    const int nreal = out.nalt;
+    if (nreal == 0) continue;
+    // Primal heuristic while the plan has no incumbent: the completion of this node by the least violated alternative of every
+    // open disjunction (k.imp) goes in as one extra, fully decided node.  It is redundant -- the children still cover the node --
+    // so it is flagged (depth bit 21: never counted in the bounds) and costs one relaxation; with dozens of
+    // violated collision disjunctions (8 cars) it finds a first incumbent hundreds of dive levels early.
+    const int nheur = (st.multi_heur > 0 && !(cutoff < MQM_INF) && out.soff >= 0 && nmeta.x < (1 << 20) && (nmeta.x % st.multi_heur) == 0) ? 1 : 0;
+    const int nalt = nreal + nheur;
     if (tid == 0) {
       const int old = atomicSub(&st.free_cnt[s], nalt);
       if (old < nalt) {   // node pool of this plan exhausted: the children are dropped, their bound stays in the books
@@ -109,8 +116,9 @@ __global__ void __launch_bounds__(MULTI_MAX_THREADS) bnb_nodes_multi_kernel(BnbS
     __syncthreads();
     const int ok = s_i[1], fbase = s_i[2], opos = s_i[3];
     if (ok) {
-      const unsigned char *src = out.from_imp ? k.imp : k.dec;
       for (int a = 0; a < nalt; ++a) {
+        const bool heur = (a >= nreal);
+        const unsigned char *src = (out.from_imp || heur) ? k.imp : k.dec;
         const int cs = st.free_stack[pb + fbase + a];
         unsigned char *dst = st.dec + (pb + cs) * st.ndec_stride;
         const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
@@ -119,9 +127,10 @@ __global__ void __launch_bounds__(MULTI_MAX_THREADS) bnb_nodes_multi_kernel(BnbS
         __syncthreads();
         if (tid == 0) {
           int rank = 0;
-          if (out.soff >= 0) { dst[out.soff] = sh.alts[a]; rank = (sh.alts[a] == k.imp[out.soff]) ? -1 : a; }
-          st.bound[pb + cs] = sh.cb[a];
-          st.meta[pb + cs] = make_int2(nmeta.x >= (1 << 20) ? nmeta.x : nmeta.x + 1, (round << 8) | (rank + 1));
+          if (heur) rank = -1;
+          else if (out.soff >= 0) { dst[out.soff] = sh.alts[a]; rank = (sh.alts[a] == k.imp[out.soff]) ? -1 : a; }
+          st.bound[pb + cs] = heur ? out.obj : sh.cb[a];
+          st.meta[pb + cs] = make_int2(heur ? (nmeta.x | (1 << 21)) : (nmeta.x >= (1 << 20)) ? nmeta.x : nmeta.x + 1, (round << 8) | (rank + 1));
           st.uid[pb + cs] = mix64(nuid * 0x9e3779b97f4a7c15ULL + (unsigned long long)(a + 1));
           st.open_idx[pb + opos + a] = cs;
         }

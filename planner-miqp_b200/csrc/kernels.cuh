@@ -27,6 +27,7 @@ struct BnbState {
   int sel_dive;         // nodes per plan per round while diving for the first incumbent
   int dive_fill;        // >0: while diving, widen to (resident warps / active plans) / dive_fill heads when few plans are active
   int wide_div;         // >0: a plan with an incumbent takes at least (open nodes below the cutoff) / wide_div nodes per round
+  int multi_heur;                   // multi-car plans without incumbent: completion heuristic at every multi_heur-th level of the tree (0: off)
   int dive_patience, dive_growth;   // a plan without incumbent after dive_patience rounds widens its dive by dive_growth heads per round
   int work_cap;
   int force_multi;      // route every plan to the CTA-per-node kernel (test hook)
@@ -78,6 +79,8 @@ constexpr int NODE_TEAM_WARPS_WIDE = 8;   // the same for rounds with fewer node
 int launch_bnb_nodes(const BnbState &st, const DevProb *probs, const double *dblob, const int *iblob,
                      int smem_per_warp, int warps_per_cta, int ctas, int maxN, int round, cudaStream_t s);
 void launch_bnb_split(const BnbState &st, int rank, int world, cudaStream_t s);       // frontier sharding: keep this rank's share of every open list
+void launch_bnb_shift_warm(const DevProb *probs, const int *iblob, int count, const unsigned char *prev_dec, int prev_stride, const double *prev_ub,
+                           const unsigned long long *prev_uid, const int *same_shape, unsigned char *warm_dec, int stride, int *has_warm, cudaStream_t s);
 void launch_bnb_fingerprint(const BnbState &st, unsigned long long *out, cudaStream_t s);   // frontier sharding: open-list fingerprint per plan
 void launch_bnb_tighten(const BnbState &st, const double *ub, cudaStream_t s);      // st.ub = min(st.ub, ub): incumbents of other ranks
 void launch_bnb_finish(const BnbState &st, const DevProb *probs, const double *dblob, const int *iblob,

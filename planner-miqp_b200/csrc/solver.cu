@@ -62,6 +62,7 @@ struct MiqpB200Solver {
   std::string err;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evr0 = nullptr, evr1 = nullptr;
+  cudaEvent_t mark[2] = {nullptr, nullptr};   // miqp_b200_mark / miqp_b200_elapsed: device time across several runs and solvers
   int num_sms = 0;
   // batch
   Packed pk;
@@ -95,6 +96,7 @@ struct MiqpB200Solver {
   long fr_rounds = 0; int fr_ctrl0 = 0;                       // rounds run so far / work items of the last round
   std::chrono::steady_clock::time_point fr_t0;                // start of the current run (time limit)
   long fr_launches = 0, fr_node_launches = 0; double fr_node_ms = 0.0;
+  DevBuf<unsigned char> d_prev_dec; DevBuf<double> d_prev_ub; DevBuf<unsigned long long> d_prev_uid; DevBuf<int> d_same;   // previous cycle (replan)
   DevBuf<unsigned long long> d_fp;                            // open-list fingerprints (frontier sharding)
   DevBuf<double> d_ubx;                                       // incumbent objectives exchanged between ranks (frontier sharding)
   double last_seconds = 0.0;
@@ -302,7 +304,11 @@ void setup_bnb(MiqpB200Solver *s) {
   st.dive_patience = 14; st.dive_growth = 8;   // profiles/r1k: batch 1024 139 -> 80 ms, batch 2048 unchanged (144 ms, 53 -> 38 rounds)
   if (const char *e = getenv("MIQP_DIVE_PATIENCE")) st.dive_patience = atoi(e);
   if (const char *e = getenv("MIQP_DIVE_GROWTH")) st.dive_growth = atoi(e);
+  st.multi_heur = 1;
+  if (const char *e = getenv("MIQP_MULTI_HEUR")) st.multi_heur = atoi(e);
   int kscap = 64;
+  // a few multi-car plans alone on the GPU (config 5: ONE joint plan): let a plan take as many nodes per round as CTAs are resident
+  if (s->n_single == 0 && s->n_multi > 0) kscap = std::max(64, std::min(1024, st.nwarps / std::max(count, 1)));
   if (const char *e = getenv("MIQP_KS")) kscap = std::max(1, atoi(e));
   int KS = std::max(K, std::min(kscap, std::max(1, st.nwarps)));
   st.sel_per_plan = KS;
@@ -413,6 +419,7 @@ int miqp_b200_create(const MiqpB200Options *opt, MiqpB200Solver **out) {
     CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&s->ev0)); CK(cudaEventCreate(&s->ev1));
     CK(cudaEventCreate(&s->evr0)); CK(cudaEventCreate(&s->evr1));
+    CK(cudaEventCreate(&s->mark[0])); CK(cudaEventCreate(&s->mark[1]));
   } catch (const std::exception &ex) {
     fprintf(stderr, "miqp_b200: %s\n", ex.what());
     delete s;
@@ -436,6 +443,8 @@ void miqp_b200_destroy(MiqpB200Solver *s) {
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   if (s->evr0) cudaEventDestroy(s->evr0);
+  if (s->mark[0]) cudaEventDestroy(s->mark[0]);
+  if (s->mark[1]) cudaEventDestroy(s->mark[1]);
   if (s->evr1) cudaEventDestroy(s->evr1);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
@@ -590,6 +599,54 @@ int miqp_b200_batch_upload(MiqpB200Solver *s, const MiqpB200Problem *problems, i
       CK(cudaMemcpyAsync(s->d_haswarm.p, s->h_haswarm.data(), sizeof(int) * count, cudaMemcpyHostToDevice, s->stream));
       s->stats.h2d_bytes += (long)(s->h_warm.size() + sizeof(int) * count);
     }
+    CK(cudaStreamSynchronize(s->stream));
+    s->stats.pack_ms = std::chrono::duration<double, std::milli>(tp1 - tp0).count();
+    s->stats.upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp1).count();
+    s->uploaded = true;
+  } catch (const std::invalid_argument &ex) {
+    return fail(s, MIQP_B200_ERR_ARG, ex.what());
+  } catch (const std::exception &ex) {
+    return fail(s, MIQP_B200_ERR_CUDA, ex.what());
+  }
+  return MIQP_B200_OK;
+}
+
+// Receding-horizon replanning without a host round trip of the solutions: the MIP start of every plan is the incumbent of the
+// previous batch on this solver (same plan order, same shapes), shifted by one step on the device (bnb_shift_warm_kernel).
+int miqp_b200_batch_upload_replan(MiqpB200Solver *s, const MiqpB200Problem *problems, int count) {
+  if (!s || !problems || count <= 0) return MIQP_B200_ERR_ARG;
+  if (!s->ran) return fail(s, MIQP_B200_ERR_ARG, "batch_upload_replan needs the results of a previous batch_run on this solver");
+  if (count != s->st.count) return fail(s, MIQP_B200_ERR_ARG, "batch_upload_replan: the batch must hold the same plans as the previous one");
+  try {
+    CK(cudaSetDevice(s->opt.device));
+    // the previous cycle's incumbents, before the buffers are reused
+    const int prev_stride = s->st.ndec_stride;
+    s->d_prev_dec.ensure((size_t)count * prev_stride); s->d_prev_ub.ensure(count); s->d_prev_uid.ensure(count); s->d_same.ensure(count);
+    CK(cudaMemcpyAsync(s->d_prev_dec.p, s->st.inc_dec, (size_t)count * prev_stride, cudaMemcpyDeviceToDevice, s->stream));
+    CK(cudaMemcpyAsync(s->d_prev_ub.p, s->st.ub, sizeof(double) * count, cudaMemcpyDeviceToDevice, s->stream));
+    CK(cudaMemcpyAsync(s->d_prev_uid.p, s->st.inc_uid, sizeof(unsigned long long) * count, cudaMemcpyDeviceToDevice, s->stream));
+    struct Shape { int C, N, R, O, E, L; };
+    std::vector<Shape> prev(count);
+    for (int k = 0; k < count; ++k) { const DevProb &p = s->pk.probs[k]; prev[k] = Shape{p.C, p.N, p.R, p.O, p.E, p.L}; }
+    CK(cudaStreamSynchronize(s->stream));
+    s->uploaded = false; s->ran = false;
+    const auto tp0 = std::chrono::steady_clock::now();
+    pack_batch(s, problems, count);
+    const auto tp1 = std::chrono::steady_clock::now();
+    upload_packed(s);
+    setup_bnb(s);
+    s->h_haswarm.assign(count, 0);
+    for (int k = 0; k < count; ++k) {
+      const DevProb &p = s->pk.probs[k];
+      s->h_haswarm[k] = (p.C == prev[k].C && p.N == prev[k].N && p.R == prev[k].R && p.O == prev[k].O && p.E == prev[k].E && p.L == prev[k].L) ? 1 : 0;
+    }
+    CK(cudaMemcpyAsync(s->d_same.p, s->h_haswarm.data(), sizeof(int) * count, cudaMemcpyHostToDevice, s->stream));
+    s->d_warm.ensure((size_t)count * s->st.ndec_stride); s->d_haswarm.ensure(count);
+    launch_bnb_shift_warm(s->d_probs.p, s->d_iblob.p, count, s->d_prev_dec.p, prev_stride, s->d_prev_ub.p, s->d_prev_uid.p, s->d_same.p,
+                          s->d_warm.p, s->st.ndec_stride, s->d_haswarm.p, s->stream);
+    CK(cudaGetLastError());
+    s->any_warm = true;
+    s->stats.h2d_bytes += (long)(sizeof(int) * count);
     CK(cudaStreamSynchronize(s->stream));
     s->stats.pack_ms = std::chrono::duration<double, std::milli>(tp1 - tp0).count();
     s->stats.upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp1).count();
@@ -826,6 +883,19 @@ int miqp_b200_frontier_finish(MiqpB200Solver *s, float *device_ms) {
     s->stats.node_kernel_ms = s->fr_node_ms; s->stats.total_ms = total_ms;
     s->ran = true;
   } catch (const std::exception &ex) { return fail(s, MIQP_B200_ERR_CUDA, ex.what()); }
+  return MIQP_B200_OK;
+}
+
+int miqp_b200_mark(MiqpB200Solver *s, int which) {
+  if (!s || which < 0 || which > 1) return MIQP_B200_ERR_ARG;
+  if (cudaSetDevice(s->opt.device) != cudaSuccess || cudaEventRecord(s->mark[which], s->stream) != cudaSuccess) return fail(s, MIQP_B200_ERR_CUDA, "cudaEventRecord failed");
+  return MIQP_B200_OK;
+}
+
+int miqp_b200_elapsed(MiqpB200Solver *from, MiqpB200Solver *to, float *ms) {
+  if (!from || !to || !ms) return MIQP_B200_ERR_ARG;
+  if (cudaEventSynchronize(from->mark[0]) != cudaSuccess || cudaEventSynchronize(to->mark[1]) != cudaSuccess ||
+      cudaEventElapsedTime(ms, from->mark[0], to->mark[1]) != cudaSuccess) return fail(to, MIQP_B200_ERR_CUDA, "cudaEventElapsedTime failed");
   return MIQP_B200_OK;
 }
 

@@ -24,13 +24,18 @@ struct Node { double bound; int depth, rank; long birth; unsigned long long uid;
 struct Cmp {
   bool have_inc; long round; int policy;   // policy 0: deepest first; 1: children of the last round first, else best bound
   bool before(const Node &x, const Node &y) const {
-    if (!have_inc && policy == 1) {
+    if (!have_inc && policy >= 1) {
       const bool nx = (x.birth == round - 1), ny = (y.birth == round - 1);
       if (nx != ny) return nx;
       if (nx) { if (x.rank != y.rank) return x.rank < y.rank; if (x.bound != y.bound) return x.bound < y.bound; return x.uid < y.uid; }
       if (x.bound != y.bound) return x.bound < y.bound;
       if (x.depth != y.depth) return x.depth > y.depth;
       return x.uid < y.uid;
+    }
+    if (have_inc && policy >= 2) {   // best bound with plunging: the children of the last round first (least violated alternative first)
+      const bool nx = (x.birth == round - 1), ny = (y.birth == round - 1);
+      if (nx != ny) return nx;
+      if (nx) { if (x.rank != y.rank) return x.rank < y.rank; if (x.bound != y.bound) return x.bound < y.bound; return x.uid < y.uid; }
     }
     if (!have_inc) { if (x.depth != y.depth) return x.depth > y.depth; if (x.rank != y.rank) return x.rank < y.rank; if (x.bound != y.bound) return x.bound < y.bound; return x.uid < y.uid; }
     if (x.bound != y.bound) return x.bound < y.bound;
@@ -75,6 +80,7 @@ extern "C" int emu_multi_solve(const MiqpB200Problem *q, double gap_tol, double 
   long nodes = 0, iters = 0; unsigned long long next_uid = 2;
   Cmp cmp; cmp.have_inc = false; cmp.round = 0; { const char *ep = std::getenv("EMU_POLICY"); cmp.policy = ep ? std::atoi(ep) : 1; }
   const char *ekd = std::getenv("EMU_KDIVE"); const int Kdive = ekd ? std::atoi(ekd) : 0;
+  const char *eh = std::getenv("EMU_HEUR"); const int heur = eh ? std::atoi(eh) : 0;
   const auto t0 = std::chrono::steady_clock::now();
   bool timed_out = false;
   const char *ek = std::getenv("EMU_K");
@@ -119,6 +125,12 @@ extern "C" int emu_multi_solve(const MiqpB200Problem *q, double gap_tol, double 
       continue;
     }
     pruned_lb = std::min(pruned_lb, out.pruned_min);
+    if (heur > 0 && !cmp.have_inc && nd.depth < (1 << 20) && out.soff >= 0 && (nd.depth % heur) == 0) {
+      // primal heuristic: the completion by the least violated alternatives as one extra, fully decided node (redundant: the
+      // children below still cover the node)
+      Node hn; hn.bound = out.obj; hn.depth = 1 << 20; hn.rank = -2; hn.uid = next_uid++; hn.birth = rounds; hn.dec.assign(k.imp, k.imp + nds);
+      open.push_back(hn);
+    }
     const unsigned char *src = out.from_imp ? k.imp : k.dec;
     for (int a = 0; a < out.nalt; ++a) {
       Node ch; ch.bound = (std::getenv("EMU_NO_CHILD_BOUND") ? out.obj : sh.cb[a]); ch.depth = nd.depth + 1; ch.rank = a; ch.uid = next_uid++; ch.birth = rounds;
