@@ -466,6 +466,7 @@ def main():
     ap.add_argument("--latency-plans", type=int, default=16)
     ap.add_argument("--replan-scenarios", type=int, default=256)
     ap.add_argument("--replan-cycles", type=int, default=8)
+    ap.add_argument("--skip-extras", action="store_true", help="only the throughput legs (no latency, replanning, assembly, CPU baseline): for A/B runs")
     ap.add_argument("--in-flight", type=int, default=2, help="batches in flight on one GPU (solver instances / streams); 1 = one at a time")
     args = ap.parse_args()
     args.batch_given = any(a == "--batch" or a.startswith("--batch=") for a in sys.argv[1:])
@@ -606,6 +607,25 @@ def main():
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
+    e2e_full = world * B * args.steps / e2e_s          # every OPL column vector returned (68 MB per 2048 plans)
+    e2e_full_ms = 1e3 * e2e_s / args.steps
+    d2h_full = st2["d2h_bytes"]
+    # compact results: trajectories + status / objective / gap per plan; the full vectors stay on the device (fetch_vector on demand)
+    solver.solve_prepared_compact(prepared[shard_ids[0]])
+    barrier()
+    e2e_s = 0.0
+    for k in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        solver.solve_prepared_compact(prepared[shard_ids[k % S]])
+        e2e_s += time.perf_counter() - t0
+    barrier()
+    st2 = solver.run_stats()
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
     e2e_seq = world * B * args.steps / e2e_s
     e2e_seq_ms = 1e3 * e2e_s / args.steps
     # the same calls with two batches in flight: pack + H2D of one batch and D2H + scatter of the other overlap with the search
@@ -613,10 +633,10 @@ def main():
     if pipe is not None:
         try:
             jobs = [prepared[shard_ids[k % S]] for k in range(args.steps)]
-            pipe.solve_stream(jobs[:args.in_flight], 0.5e-3 * e2e_seq_ms)
+            pipe.solve_stream_compact(jobs[:args.in_flight], 0.5e-3 * e2e_seq_ms)
             barrier()
             t0 = time.perf_counter()
-            pipe.solve_stream(jobs, 0.5e-3 * e2e_seq_ms)
+            pipe.solve_stream_compact(jobs, 0.5e-3 * e2e_seq_ms)
             e2e_pipe_s = time.perf_counter() - t0
             barrier()
             if world > 1:
@@ -678,6 +698,14 @@ def main():
                             "plans": B, "rows": asm_rows, "nnz": asm_nnz, "bytes": asm_bytes, "peak_source": peaks["source"],
                             "assemblies_per_s": B / (asm_ms * 1e-3) if asm_ms > 0 else None}
 
+    if args.skip_extras:
+        emit({"value": value, "ms_per_step": total_ms / args.steps, "batches_in_flight": args.in_flight if use_pipe else 1, "batch": B,
+              "one_batch_at_a_time": {"value": value_seq, "ms_per_step": seq_ms_per_step, "e2e": e2e_seq, "e2e_full_vectors": e2e_full},
+              "e2e": e2e_value, "steps": args.steps, "env": {k: v for k, v in os.environ.items() if k.startswith("MIQP_")}})
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
     # ---- single-plan latency ----------------------------------------------------------------
     lat_e2e, lat_dev = [], []
     for k in range(min(args.latency_plans, B)):
@@ -716,10 +744,13 @@ def main():
         "config": cfg,
         "clocks": clocks,
         "one_batch_at_a_time": {"value": value_seq, "ms_per_step": seq_ms_per_step, "e2e_value": e2e_seq, "e2e_ms_per_step": e2e_seq_ms,
+                                "e2e_full_vectors": {"value": e2e_full, "ms_per_step": e2e_full_ms, "d2h_bytes_per_step": d2h_full},
                                 "note": "one solver, one stream: batch k + 1 starts when batch k has finished (L2 flushed in between); "
                                         "the roofline and per-shard figures below are from this leg"},
         "e2e": {"value": e2e_value, "unit": "plans/s", "h2d_bytes_per_step": st2["h2d_bytes"], "d2h_bytes_per_step": st2["d2h_bytes"],
                 "ms_per_step": 1e3 * e2e_s / args.steps,
+                "results": "compact: per plan the trajectory [C][N][8] and status / objective / bound / gap / violation (miqp_b200_solve_batch_compact); "
+                           "the full column vectors stay on the device (miqp_b200_fetch_vector)",
                 "host_ms_last_step": {"pack": st2.get("pack_ms"), "h2d_tables_pool": st2.get("upload_ms"), "d2h_scatter": st2.get("fetch_ms")}},
         "gpu_launches": launches_pipe if use_pipe else launches,
         "roofline": roofline,

@@ -162,6 +162,16 @@ int miqp_b200_batch_upload_replan(MiqpB200Solver *s, const MiqpB200Problem *prob
 int miqp_b200_batch_run(MiqpB200Solver *s, float *device_ms);
 int miqp_b200_batch_fetch(MiqpB200Solver *s, double *const *x_out, MiqpB200SolveInfo *infos);
 
+/* Compact results: per plan the trajectory of every car, [C][N][8] doubles (pos_x, vel_x, acc_x, pos_y, vel_y, acc_y, u_x, u_y per
+ * step: what MiqpPlanner::GetTrajectory reads, src/miqp_planner.cpp:1117-1192) instead of the full OPL column vector (config 2:
+ * 2.5 kB instead of 33 kB per plan across PCIe).  Objective, gap, status and violation in `infos` are those of the full vector,
+ * which stays on the device until the next upload: fetch_vector(s, k, x_out) copies plan k's RawResults vector on demand, and
+ * batch_upload_replan uses the incumbents in place. */
+int miqp_b200_batch_fetch_compact(MiqpB200Solver *s, double *const *traj_out, MiqpB200SolveInfo *infos);
+int miqp_b200_fetch_vector(MiqpB200Solver *s, int k, double *x_out /* [ncols of plan k] */);
+int miqp_b200_solve_batch_compact(MiqpB200Solver *s, const MiqpB200Problem *problems, int count, const double *const *warm,
+                                  double *const *traj_out, MiqpB200SolveInfo *infos);
+
 /* The same search in steps, for a caller that shards the FRONTIER of the uploaded plans over several GPUs (one process and one
  * solver per GPU).  Every rank uploads the same batch and runs the same deterministic ramp-up
  * (frontier_start, frontier_rounds); frontier_split then keeps, in every open list, the nodes whose uid hashes to this rank.

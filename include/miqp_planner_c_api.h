@@ -92,6 +92,11 @@ void RemoveAllObstaclesCMiqpPlanner(CMiqpPlanner c_miqp_planner);
  * returned for planners[k].  Returns the number of successful plans, -1 on a device error. */
 int PlanBatchCMiqpPlanner(CMiqpPlanner *planners, int count, const double timestep, bool *success);
 
+/* When the same planners are planned again in the same order with RECEDING_HORIZON_WARMSTART, PlanBatchCMiqpPlanner takes the
+ * MIP starts from the previous incumbents on the device (shifted by one step there, miqp_b200_batch_upload_replan) instead of the
+ * host-side shifted vectors; this counts the batches that did so (process-wide). */
+long DeviceWarmstartBatchesCMiqpPlanner(void);
+
 /* SolutionProperties of the last Plan() (reference src/cplex_wrapper.hpp:41-52):
  * out = {objective, gap, time [s], status, nodes, rows, binaries, continuous}. */
 void GetSolutionPropertiesCMiqpPlanner(CMiqpPlanner c_miqp_planner, double out[8]);

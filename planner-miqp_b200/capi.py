@@ -24,7 +24,8 @@ DECLARED_SYMBOLS = [
     "miqp_b200_batch_fetch", "miqp_b200_run_stats", "miqp_b200_measure_fp64_peak",
     "miqp_b200_debug_profile", "miqp_b200_debug_traces",
     "miqp_b200_frontier_start", "miqp_b200_frontier_rounds", "miqp_b200_frontier_split", "miqp_b200_frontier_get_ub",
-    "miqp_b200_frontier_tighten", "miqp_b200_frontier_finish", "miqp_b200_frontier_fingerprint", "miqp_b200_frontier_ub_device", "miqp_b200_batch_upload_replan", "miqp_b200_mark", "miqp_b200_elapsed",
+    "miqp_b200_frontier_tighten", "miqp_b200_frontier_finish", "miqp_b200_frontier_fingerprint", "miqp_b200_frontier_ub_device", "miqp_b200_batch_upload_replan", "miqp_b200_mark", "miqp_b200_elapsed", "miqp_b200_batch_fetch_compact", "miqp_b200_fetch_vector",
+    "miqp_b200_solve_batch_compact",
 ]
 
 
@@ -100,7 +101,9 @@ class SolveInfo:
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "libmiqp_b200.so")
+    # MIQP_B200_VARIANT=<tag>: a build variant made by `MIQP_VARIANT=<tag> python build.py` (A/B runs of build-time switches)
+    tag = os.environ.get("MIQP_B200_VARIANT")
+    return os.path.join(_HERE, f"libmiqp_b200_{tag}.so" if tag else "libmiqp_b200.so")
 
 
 _lib = None
@@ -324,7 +327,7 @@ class Solver:
         xs = [np.zeros(c) for c in ncols]
         xptr = (_dp * n)(*[x.ctypes.data_as(_dp) for x in xs])
         infos = (CSolveInfo * n)()
-        return dict(n=n, arr=arr, warm=warm_arr, xs=xs, xptr=xptr, infos=infos, keep=keep)
+        return dict(n=n, arr=arr, warm=warm_arr, xs=xs, xptr=xptr, infos=infos, keep=keep, problems=list(problems))
 
     def solve_prepared(self, b):
         """One miqp_b200_solve_batch call on host buffers: pack + H2D + device solve + D2H."""
@@ -350,7 +353,37 @@ class Solver:
         n = len(problems)
         arr, warm_arr, ncols, keep = self._pack(problems, gap_tol, time_limit, warm)
         self._check(self._lib.miqp_b200_batch_upload(self._h, arr, n, warm_arr), "miqp_b200_batch_upload")
-        self._batch = (n, ncols)
+        self._batch = (n, ncols); self._shapes = [(p.C, p.N) for p in problems]
+
+    def fetch_compact(self):
+        """trajectories [C][N][8] per plan + infos (miqp_b200_batch_fetch_compact); the full vectors stay on the device"""
+        n, ncols = self._batch
+        shapes = self._shapes if getattr(self, "_shapes", None) and len(self._shapes) == n else None
+        if shapes is None:
+            raise MiqpB200Error("fetch_compact needs upload() / upload_prepared() of this batch")
+        tr = [np.zeros((c, nn, 8)) for c, nn in shapes]
+        tptr = (_dp * n)(*[t.ctypes.data_as(_dp) for t in tr])
+        infos = (CSolveInfo * n)()
+        self._lib.miqp_b200_batch_fetch_compact.argtypes = [C.c_void_p, C.POINTER(_dp), C.POINTER(CSolveInfo)]
+        self._check(self._lib.miqp_b200_batch_fetch_compact(self._h, tptr, infos), "miqp_b200_batch_fetch_compact")
+        return tr, [self._info(i) for i in infos]
+
+    def fetch_vector(self, k: int) -> np.ndarray:
+        n, ncols = self._batch
+        x = np.zeros(ncols[k])
+        self._lib.miqp_b200_fetch_vector.argtypes = [C.c_void_p, C.c_int, _dp]
+        self._check(self._lib.miqp_b200_fetch_vector(self._h, int(k), x.ctypes.data_as(_dp)), "miqp_b200_fetch_vector")
+        return x
+
+    def solve_prepared_compact(self, b):
+        """One miqp_b200_solve_batch_compact call on host buffers: pack + H2D + device solve + D2H of trajectories and infos."""
+        if "traj" not in b:
+            b["traj"] = [np.zeros((p.C, p.N, 8)) for p in b["problems"]]
+            b["tptr"] = (_dp * b["n"])(*[t.ctypes.data_as(_dp) for t in b["traj"]])
+        self._lib.miqp_b200_solve_batch_compact.argtypes = [C.c_void_p, C.POINTER(CProblem), C.c_int, C.POINTER(_dp), C.POINTER(_dp), C.POINTER(CSolveInfo)]
+        self._check(self._lib.miqp_b200_solve_batch_compact(self._h, b["arr"], b["n"], b["warm"], b["tptr"], b["infos"]), "miqp_b200_solve_batch_compact")
+        self._batch = (b["n"], [len(x) for x in b["xs"]]); self._shapes = [(p.C, p.N) for p in b["problems"]]
+        return b["traj"], b["infos"]
 
     def upload_replan(self, problems, gap_tol=None, time_limit=None):
         """next planning cycle of the previous batch: MIP starts = previous incumbents shifted by one step on the device"""
@@ -358,17 +391,17 @@ class Solver:
         arr, _, ncols, keep = self._pack(problems, gap_tol, time_limit, None)
         self._lib.miqp_b200_batch_upload_replan.argtypes = [C.c_void_p, C.POINTER(CProblem), C.c_int]
         self._check(self._lib.miqp_b200_batch_upload_replan(self._h, arr, n), "miqp_b200_batch_upload_replan")
-        self._batch = (n, ncols)
+        self._batch = (n, ncols); self._shapes = [(p.C, p.N) for p in problems]
 
     def upload_replan_prepared(self, b):
         self._lib.miqp_b200_batch_upload_replan.argtypes = [C.c_void_p, C.POINTER(CProblem), C.c_int]
         self._check(self._lib.miqp_b200_batch_upload_replan(self._h, b["arr"], b["n"]), "miqp_b200_batch_upload_replan")
-        self._batch = (b["n"], [len(x) for x in b["xs"]])
+        self._batch = (b["n"], [len(x) for x in b["xs"]]); self._shapes = [(p.C, p.N) for p in b["problems"]]
 
     def upload_prepared(self, b):
         """miqp_b200_batch_upload of a batch built by prepare() (no Python-side packing)."""
         self._check(self._lib.miqp_b200_batch_upload(self._h, b["arr"], b["n"], b["warm"]), "miqp_b200_batch_upload")
-        self._batch = (b["n"], [len(x) for x in b["xs"]])
+        self._batch = (b["n"], [len(x) for x in b["xs"]]); self._shapes = [(p.C, p.N) for p in b["problems"]]
 
     def run(self) -> float:
         ms = C.c_float()
@@ -516,6 +549,10 @@ class PipelinedSolver:
         """miqp_b200_solve_batch of every prepared batch (host buffers in and out), batch k on instance k mod depth.
         Two batches that are in flight together must not share their prepared buffers.  Returns [(xs, infos), ...]."""
         return self._run_threads(list(prepared_batches), lambda s, b: s.solve_prepared(b), stagger_s)
+
+    def solve_stream_compact(self, prepared_batches, stagger_s: float = 0.0):
+        """solve_stream with compact results (trajectories + infos; the full vectors stay on the device)"""
+        return self._run_threads(list(prepared_batches), lambda s, b: s.solve_prepared_compact(b), stagger_s)
 
     def upload_resident(self, prepared_batches):
         """one resident batch per instance (miqp_b200_batch_upload)"""

@@ -520,34 +520,41 @@ __device__ __forceinline__ void effective_regions(const WarpCtx &w) {
 // shared memory of one node: S[N][S_STRIDE] V[N][V_STRIDE] T[T_SIZE] auxd[N] | rows[kmax+1][NP] (16-byte
 // aligned, NP = padded stage stride, node_qp.cuh:team_row_stride) | jeff[N] aux[3N] | dec imp alternatives
 struct NodeSmem { int off_rows, off_int, off_dec, total; };
-__host__ __device__ inline NodeSmem node_smem_layout(int maxN, int kmax, int ndec_stride) {
+// np: bound of the padded stage stride of the (s, lambda) records (team_row_stride; maxN + 7 covers every team size)
+__host__ __device__ inline NodeSmem node_smem_layout(int maxN, int kmax, int ndec_stride, int np) {
   NodeSmem L;
   int b = (maxN * (S_STRIDE + V_STRIDE + 1) + T_SIZE) * 8;
   b = (b + 15) & ~15;
   L.off_rows = b;   // (s, lambda) records: see RowIO (node_qp.cuh)
-  b += (kmax + 1) * (maxN + 7) * 16;
+  b += (kmax + 1) * np * 16;
   L.off_int = b; b += maxN * 4 * 4;
   b = (b + 15) & ~15;
   L.off_dec = b; b += 2 * ndec_stride + 272;
   L.total = (b + 15) & ~15;
   return L;
 }
-int node_kernel_smem_per_warp(int maxN, int kmax, int ndec_stride) { return node_smem_layout(maxN, kmax, ndec_stride).total; }
+int node_kernel_smem_per_warp(int maxN, int kmax, int ndec_stride) { return node_smem_layout(maxN, kmax, ndec_stride, maxN + 7).total; }
+int node_kernel_narrow_np(int N) { return team_row_stride(N, team_sublanes(N, NODE_TEAM_WARPS_NARROW)); }
+// two-warp teams on a batch whose single-car plans all have N steps: the records use the stride of that team size only
+int node_kernel_smem_narrow(int N, int kmax, int ndec_stride) { return node_smem_layout(N, kmax, ndec_stride, team_row_stride(N, team_sublanes(N, NODE_TEAM_WARPS_NARROW))).total; }
 
 // One CTA = one team of NODE_TEAM_WARPS warps = one node relaxation at a time (persistent: teams pull
 // (plan, node) items from the round's work list).  255 registers x 128 threads x 2 CTAs fill the
 // register file of an SM; the third CTA that shared memory would allow (57 kB per node at N = 40) does not fit.
 // NW = 8 (one CTA per SM, 6 sub-lanes per stage at N = 40) is launched for rounds that hold fewer nodes than SMs: the
 // round time is then the latency of its slowest node, and the wider team shortens the row passes.
+// NW = 2 (four CTAs per SM: 255 registers x 64 threads x 4; 51 kB of shared memory per node at N = 40) is the throughput variant
+// for rounds with more nodes than the four-warp teams hold at once: a node takes about 1.5x longer on two warps, twice as many are
+// in flight.
 template <int NW>
-__global__ void __launch_bounds__(NW * 32, NW == 4 ? NODE_TEAMS_PER_SM : 1) bnb_nodes_kernel(BnbState st, const DevProb *probs, const double *dblob,
-                                                                                            const int *iblob, int smem_per_node, int maxN, int round) {
+__global__ void __launch_bounds__(NW * 32, NW == 4 ? NODE_TEAMS_PER_SM : NW == 2 ? 4 : 1) bnb_nodes_kernel(BnbState st, const DevProb *probs, const double *dblob,
+                                                                                            const int *iblob, int smem_per_node, int maxN, int row_np, int round) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double s_red[32];
   __shared__ int s_wi;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   unsigned char *base = smem_raw;
-  const NodeSmem L = node_smem_layout(maxN, st.kmax, st.ndec_stride);
+  const NodeSmem L = node_smem_layout(maxN, st.kmax, st.ndec_stride, row_np);
   WarpCtx w;
   w.D = dblob; w.I = iblob; w.lane = lane; w.wid = wid; w.nw = nw; w.red = s_red;
   w.dbgrow = nullptr; w.tau_k = st.tau_k;
@@ -765,22 +772,22 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? NODE_TEAMS_PER_SM : 1) bnb_
 
 int node_kernel_max_ctas(int smem_per_cta, int threads) {
   int nb = 0;
-  if (threads == NODE_TEAM_WARPS_WIDE * 32) {
-    cudaFuncSetAttribute(bnb_nodes_kernel<NODE_TEAM_WARPS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_per_cta);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bnb_nodes_kernel<NODE_TEAM_WARPS_WIDE>, threads, smem_per_cta) != cudaSuccess) return 0;
-    return nb;
-  }
-  cudaFuncSetAttribute(bnb_nodes_kernel<NODE_TEAM_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_per_cta);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bnb_nodes_kernel<NODE_TEAM_WARPS>, threads, smem_per_cta) != cudaSuccess) return 0;
+  const void *fn = (threads == NODE_TEAM_WARPS_WIDE * 32) ? (const void *)bnb_nodes_kernel<NODE_TEAM_WARPS_WIDE>
+                 : (threads == NODE_TEAM_WARPS_NARROW * 32) ? (const void *)bnb_nodes_kernel<NODE_TEAM_WARPS_NARROW>
+                 : (const void *)bnb_nodes_kernel<NODE_TEAM_WARPS>;
+  if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_per_cta) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, threads, smem_per_cta) != cudaSuccess) { cudaGetLastError(); return 0; }
   return nb;
 }
 
 int launch_bnb_nodes(const BnbState &st, const DevProb *probs, const double *dblob, const int *iblob,
-                     int smem_per_node, int warps_per_cta, int ctas, int maxN, int round, cudaStream_t s) {
+                     int smem_per_node, int warps_per_cta, int ctas, int maxN, int row_np, int round, cudaStream_t s) {
   if (warps_per_cta == NODE_TEAM_WARPS_WIDE)
-    bnb_nodes_kernel<NODE_TEAM_WARPS_WIDE><<<ctas, warps_per_cta * 32, (size_t)smem_per_node, s>>>(st, probs, dblob, iblob, smem_per_node, maxN, round);
+    bnb_nodes_kernel<NODE_TEAM_WARPS_WIDE><<<ctas, warps_per_cta * 32, (size_t)smem_per_node, s>>>(st, probs, dblob, iblob, smem_per_node, maxN, row_np, round);
+  else if (warps_per_cta == NODE_TEAM_WARPS_NARROW)
+    bnb_nodes_kernel<NODE_TEAM_WARPS_NARROW><<<ctas, warps_per_cta * 32, (size_t)smem_per_node, s>>>(st, probs, dblob, iblob, smem_per_node, maxN, row_np, round);
   else
-    bnb_nodes_kernel<NODE_TEAM_WARPS><<<ctas, warps_per_cta * 32, (size_t)smem_per_node, s>>>(st, probs, dblob, iblob, smem_per_node, maxN, round);
+    bnb_nodes_kernel<NODE_TEAM_WARPS><<<ctas, warps_per_cta * 32, (size_t)smem_per_node, s>>>(st, probs, dblob, iblob, smem_per_node, maxN, row_np, round);
   return (int)cudaGetLastError();
 }
 

@@ -74,10 +74,11 @@ constexpr int NODE_TEAM_WARPS = 4;        // warps that share one node relaxatio
 #define MQ_TEAMS_PER_SM 2
 #endif
 constexpr int NODE_TEAMS_PER_SM = MQ_TEAMS_PER_SM;   // 2: 255 registers per thread; 3: 168 registers (spills), A/B in profiles/r1k
+constexpr int NODE_TEAM_WARPS_NARROW = 2; // throughput variant: two warps per node, four teams per SM (rounds with more nodes than the four-warp teams hold)
 constexpr int NODE_TEAM_WARPS_WIDE = 8;   // the same for rounds with fewer nodes than SMs, 1 team per SM
 // returns 0 or a cudaError
 int launch_bnb_nodes(const BnbState &st, const DevProb *probs, const double *dblob, const int *iblob,
-                     int smem_per_warp, int warps_per_cta, int ctas, int maxN, int round, cudaStream_t s);
+                     int smem_per_warp, int warps_per_cta, int ctas, int maxN, int row_np, int round, cudaStream_t s);
 void launch_bnb_split(const BnbState &st, int rank, int world, cudaStream_t s);       // frontier sharding: keep this rank's share of every open list
 void launch_bnb_shift_warm(const DevProb *probs, const int *iblob, int count, const unsigned char *prev_dec, int prev_stride, const double *prev_ub,
                            const unsigned long long *prev_uid, const int *same_shape, unsigned char *warm_dec, int stride, int *has_warm, cudaStream_t s);
@@ -86,6 +87,8 @@ void launch_bnb_tighten(const BnbState &st, const double *ub, cudaStream_t s);  
 void launch_bnb_finish(const BnbState &st, const DevProb *probs, const double *dblob, const int *iblob,
                        double *xall, double *best_bound, cudaStream_t s);
 int node_kernel_smem_per_warp(int maxN, int kmax, int ndec_stride);
+int node_kernel_narrow_np(int N);                                  // row stride of the (s, lambda) records of a two-warp team
+int node_kernel_smem_narrow(int N, int kmax, int ndec_stride);   // shared memory of a two-warp team (uniform horizon N)
 int node_kernel_max_ctas(int smem_per_cta, int threads);
 
 // ---- bnb_multi.cu ---------------------------------------------------------------------

@@ -39,8 +39,11 @@ constexpr unsigned FULL = 0xffffffffu;
 
 // per-stage shared-memory records (strides are odd so that lane = stage accesses are
 // bank-conflict free for 64-bit words)
-constexpr int S_STRIDE = 39;  // [0..20] Mxx packed lower, [21..32] G = Phi_ux (2x6), [33..35] Finv, [36..37] Muu diag
-constexpr int S_G = 21, S_FINV = 33, S_MUU = 36;
+// Stage record of the Riccati recursion.  The Hessian block Mxx (pass A) is dead once its stage has been factorised, and the
+// factors of the stage (G, Finv: read by the sweeps) take its place: 23 doubles per stage instead of 39 -- 5 kB less shared
+// memory per node at N = 40, which is what lets four two-warp teams share an SM.
+constexpr int S_STRIDE = 23;  // [0..20] Mxx packed lower (until the stage is factorised), then [0..11] G = Phi_ux (2x6), [12..14] Finv; [21..22] Muu diag
+constexpr int S_G = 0, S_FINV = 12, S_MUU = 21;
 constexpr int V_STRIDE = 35;  // z[8] g[8] dz[8] dza[8] k[2]
 constexpr int V_Z = 0, V_G = 8, V_DZ = 16, V_DZA = 24, V_K = 32;
 constexpr int T_P = 0, T_PV = 48, T_PUU = 60, T_PHIU = 63, T_SIZE = 66;  // warp scratch: 2 x P (24), 2 x p (6), Phi_uu (3), phi_u (2)
@@ -529,8 +532,9 @@ __device__ __forceinline__ void riccati_factor(const WarpCtx &w, const PhiEntry 
     const double phi1 = m1 + e1.eval(Pn);
     const double phi2 = m2 + e2.eval(Pn);
     const double phiv = fma(pcf[2], pn[prow0 + 2 < 6 ? prow0 + 2 : 5], fma(pcf[1], pn[prow0 + 1 < 6 ? prow0 + 1 : 5], fma(pcf[0], pn[prow0], gv)));
-    if (lane >= 21) Si[lane] = phi1;                       // G entries 21..31
-    if (lane == 0) Si[32] = phi2;                          // G entry 32
+    __syncwarp();                                          // every lane has read its Mxx entry: the record is reused for G
+    if (lane >= 21) Si[S_G + lane - 21] = phi1;            // G entries 0..10 (Phi entries 21..31)
+    if (lane == 0) Si[S_G + 11] = phi2;                    // G entry 11 (Phi entry 32)
     if (lane >= 1 && lane < 4) T[T_PUU + lane - 1] = phi2; // Phi_uu
     if (lane == 6 || lane == 7) T[T_PHIU + lane - 6] = phiv;
     __syncwarp();

@@ -87,6 +87,7 @@ struct MiqpB200Solver {
   DevBuf<unsigned long long> b_uid, b_keybuf, b_incuid, b_stats, b_prof;
   DevBuf<int> b_open, b_opencnt, b_free, b_freecnt, b_sel, b_selcnt, b_done, b_lock, b_ctrl, b_overflow;
   int smem_per_warp = 0, warps_per_cta = 4, ctas = 0, wide_ctas = 0;
+  int narrow_ctas = 0, smem_narrow = 0, narrow_np = 0, narrow_min = 0; long narrow_launches = 0;   // two-warp teams (throughput rounds)
   // CTA-per-node kernel for plans with several cars
   int n_single = 0, n_multi = 0, multi_threads = 64, multi_ctas = 0, multi_use_smem = 1;
   long multi_ws_bytes = 0;
@@ -107,6 +108,7 @@ struct MiqpB200Solver {
   std::vector<unsigned long long> h_stats;
   std::vector<int> h_done, h_overflow;
   std::vector<unsigned long long> h_incuid;
+  std::vector<double> h_z;                                     // compact results: incumbent trajectories
   int single_maxN = 2;
   size_t pool_budget = 0;
 };
@@ -208,11 +210,17 @@ int run_rounds(MiqpB200Solver *s, long max_rounds_now, double tlim, long &launch
     launches += 2;
     CK(cudaEventRecord(s->evr0, s->stream));
     if (s->n_single > 0) {
-      // fewer single-car nodes than wide teams fit (work count of the last round as the estimate): latency matters, not throughput
-      const bool wide = s->wide_ctas > 0 && rounds > 0 && ctrl[0] > 0 && ctrl[0] <= s->wide_ctas;
-      int rc = launch_bnb_nodes(s->st, s->d_probs.p, s->d_dblob.p, s->d_iblob.p, s->smem_per_warp,
-                                wide ? NODE_TEAM_WARPS_WIDE : s->warps_per_cta, wide ? s->wide_ctas : s->ctas, s->single_maxN,
-                                (int)rounds + 1, s->stream);
+      // fewer single-car nodes than wide teams fit (work count of the last round as the estimate): latency matters, not throughput;
+      // more than the four-warp teams hold at once: two-warp teams, twice as many nodes in flight
+      const int est = (rounds == 0) ? s->n_single : ctrl[0];
+      const bool wide = s->wide_ctas > 0 && rounds > 0 && est > 0 && est <= s->wide_ctas;
+      const bool narrow = !wide && s->narrow_ctas > 0 && est >= s->narrow_min;
+      int rc = narrow ? launch_bnb_nodes(s->st, s->d_probs.p, s->d_dblob.p, s->d_iblob.p, s->smem_narrow, NODE_TEAM_WARPS_NARROW,
+                                         s->narrow_ctas, s->single_maxN, s->narrow_np, (int)rounds + 1, s->stream)
+                      : launch_bnb_nodes(s->st, s->d_probs.p, s->d_dblob.p, s->d_iblob.p, s->smem_per_warp,
+                                         wide ? NODE_TEAM_WARPS_WIDE : s->warps_per_cta, wide ? s->wide_ctas : s->ctas, s->single_maxN,
+                                         s->single_maxN + 7, (int)rounds + 1, s->stream);
+      if (narrow) ++s->narrow_launches;
       if (rc != 0) throw std::runtime_error(std::string("node kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
       ++launches; ++node_launches;
     }
@@ -249,12 +257,12 @@ void setup_bnb(MiqpB200Solver *s) {
   st.kmax = pk.max_kmax;
   st.npad = ((pk.maxN + 31) / 32) * 32;
   // node kernel geometry: warp-per-node kernel for single-car plans, CTA-per-node kernel otherwise
-  int maxN1 = 0, kmax1 = 0, maxCm = 0;
+  int maxN1 = 0, minN1 = 1 << 30, kmax1 = 0, maxCm = 0;
   s->n_single = 0; s->n_multi = 0; s->multi_ws_bytes = 0;
   const char *fm = std::getenv("MIQP_B200_FORCE_MULTI");   // test hook: run single-car plans through the CTA-per-node kernel
   st.force_multi = (fm && fm[0] == '1') ? 1 : 0;
   for (const DevProb &p : pk.probs) {
-    if (p.C == 1 && !st.force_multi) { ++s->n_single; maxN1 = std::max(maxN1, p.N); kmax1 = std::max(kmax1, p.kmax); }
+    if (p.C == 1 && !st.force_multi) { ++s->n_single; maxN1 = std::max(maxN1, p.N); minN1 = std::min(minN1, p.N); kmax1 = std::max(kmax1, p.kmax); }
     else {
       ++s->n_multi; maxCm = std::max(maxCm, p.C);
       s->multi_ws_bytes = std::max(s->multi_ws_bytes, multi_workspace_bytes(p.C, p.N, p.P, p.kmax, st.ndec_stride));
@@ -273,6 +281,17 @@ void setup_bnb(MiqpB200Solver *s) {
     if (!getenv("MIQP_NO_WIDE_TEAM")) {
       const int wide_per_sm = node_kernel_max_ctas(s->smem_per_warp, NODE_TEAM_WARPS_WIDE * 32);
       if (wide_per_sm > 0) s->wide_ctas = wide_per_sm * s->num_sms;
+    }
+    // two-warp teams (four per SM) for rounds with many nodes; only when every single-car plan has the same horizon (the
+    // shared-memory layout then uses the row stride of that team size)
+    s->narrow_ctas = 0; s->narrow_launches = 0;
+    if (!getenv("MIQP_NO_NARROW_TEAM") && minN1 == maxN1) {
+      s->narrow_np = node_kernel_narrow_np(maxN1);
+      s->smem_narrow = node_kernel_smem_narrow(maxN1, st.kmax, st.ndec_stride);
+      const int narrow_per_sm = node_kernel_max_ctas(s->smem_narrow, NODE_TEAM_WARPS_NARROW * 32);
+      if (narrow_per_sm * NODE_TEAM_WARPS_NARROW > per_sm * NODE_TEAM_WARPS) s->narrow_ctas = narrow_per_sm * s->num_sms;   // only if more nodes fit
+      s->narrow_min = (s->ctas * 5) / 4;
+      if (const char *e = getenv("MIQP_NARROW_MIN")) s->narrow_min = atoi(e);
     }
     int fm = 1;
     if (const char *e = getenv("MIQP_FILL_MULT")) fm = std::max(1, atoi(e));
@@ -699,18 +718,38 @@ int miqp_b200_batch_run(MiqpB200Solver *s, float *device_ms) {
   return MIQP_B200_OK;
 }
 
-int miqp_b200_batch_fetch(MiqpB200Solver *s, double *const *x_out, MiqpB200SolveInfo *infos) {
+static int fetch_results(MiqpB200Solver *s, double *const *x_out, double *const *traj_out, MiqpB200SolveInfo *infos);
+int miqp_b200_batch_fetch(MiqpB200Solver *s, double *const *x_out, MiqpB200SolveInfo *infos) { return fetch_results(s, x_out, nullptr, infos); }
+int miqp_b200_batch_fetch_compact(MiqpB200Solver *s, double *const *traj_out, MiqpB200SolveInfo *infos) { return fetch_results(s, nullptr, traj_out, infos); }
+
+int miqp_b200_fetch_vector(MiqpB200Solver *s, int k, double *x_out) {
+  if (!s || !x_out) return MIQP_B200_ERR_ARG;
+  if (!s->ran || k < 0 || k >= s->st.count) return fail(s, MIQP_B200_ERR_ARG, "fetch_vector: no results for this plan index");
+  const DevProb &p = s->pk.probs[k];
+  if (cudaSetDevice(s->opt.device) != cudaSuccess ||
+      cudaMemcpyAsync(x_out, s->d_x.p + p.x_base, sizeof(double) * p.ncols, cudaMemcpyDeviceToHost, s->stream) != cudaSuccess ||
+      cudaStreamSynchronize(s->stream) != cudaSuccess) return fail(s, MIQP_B200_ERR_CUDA, "copy of the solution vector failed");
+  return MIQP_B200_OK;
+}
+
+// x_out: full OPL column vectors; traj_out (compact results): [C][N][8] per plan, the incumbent trajectories as bnb_finish_kernel
+// left them in inc_z.  Either may be null.
+static int fetch_results(MiqpB200Solver *s, double *const *x_out, double *const *traj_out, MiqpB200SolveInfo *infos) {
   if (!s) return MIQP_B200_ERR_ARG;
   if (!s->ran) return fail(s, MIQP_B200_ERR_ARG, "batch_fetch without batch_run");
   try {
     CK(cudaSetDevice(s->opt.device));
     const int count = s->st.count;
-    const long ncols = s->pk.total_cols;
+    const long ncols = x_out ? s->pk.total_cols : 0;
     const auto tf0 = std::chrono::steady_clock::now();
+    if (traj_out) {
+      s->h_z.resize((size_t)count * s->st.zstride);
+      CK(cudaMemcpyAsync(s->h_z.data(), s->st.inc_z, sizeof(double) * s->h_z.size(), cudaMemcpyDeviceToHost, s->stream));
+    }
     s->h_x.resize(ncols); s->h_viol.resize(count); s->h_obj.resize(count); s->h_bb.resize(count); s->h_ub.resize(count);
     s->h_stats.resize((size_t)4 * count); s->h_done.resize(count); s->h_overflow.resize(count); s->h_incuid.resize(count);
     CK(cudaMemcpyAsync(s->h_incuid.data(), s->st.inc_uid, sizeof(unsigned long long) * count, cudaMemcpyDeviceToHost, s->stream));
-    CK(cudaMemcpyAsync(s->h_x.data(), s->d_x.p, sizeof(double) * ncols, cudaMemcpyDeviceToHost, s->stream));
+    if (ncols > 0) CK(cudaMemcpyAsync(s->h_x.data(), s->d_x.p, sizeof(double) * ncols, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaMemcpyAsync(s->h_viol.data(), s->d_viol.p, sizeof(double) * count, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaMemcpyAsync(s->h_obj.data(), s->d_obj.p, sizeof(double) * count, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaMemcpyAsync(s->h_bb.data(), s->d_bb.p, sizeof(double) * count, cudaMemcpyDeviceToHost, s->stream));
@@ -719,7 +758,12 @@ int miqp_b200_batch_fetch(MiqpB200Solver *s, double *const *x_out, MiqpB200Solve
     CK(cudaMemcpyAsync(s->h_done.data(), s->st.done, sizeof(int) * count, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaMemcpyAsync(s->h_overflow.data(), s->st.overflow, sizeof(int) * count, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
-    s->stats.d2h_bytes = (long)(sizeof(double) * (ncols + 4 * count) + sizeof(unsigned long long) * 4 * count + 2 * sizeof(int) * count);
+    s->stats.d2h_bytes = (long)(sizeof(double) * (ncols + 4 * count + (traj_out ? s->h_z.size() : 0)) + sizeof(unsigned long long) * 5 * count + 2 * sizeof(int) * count);
+    if (traj_out)
+      for (int k = 0; k < count; ++k) {
+        const DevProb &p = s->pk.probs[k];
+        if (traj_out[k]) std::memcpy(traj_out[k], s->h_z.data() + (size_t)k * s->st.zstride, sizeof(double) * (size_t)p.C * p.N * 8);
+      }
     long nodes = 0, iters = 0, rows = 0;
     if (x_out) {   // scatter of the solution vectors into the caller's buffers: a few host threads for large batches
       const int nthr = (ncols * (long)sizeof(double) > (8L << 20)) ? 4 : 1;
@@ -770,6 +814,15 @@ int miqp_b200_batch_fetch(MiqpB200Solver *s, double *const *x_out, MiqpB200Solve
     return fail(s, MIQP_B200_ERR_CUDA, ex.what());
   }
   return MIQP_B200_OK;
+}
+
+int miqp_b200_solve_batch_compact(MiqpB200Solver *s, const MiqpB200Problem *problems, int count, const double *const *warm,
+                                  double *const *traj_out, MiqpB200SolveInfo *infos) {
+  int rc = miqp_b200_batch_upload(s, problems, count, warm);
+  if (rc != MIQP_B200_OK) return rc;
+  rc = miqp_b200_batch_run(s, nullptr);
+  if (rc != MIQP_B200_OK) return rc;
+  return miqp_b200_batch_fetch_compact(s, traj_out, infos);
 }
 
 int miqp_b200_solve_batch(MiqpB200Solver *s, const MiqpB200Problem *problems, int count, const double *const *warm,

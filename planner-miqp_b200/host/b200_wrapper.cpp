@@ -581,6 +581,8 @@ OptimizationStatus B200Wrapper::callCplex(double timestamp) {
   return Finish(pr, info, x.data(), timestamp);
 }
 
+long B200Wrapper::deviceWarmstartBatches_ = 0;
+
 std::vector<OptimizationStatus> B200Wrapper::callBatch(const std::vector<B200Wrapper *> &solvers, double timestamp) {
   const int n = (int)solvers.size();
   std::vector<OptimizationStatus> out(n, FAILED_SEG_FAULT);
@@ -603,7 +605,21 @@ std::vector<OptimizationStatus> B200Wrapper::callBatch(const std::vector<B200Wra
     if (p.have_warm) { warm[j] = p.warm.data(); any_warm = true; }
   }
   std::vector<MiqpB200SolveInfo> infos(m);
-  const int rc = miqp_b200_solve_batch(lead->solver_, probs.data(), m, any_warm ? warm.data() : nullptr, xo.data(), infos.data());
+  // Receding-horizon replanning of the same planners in the same order: the MIP starts are the previous incumbents, shifted by one
+  // step on the device (miqp_b200_batch_upload_replan) -- the host-side shifted vectors (CalculateWarmstart) are not sent.
+  std::vector<B200Wrapper *> members(m);
+  bool all_warm = true;
+  for (int j = 0; j < m; ++j) { members[j] = solvers[idx[j]]; all_warm = all_warm && pr[idx[j]].have_warm; }
+  int rc;
+  if (lead->deviceWarmstart_ && all_warm && m > 1 && lead->lastBatch_ == members) {
+    rc = miqp_b200_batch_upload_replan(lead->solver_, probs.data(), m);
+    if (rc == MIQP_B200_OK) rc = miqp_b200_batch_run(lead->solver_, nullptr);
+    if (rc == MIQP_B200_OK) rc = miqp_b200_batch_fetch(lead->solver_, xo.data(), infos.data());
+    if (rc == MIQP_B200_OK) ++deviceWarmstartBatches_;
+  } else {
+    rc = miqp_b200_solve_batch(lead->solver_, probs.data(), m, any_warm ? warm.data() : nullptr, xo.data(), infos.data());
+  }
+  lead->lastBatch_ = (rc == MIQP_B200_OK) ? members : std::vector<B200Wrapper *>();
   if (rc != MIQP_B200_OK) {
     const char *e = miqp_b200_last_error(lead->solver_);
     for (int k : idx) solvers[k]->error_ = e ? e : "device solve failed";

@@ -96,6 +96,10 @@ class B200Wrapper {
   OptimizationStatus callCplex(double timestamp = 0.0);
   // the same for many independent problems in ONE device batch (multi-scenario dispatch)
   static std::vector<OptimizationStatus> callBatch(const std::vector<B200Wrapper *> &solvers, double timestamp = 0.0);
+  // callBatch of the same solvers in the same order with receding-horizon warm starts: the previous incumbents are shifted on the
+  // device instead of sending the host-side shifted vectors (on by default; off = always the host path of callCplex)
+  void setDeviceWarmstart(bool on) { deviceWarmstart_ = on; }
+  static long deviceWarmstartBatches() { return deviceWarmstartBatches_; }   // batches that took the device path so far
 
   std::shared_ptr<RawResults> getRawResults() const { return results_; }
   // injects a solution vector as if a solve had returned it (replay of recorded solutions, tests of the warm-start logic)
@@ -124,6 +128,9 @@ class B200Wrapper {
   std::string tmpWarmstartFile_ = "/tmp/warmstart_debug_res.mst";
   // MIP starts
   std::shared_ptr<RawResults> recedingWarm_;
+  bool deviceWarmstart_ = true;
+  std::vector<B200Wrapper *> lastBatch_;      // members of the last successful batch run on this solver's handle
+  static long deviceWarmstartBatches_;
   bool useRecedingWarm_ = false, useLastSolution_ = false;
   std::vector<double> lastX_;           // last solution vector (the ".mst" of the reference)
   MiqpB200Layout lastLayout_{};

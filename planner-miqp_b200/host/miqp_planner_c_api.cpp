@@ -152,6 +152,8 @@ int PlanBatchCMiqpPlanner(CMiqpPlanner *planners, int count, const double timest
   return n;
 }
 
+long DeviceWarmstartBatchesCMiqpPlanner() { return miqp::planner::cplex::B200Wrapper::deviceWarmstartBatches(); }
+
 void GetSolutionPropertiesCMiqpPlanner(CMiqpPlanner h, double out[8]) {
   const miqp::planner::SolutionProperties s = P(h)->GetSolutionProperties();
   out[0] = s.objective; out[1] = s.gap; out[2] = s.time; out[3] = s.status; out[4] = (double)s.NrNodes;

@@ -18,7 +18,7 @@ C_API_SYMBOLS = [
     "UpdateConvexifiedMapCMiqpPlaner", "UpdateDesiredVelocityCMiqpPlanner", "AddObstacleCMiqpPlanner",
     "UpdateObstacleCMiqpPlanner", "RemoveAllObstaclesCMiqpPlanner",
     # additions of this backend
-    "PlanBatchCMiqpPlanner", "GetSolutionPropertiesCMiqpPlanner",
+    "PlanBatchCMiqpPlanner", "GetSolutionPropertiesCMiqpPlanner", "DeviceWarmstartBatchesCMiqpPlanner",
 ]
 
 
@@ -233,6 +233,12 @@ class CMiqpPlanner:
 
     def write_parameters(self, path: str) -> bool:
         return bool(self.lib.DebugWriteParametersCMiqpPlanner(self.h, path.encode(), 0))
+
+
+def device_warmstart_batches() -> int:
+    lib = load_library()
+    lib.DeviceWarmstartBatchesCMiqpPlanner.restype = C.c_long
+    return int(lib.DeviceWarmstartBatchesCMiqpPlanner())
 
 
 def plan_batch(planners, t=0.0):

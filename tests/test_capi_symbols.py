@@ -48,6 +48,6 @@ def test_every_function_declared_in_the_headers_is_exported():
     assert sorted(names) == sorted(P.DECLARED_SYMBOLS)
     text = re.sub(r"/\*.*?\*/", "", open(os.path.join(inc, "miqp_planner_c_api.h")).read(), flags=re.S)
     names = sorted(set(re.findall(r"\b(\w+CMiqpPlan\w*|GetCollisionRadius)\s*\(", text)))
-    assert len(names) == 19, names
+    assert len(names) == 20, names
     for n in names:
         assert hasattr(planner, n), n

@@ -153,3 +153,31 @@ def test_two_cars_receding_horizon():
             p.update_car(idx, [t[1, 1], t[1, 3], t[1, 5], t[1, 2], t[1, 4], t[1, 6]], ref)
     assert x1[0] < x1[-1] and x2[0] > x2[-1]
     p.close()
+
+
+def test_batched_receding_horizon_uses_the_device_warm_start():
+    """PlanBatch of the same planners, cycle after cycle, with RECEDING_HORIZON_WARMSTART: from the second cycle on the MIP starts
+    are the previous incumbents shifted on the device (no host warm-start vectors); results equal cold planners within the gap"""
+    def make(k, warm):
+        p = _planner_with_map(warm=warm, regions=32)
+        p.add_car([0, 4.5 + 0.3 * k, 0, 0.2 * k, 0.1, 0], [0, 0, 100, 0], 6, 1)
+        p.add_obstacle([[[18 + k, -2.5], [21 + k, -2.5], [21 + k, 0.5], [18 + k, 0.5]]] * p.N, is_static=True)
+        return p
+    n = 5
+    warm = [make(k, 1) for k in range(n)]
+    cold = [make(k, 0) for k in range(n)]
+    before = PC.device_warmstart_batches()
+    for cycle in range(4):
+        assert PC.plan_batch(warm, cycle * 0.25) == [True] * n
+        assert PC.plan_batch(cold, cycle * 0.25) == [True] * n
+        for k in range(n):
+            pw, pc = warm[k].solution_properties(), cold[k].solution_properties()
+            assert pw["objective"] == pytest.approx(pc["objective"], rel=2e-4)
+            t = warm[k].trajectory(0)
+            state = [t[1, 1], t[1, 3], t[1, 5], t[1, 2], t[1, 4], t[1, 6]]
+            for p in (warm[k], cold[k]):
+                p.update_car(0, state, [0, 0, 100, 0], (cycle + 1) * 0.25)
+    # cycles 2-4 of the warm planners went through miqp_b200_batch_upload_replan
+    assert PC.device_warmstart_batches() - before == 3
+    for p in warm + cold:
+        p.close()

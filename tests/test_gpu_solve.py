@@ -101,3 +101,56 @@ def test_infeasible_plan_reports_no_solution(solver, testcase_problem):
     assert info.status == 1 and np.isnan(info.objective)
     xo, io = O.solve(q, gap_tol=1e-4, time_limit=30)
     assert io.status == 1
+
+
+def test_compact_results_equal_the_trajectory_blocks_of_the_full_vector(testcase_problem):
+    """miqp_b200_batch_fetch_compact / fetch_vector: [C][N][8] trajectories = the pos / vel / acc / u blocks of the RawResults vector"""
+    from planner_miqp_b200.scenarios import obstacle_scenario, parallel_lanes
+    from planner_miqp_b200.results import block_views
+    ps = [testcase_problem, obstacle_scenario(3).build(), parallel_lanes(2, 5, 4.5).build()]
+    s = P.Solver()
+    s.upload(ps, gap_tol=1e-4, time_limit=60)
+    s.run()
+    tr, infos_c = s.fetch_compact()
+    xs, infos = s.fetch()
+    d2h_full = s.run_stats()["d2h_bytes"]
+    for k, (p, x) in enumerate(zip(ps, xs)):
+        assert infos[k].status == 0 and infos_c[k].objective == infos[k].objective and infos_c[k].gap == infos[k].gap
+        v = block_views(p, x)
+        for t, name in enumerate(("pos_x", "vel_x", "acc_x", "pos_y", "vel_y", "acc_y", "u_x", "u_y")):
+            assert np.array_equal(tr[k][:, :, t], v[name]), (k, name)
+        assert np.array_equal(s.fetch_vector(k), x)
+    s.fetch_compact()
+    assert s.run_stats()["d2h_bytes"] < d2h_full / 4
+    # the one-call form
+    prep = s.prepare(ps, gap_tol=1e-4, time_limit=60)
+    tr2, infos2 = s.solve_prepared_compact(prep)
+    assert all(np.array_equal(a, b) for a, b in zip(tr, tr2))
+    s.close()
+
+
+def test_two_warp_teams_give_the_same_results(testcase_problem, monkeypatch):
+    """the throughput variant of the node kernel (two warps per node, four teams per SM) is chosen for rounds with many nodes;
+    forced here for every round (MIQP_NARROW_MIN=1) and switched off (MIQP_NO_NARROW_TEAM): identical searches"""
+    from planner_miqp_b200.scenarios import obstacle_scenario
+    ps = [obstacle_scenario(k).build() for k in range(24)]
+    s = P.Solver()
+    monkeypatch.setenv("MIQP_NO_NARROW_TEAM", "1")
+    xs0, infos0 = s.solve_batch(ps, gap_tol=1e-4, time_limit=60)
+    monkeypatch.delenv("MIQP_NO_NARROW_TEAM")
+    monkeypatch.setenv("MIQP_NARROW_MIN", "1")
+    monkeypatch.setenv("MIQP_NO_WIDE_TEAM", "1")
+    xs1, infos1 = s.solve_batch(ps, gap_tol=1e-4, time_limit=60)
+    for a, b, xa, xb, p in zip(infos0, infos1, xs0, xs1, ps):
+        assert a.status == b.status == 0 and a.proven and b.proven
+        assert b.objective == pytest.approx(a.objective, rel=1e-9)
+        assert b.nodes == a.nodes                      # the search does not depend on the team size
+        np.testing.assert_allclose(xa, xb, atol=1e-6)
+        viol, _ = O.max_violation(p, xb)
+        assert viol <= 1e-6
+    # a different horizon in the same batch: the two-warp layout is not used, results unchanged
+    ps2 = ps[:4] + [testcase_problem]
+    xs2, infos2 = s.solve_batch(ps2, gap_tol=1e-4, time_limit=60)
+    assert [i.objective for i in infos2[:4]] == pytest.approx([i.objective for i in infos0[:4]], rel=1e-9)
+    assert abs(infos2[4].objective - 9.57603) < 1e-5
+    s.close()
