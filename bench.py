@@ -29,6 +29,11 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    # communicator lines ("... nranks N ... Init COMPLETE") go to stderr (fd 1 is redirected there, see emit()); NCCL reads the
+    # variable once, at the first library call, which torch makes on import: set it before
+    os.environ.setdefault("NCCL_DEBUG", "INFO")
+    os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
 
 import numpy as np  # noqa: E402
 
@@ -466,6 +471,7 @@ def main():
     ap.add_argument("--latency-plans", type=int, default=16)
     ap.add_argument("--replan-scenarios", type=int, default=256)
     ap.add_argument("--replan-cycles", type=int, default=8)
+    ap.add_argument("--first-shard", type=int, default=0, help="offset of the scenario shards (knobs are tuned on held-out shards >= 100, the reported runs use 0)")
     ap.add_argument("--skip-extras", action="store_true", help="only the throughput legs (no latency, replanning, assembly, CPU baseline): for A/B runs")
     ap.add_argument("--in-flight", type=int, default=2, help="batches in flight on one GPU (solver instances / streams); 1 = one at a time")
     args = ap.parse_args()
@@ -492,7 +498,7 @@ def main():
     import planner_miqp_b200 as P
     B = args.batch
     S = max(1, min(args.shards, args.steps))
-    shard_ids = [rank + k * world for k in range(S)]          # rank r: shards r, r + world, ...
+    shard_ids = [args.first_shard + rank + k * world for k in range(S)]          # rank r: shards r, r + world, ...
     solver = P.Solver(device=local_rank, nodes_per_round=args.nodes_per_round)
     shard_plans = {sid: make_plans(sid * B, B) for sid in shard_ids}
     prepared = {sid: solver.prepare(shard_plans[sid], gap_tol=GAP, time_limit=600.0) for sid in shard_ids}

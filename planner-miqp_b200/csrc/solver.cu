@@ -238,7 +238,7 @@ int run_rounds(MiqpB200Solver *s, long max_rounds_now, double tlim, long &launch
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, s->evr0, s->evr1));
     node_ms += ms;
-    if (s->opt.verbose > 1) fprintf(stderr, "[miqp_b200] round %ld: work %d active %d err %d node kernel %.3f ms\n", s->fr_rounds, ctrl[0], ctrl[2], ctrl[3], ms);
+    if (s->opt.verbose > 1) fprintf(stderr, "[miqp_b200] round %ld: work %d active %d err %d node kernel %.3f ms (narrow launches so far %ld)\n", s->fr_rounds, ctrl[0], ctrl[2], ctrl[3], ms, s->narrow_launches);
     if (ctrl[2] == 0) break;  // every plan finished
     const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - s->fr_t0).count();
     if (el > tlim) { s->timed_out = true; break; }
@@ -289,8 +289,8 @@ void setup_bnb(MiqpB200Solver *s) {
       s->narrow_np = node_kernel_narrow_np(maxN1);
       s->smem_narrow = node_kernel_smem_narrow(maxN1, st.kmax, st.ndec_stride);
       const int narrow_per_sm = node_kernel_max_ctas(s->smem_narrow, NODE_TEAM_WARPS_NARROW * 32);
-      if (narrow_per_sm * NODE_TEAM_WARPS_NARROW > per_sm * NODE_TEAM_WARPS) s->narrow_ctas = narrow_per_sm * s->num_sms;   // only if more nodes fit
-      s->narrow_min = (s->ctas * 5) / 4;
+      if (narrow_per_sm > per_sm) s->narrow_ctas = narrow_per_sm * s->num_sms;   // only if more nodes are in flight than with four-warp teams
+      s->narrow_min = 2 * s->ctas;   // between one and two waves of four-warp teams the two variants take the same time; the wider team has the lower latency
       if (const char *e = getenv("MIQP_NARROW_MIN")) s->narrow_min = atoi(e);
     }
     int fm = 1;
@@ -341,11 +341,12 @@ void setup_bnb(MiqpB200Solver *s) {
   if (st.warm_mu > 0.0 && s->n_single > 0) st.zp_stride = s->single_maxN * 8;
   if (cap <= 0) {
     const size_t node_bytes = (size_t)st.ndec_stride + 48 + (size_t)8 * st.zp_stride;
-    // pool budget: a third of the free HBM, at most 48 GiB (B200: 180 GB per GPU)
+    // pool budget: a quarter of the free HBM, at most 24 GiB (B200: 180 GB per GPU; several solver instances share a GPU when
+    // batches are pipelined: capi.PipelinedSolver)
     if (s->pool_budget == 0) {   // asked once per solver: cudaMemGetInfo costs about a millisecond
       size_t free_b = 0, total_b = 0;
       s->pool_budget = (size_t)8 << 30;
-      if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) s->pool_budget = std::min<size_t>(free_b / 3, (size_t)48 << 30);
+      if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) s->pool_budget = std::min<size_t>(free_b / 4, (size_t)24 << 30);
     }
     const size_t budget = s->pool_budget;
     size_t c = budget / (node_bytes * (size_t)count);
