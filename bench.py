@@ -473,7 +473,7 @@ def main():
     ap.add_argument("--replan-cycles", type=int, default=8)
     ap.add_argument("--first-shard", type=int, default=0, help="offset of the scenario shards (knobs are tuned on held-out shards >= 100, the reported runs use 0)")
     ap.add_argument("--skip-extras", action="store_true", help="only the throughput legs (no latency, replanning, assembly, CPU baseline): for A/B runs")
-    ap.add_argument("--in-flight", type=int, default=2, help="batches in flight on one GPU (solver instances / streams); 1 = one at a time")
+    ap.add_argument("--in-flight", type=int, default=3, help="batches in flight on one GPU (solver instances / streams); 1 = one at a time")
     args = ap.parse_args()
     args.batch_given = any(a == "--batch" or a.startswith("--batch=") for a in sys.argv[1:])
     if args.impl == "reference":
