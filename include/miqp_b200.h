@@ -99,7 +99,8 @@ typedef struct MiqpB200SolveInfo {
   int status;            /* MIQP_B200_SUCCESS / FAILED_NO_SOLUT / FAILED_TIMEOUT */
   int proven;            /* 1 if gap <= gap_tol was reached */
   double objective, best_bound, gap; /* gap = |best_bound-objective| / (1e-10+|objective|) */
-  double seconds;        /* wall time of the batch this plan was solved in */
+  double seconds;        /* solve time of THIS plan: host clock (from the start of the batch) at the end of the round after which the plan was
+                          * finished or hit its own time_limit; the batch's wall time for a plan that was stopped with the batch */
   double max_violation;  /* of the returned vector against the full big-M model, device-evaluated */
   long nodes, qp_iters, rounds;
   long uncertified;      /* node relaxations closed without optimum, feasible point or Farkas certificate; their bounds stay in best_bound */

@@ -72,7 +72,7 @@ __global__ void bnb_init_kernel(BnbState st, const DevProb *probs, const unsigne
     st.open_cnt[s] = nroot;
     st.sel_cnt[s] = 0;
     st.ub[s] = MQ_INF; st.cutoff[s] = MQ_INF; st.pruned_lb[s] = MQ_INF;
-    st.done[s] = 0; st.lock[s] = 0;
+    st.done[s] = 0; st.done_round[s] = -1; st.lock[s] = 0;
     st.stat_nodes[s] = 0; st.stat_iters[s] = 0; st.stat_rows[s] = 0; st.stat_uncert[s] = 0; st.overflow[s] = 0;
     st.inc_uid[s] = ~0ULL;
     if (s == 0) { *st.active_prev = 0; *st.work_cnt = 0; *st.work_next = 0; *st.active = 0; *st.err = 0; *st.work_cnt2 = 0; *st.work_next2 = 0; }
@@ -100,7 +100,7 @@ __device__ __forceinline__ int block_excl_scan(int flag, int *warp_tot /*[8]*/, 
   return off + pre;
 }
 
-__global__ void __launch_bounds__(SEL_THREADS) bnb_select_kernel(BnbState st, const DevProb *probs, int round) {
+__global__ void __launch_bounds__(SEL_THREADS) bnb_select_kernel(BnbState st, const DevProb *probs, int round, double elapsed_s) {
   const int s = blockIdx.x;
   const int tid = threadIdx.x;
   __shared__ int warp_tot[SEL_THREADS / 32];
@@ -109,6 +109,10 @@ __global__ void __launch_bounds__(SEL_THREADS) bnb_select_kernel(BnbState st, co
   __shared__ double s_pruned[SEL_THREADS / 32];
   __shared__ unsigned long long s_prefix; __shared__ int s_remaining;
   if (st.done[s]) return;
+  if (st.tlimit && elapsed_s > st.tlimit[s]) {   // this plan's own time limit (max_solution_time): it stops with what it has
+    if (tid == 0) { st.done[s] = 2; st.done_round[s] = round - 1; st.sel_cnt[s] = 0; }
+    return;
+  }
   const DevProb &p = probs[s];
   const long pb = (long)s * st.cap;
   const int KS = st.sel_per_plan;   // stride of sel_idx = largest number of nodes a plan may take per round
@@ -232,7 +236,7 @@ __global__ void __launch_bounds__(SEL_THREADS) bnb_select_kernel(BnbState st, co
     st.sel_cnt[s] = nsel_total;
     st.free_cnt[s] = s_free;
     st.cutoff[s] = cutoff;
-    if (nsel_total == 0) st.done[s] = 1;  // frontier exhausted (everything pruned or solved)
+    if (nsel_total == 0) { st.done[s] = 1; st.done_round[s] = round - 1; }  // frontier exhausted (everything pruned or solved) after the last round
     else { atomicAdd(st.active, 1); s_wbase = atomicAdd((p.C > 1 || st.force_multi) ? st.work_cnt2 : st.work_cnt, nsel_total); }
   }
   __syncthreads();
@@ -245,9 +249,9 @@ __global__ void __launch_bounds__(SEL_THREADS) bnb_select_kernel(BnbState st, co
 
 __global__ void bnb_round_reset_kernel(BnbState st) { if (st.susp_cnt) *st.susp_cnt = 0; *st.active_prev = *st.active; *st.work_cnt = 0; *st.work_next = 0; *st.active = 0; *st.work_cnt2 = 0; *st.work_next2 = 0; }
 
-void launch_bnb_select(const BnbState &st, const DevProb *probs, int round, cudaStream_t s) {
+void launch_bnb_select(const BnbState &st, const DevProb *probs, int round, double elapsed_s, cudaStream_t s) {
   bnb_round_reset_kernel<<<1, 1, 0, s>>>(st);
-  bnb_select_kernel<<<st.count, SEL_THREADS, 0, s>>>(st, probs, round);
+  bnb_select_kernel<<<st.count, SEL_THREADS, 0, s>>>(st, probs, round, elapsed_s);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -51,7 +51,9 @@ struct BnbState {
   double *ub;           // incumbent objective (inf if none)
   double *cutoff;       // snapshot used by the node kernel in the current round
   double *pruned_lb;
-  int *done;
+  int *done;               // 0 searching, 1 finished (frontier exhausted within the gap), 2 stopped at its own time limit
+  int *done_round;         // round in which the plan finished (its solve time = the host's clock at that round)
+  const double *tlimit;    // per-plan time limits in seconds (device copy)
   int *lock;
   double *inc_z;        // [count][zstride]
   unsigned char *inc_dec;  // [count][ndec_stride]
@@ -68,7 +70,7 @@ struct BnbState {
 
 void launch_bnb_init(const BnbState &st, const DevProb *probs, const unsigned char *warm_dec /* [count][ndec_stride] or null */,
                      const int *has_warm, cudaStream_t s);
-void launch_bnb_select(const BnbState &st, const DevProb *probs, int round, cudaStream_t s);
+void launch_bnb_select(const BnbState &st, const DevProb *probs, int round, double elapsed_s, cudaStream_t s);
 constexpr int NODE_TEAM_WARPS = 4;        // warps that share one node relaxation (bnb_nodes_kernel), 2 teams per SM
 #ifndef MQ_TEAMS_PER_SM
 #define MQ_TEAMS_PER_SM 2

@@ -97,6 +97,7 @@ struct MiqpB200Solver {
   long fr_rounds = 0; int fr_ctrl0 = 0;                       // rounds run so far / work items of the last round
   std::chrono::steady_clock::time_point fr_t0;                // start of the current run (time limit)
   long fr_launches = 0, fr_node_launches = 0; double fr_node_ms = 0.0;
+  DevBuf<int> b_doneround; DevBuf<double> d_tlimit; std::vector<double> round_elapsed; std::vector<int> h_doneround;   // per-plan solve times and limits
   DevBuf<unsigned char> d_prev_dec; DevBuf<double> d_prev_ub; DevBuf<unsigned long long> d_prev_uid; DevBuf<int> d_same;   // previous cycle (replan)
   DevBuf<unsigned long long> d_fp;                            // open-list fingerprints (frontier sharding)
   DevBuf<double> d_ubx;                                       // incumbent objectives exchanged between ranks (frontier sharding)
@@ -206,7 +207,9 @@ int run_rounds(MiqpB200Solver *s, long max_rounds_now, double tlim, long &launch
   for (;;) {
     if (max_rounds_now >= 0 && done_now >= max_rounds_now) break;
     const long rounds = s->fr_rounds;
-    launch_bnb_select(s->st, s->d_probs.p, (int)rounds + 1, s->stream);
+    const double el0 = std::chrono::duration<double>(std::chrono::steady_clock::now() - s->fr_t0).count();
+    if ((size_t)rounds >= s->round_elapsed.size()) s->round_elapsed.resize(rounds + 64, 0.0);
+    launch_bnb_select(s->st, s->d_probs.p, (int)rounds + 1, el0, s->stream);
     launches += 2;
     CK(cudaEventRecord(s->evr0, s->stream));
     if (s->n_single > 0) {
@@ -241,6 +244,7 @@ int run_rounds(MiqpB200Solver *s, long max_rounds_now, double tlim, long &launch
     if (s->opt.verbose > 1) fprintf(stderr, "[miqp_b200] round %ld: work %d active %d err %d node kernel %.3f ms (narrow launches so far %ld)\n", s->fr_rounds, ctrl[0], ctrl[2], ctrl[3], ms, s->narrow_launches);
     if (ctrl[2] == 0) break;  // every plan finished
     const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - s->fr_t0).count();
+    s->round_elapsed[rounds] = el;   // (rounds = index of the round that just ended, counted from 0)
     if (el > tlim) { s->timed_out = true; break; }
     if (s->opt.max_rounds > 0 && s->fr_rounds >= s->opt.max_rounds) { s->timed_out = true; break; }
   }
@@ -388,6 +392,9 @@ void setup_bnb(MiqpB200Solver *s) {
   s->b_cutoff.ensure(count); st.cutoff = s->b_cutoff.p;
   s->b_pruned.ensure(count); st.pruned_lb = s->b_pruned.p;
   s->b_done.ensure(count); st.done = s->b_done.p;
+  s->b_doneround.ensure(count); st.done_round = s->b_doneround.p;
+  s->d_tlimit.ensure(count); st.tlimit = s->d_tlimit.p;
+  CK(cudaMemcpyAsync(s->d_tlimit.p, s->time_limits.data(), sizeof(double) * count, cudaMemcpyHostToDevice, s->stream));
   s->b_lock.ensure(count); st.lock = s->b_lock.p;
   s->b_incz.ensure((size_t)count * st.zstride); st.inc_z = s->b_incz.p;
   s->b_incdec.ensure((size_t)count * st.ndec_stride); st.inc_dec = s->b_incdec.p;
@@ -757,6 +764,8 @@ static int fetch_results(MiqpB200Solver *s, double *const *x_out, double *const 
     CK(cudaMemcpyAsync(s->h_ub.data(), s->st.ub, sizeof(double) * count, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaMemcpyAsync(s->h_stats.data(), s->b_stats.p, sizeof(unsigned long long) * 4 * count, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaMemcpyAsync(s->h_done.data(), s->st.done, sizeof(int) * count, cudaMemcpyDeviceToHost, s->stream));
+    s->h_doneround.resize(count);
+    CK(cudaMemcpyAsync(s->h_doneround.data(), s->st.done_round, sizeof(int) * count, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaMemcpyAsync(s->h_overflow.data(), s->st.overflow, sizeof(int) * count, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     s->stats.d2h_bytes = (long)(sizeof(double) * (ncols + 4 * count + (traj_out ? s->h_z.size() : 0)) + sizeof(unsigned long long) * 5 * count + 2 * sizeof(int) * count);
@@ -789,7 +798,10 @@ static int fetch_results(MiqpB200Solver *s, double *const *x_out, double *const 
       std::memset(&in, 0, sizeof in);
       // (a finite bound without an incumbent of its own: the objective came from another rank, frontier sharding)
       const bool have = std::isfinite(s->h_ub[k]) && s->h_incuid[k] != ~0ULL;
-      in.seconds = s->last_seconds;
+      // solve time of THIS plan: the host's clock at the end of the round after which it was finished (the batch's time for a
+      // plan that was still searching when the batch stopped)
+      const int dr = s->h_doneround[k];
+      in.seconds = (s->h_done[k] && dr >= 1 && (size_t)(dr - 1) < s->round_elapsed.size() && s->round_elapsed[dr - 1] > 0.0) ? s->round_elapsed[dr - 1] : s->last_seconds;
       in.nodes = (long)s->h_stats[k]; in.qp_iters = (long)s->h_stats[count + k]; in.rounds = s->stats.rounds;
       in.best_bound = s->h_bb[k];
       in.uncertified = (long)s->h_stats[3 * (size_t)count + k];
@@ -805,7 +817,7 @@ static int fetch_results(MiqpB200Solver *s, double *const *x_out, double *const 
         in.proven = (in.gap <= p.gap_tol + 1e-15) ? 1 : 0;
       } else {
         // no incumbent: the reference reports FAILED_TIMEOUT only for the time-limit status
-        in.status = (s->timed_out && !s->h_done[k]) ? MIQP_B200_FAILED_TIMEOUT : MIQP_B200_FAILED_NO_SOLUT;
+        in.status = ((s->timed_out && !s->h_done[k]) || s->h_done[k] == 2) ? MIQP_B200_FAILED_TIMEOUT : MIQP_B200_FAILED_NO_SOLUT;
         in.objective = NAN; in.gap = NAN; in.max_violation = NAN;
       }
     }

@@ -100,3 +100,28 @@ def test_parked_relaxations_do_not_change_the_result(testcase_problem, monkeypat
         results[budget] = [i.objective for i in infos]
     for a, b, c in zip(results["0"], results["3"], results["10"]):
         assert b == pytest.approx(a, rel=2 * GAP) and c == pytest.approx(a, rel=2 * GAP)
+
+
+def test_time_limit_and_solve_time_are_per_plan():
+    """every plan stops at its OWN time limit (max_solution_time) and reports its own solve time, not the batch's
+    (reference: one cplex.solve() per plan with CPX_PARAM_TILIM, src/cplex_wrapper.cpp:158-185)"""
+    import copy
+    from planner_miqp_b200.scenarios import obstacle_scenario, two_agent_merge
+    easy = [obstacle_scenario(k).build() for k in range(6)]
+    hard = two_agent_merge(0).build()            # does not prove 1e-4 within seconds
+    hard.scal = dict(hard.scal); hard.scal["max_solution_time"] = 0.4
+    for p in easy:
+        p.scal = dict(p.scal); p.scal["max_solution_time"] = 30.0
+    s = P.Solver()
+    import time
+    t0 = time.perf_counter()
+    xs, infos = s.solve_batch(easy + [hard], gap_tol=1e-4)
+    wall = time.perf_counter() - t0
+    s.close()
+    assert wall < 5.0                                             # the batch does not wait for the largest limit
+    for i in infos[:6]:
+        assert i.status == 0 and i.proven and 0.0 < i.seconds < 0.4
+    h = infos[6]
+    assert not h.proven and 0.4 <= h.seconds < 2.0
+    assert h.status in (0, 3)                                     # incumbent found, or FAILED_TIMEOUT without one
+    assert len({round(i.seconds, 6) for i in infos}) > 1          # not one number for the whole batch
