@@ -137,10 +137,12 @@ def cpu_oracle_rate(plans, threads: int):
 
 
 def bench_config(B: int) -> dict:
-    """The `config` object of both arms (the reference arm times bounded samples of the same workload)."""
+    """The `config` object, identical in both arms (the reference arm times bounded samples of the same workload); what is
+    specific to a run (batches in flight, timing, cache handling of the leg that produced `value`) is in `run`."""
     return {"workload": WORKLOAD, "plans_per_gpu_per_step": B, "gap": GAP,
-            "seeds": "rank r, step k: shard (r + k * n_gpus) mod shards; shard s = scenario seeds s*B .. s*B+B-1",
-            "cache": "L2 flushed between steps (256 MiB write)"}
+            "seeds": "shard s = scenario seeds s*B .. s*B+B-1 of scenarios.obstacle_scenario; rank r works on shards r, r + n_gpus, ...",
+            "cache": "L2 flushed between steps (256 MiB write) when one batch runs at a time; batches in flight alternate over "
+                     "different resident batches whose combined footprint exceeds the 126 MB L2 (see `run`)"}
 
 
 def run_reference(args):
@@ -736,18 +738,22 @@ def main():
 
     shard_ms = {str(sid): {"min": min(v), "mean": sum(v) / len(v), "max": max(v), "steps": len(v)} for sid, v in per_shard.items() if v}
     cfg = bench_config(B)
-    cfg["nodes_per_plan_per_round"] = args.nodes_per_round or "auto"
-    cfg["batches_in_flight"] = args.in_flight if use_pipe else 1
+    run = {"nodes_per_plan_per_round": args.nodes_per_round or "auto", "batches_in_flight": args.in_flight if use_pipe else 1,
+           "first_shard": args.first_shard}
     if use_pipe:
-        cfg["cache"] = ("two solver instances alternate over different resident batches (combined footprint of problem data and node "
-                        "pools > 126 MB L2), no flush between overlapping steps; the one-batch-at-a-time leg flushes L2 (256 MiB write)")
-        cfg["seeds"] = "solver instance w holds shard (rank + w * n_gpus) resident and re-runs it (steps alternate over the instances); shard s = scenario seeds s*B .. s*B+B-1"
-        cfg["timing"] = "CUDA events on the solvers' own streams: first launch of the first step to the last completion on either stream"
+        run["seeds"] = "solver instance w holds shard (rank + w * n_gpus) resident and re-runs it (steps alternate over the instances)"
+        run["cache"] = "no flush between overlapping steps: the instances alternate over different resident batches (problem data + node pools > 126 MB L2)"
+        run["timing"] = "CUDA events on the solvers' own streams: first launch of the first step to the last completion on any stream, max over ranks"
+    else:
+        run["seeds"] = "step k of rank r: shard (r + k * n_gpus) mod shards"
+        run["cache"] = "L2 flushed between steps (256 MiB write)"
+        run["timing"] = "CUDA events on the solver stream around every miqp_b200_batch_run, summed, max over ranks"
     line = {
         "metric": "MIQP plans/sec at 1e-4 gap", "value": value, "unit": "plans/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": cfg,
+        "run": run,
         "clocks": clocks,
         "one_batch_at_a_time": {"value": value_seq, "ms_per_step": seq_ms_per_step, "e2e_value": e2e_seq, "e2e_ms_per_step": e2e_seq_ms,
                                 "e2e_full_vectors": {"value": e2e_full, "ms_per_step": e2e_full_ms, "d2h_bytes_per_step": d2h_full},

@@ -108,3 +108,83 @@ def test_cplex_wrapper_solves_the_reference_fixture(miqp):
     assert abs(sp.objective - 9.57603) <= 0.1 * 9.57603 and sp.gap <= 0.1 and sp.time > 0    # the file asks for a 10 % gap
     assert w.writeMIPStarts("/tmp/miqp_b200_pybind.mst") and w.readMIPStarts("/tmp/miqp_b200_pybind.mst")
     assert w.exportModel("/tmp/miqp_b200_pybind.lp") and os.path.getsize("/tmp/miqp_b200_pybind.lp") > 100000
+
+
+# ---- BehaviorMiqpAgent (host/behavior_miqp_agent.hpp: the planning cycle of src/behavior_miqp_agent.cpp:137-335 without BARK) ----
+ROAD = np.array([[-20.0, -6.0], [150.0, -6.0], [150.0, 6.0], [-20.0, 6.0]])
+LANE = np.array([[-20.0, 0.0], [150.0, 0.0]])
+
+
+def _world(t, ego, others=()):
+    return {"time": t, "road_polygon": ROAD,
+            "ego": {"id": 1, "state": ego, "length": 4.0, "width": 2.0, "lane_center": LANE},
+            "others": [{"id": 10 + k, "state": o, "length": 4.0, "width": 2.0, "lane_center": LANE + np.array([0.0, o[1]])}
+                       for k, o in enumerate(others)]}
+
+
+def test_behavior_agent_bookkeeping_and_failure_path(miqp):
+    """without a CUDA device Plan() cannot succeed: the agent must report it the way the reference does (status EXPIRED,
+    NaN solution time, the last trajectory -- src/behavior_miqp_agent.cpp:264-271) after having set up planner, map and obstacles"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("failure path needs a box without GPU")
+    a = miqp.BehaviorMiqpAgent({"Miqp::NrSteps": 10, "Miqp::NrRegions": 16, "Miqp::DesiredVelocity": 6.0})
+    assert a.behavior_status == miqp.BehaviorStatus.NOT_STARTED_YET
+    tr = a.Plan(0.25, _world(0.0, [0, 0, 0, 5, 0], others=[[25, 0, 0, 2, 0]]))
+    assert tr.shape == (0, 5) and not a.last_planning_success
+    assert a.behavior_status == miqp.BehaviorStatus.EXPIRED and np.isnan(a.last_solution_time)
+    assert a.car_idxs == {1: 0} and list(a.obstacle_ids) == [10]
+    np.testing.assert_allclose(a.env_polygon, ROAD)
+    # box environment (Miqp::UseBoxAsEnv): bounding box of an L-shaped road
+    b = miqp.BehaviorMiqpAgent({"Miqp::NrSteps": 10, "Miqp::UseBoxAsEnv": True})
+    w = _world(0.0, [0, 0, 0, 5, 0])
+    w["road_polygon"] = np.array([[0, 0], [40, 0], [40, 30], [30, 30], [30, 10], [0, 10.0]])
+    b.Plan(0.25, w)
+    np.testing.assert_allclose(b.env_polygon, [[0, 0], [40, 0], [40, 30], [0, 30]])
+
+
+@pytest.mark.gpu
+def test_behavior_agent_follows_and_overtakes_over_several_cycles(miqp):
+    """receding-horizon simulation: the ego (5 m/s) comes up behind a slow vehicle (2 m/s) that is predicted with constant
+    velocity; every cycle plans, the ego state moves to step 1 of the plan"""
+    a = miqp.BehaviorMiqpAgent({"Miqp::NrSteps": 20, "Miqp::NrRegions": 16, "Miqp::DesiredVelocity": 5.0, "Miqp::MaxSolutionTime": 5.0,
+                                "Miqp::RelativeMIPGapTolerance": 1e-3, "Miqp::WarmstartType": 1, "Miqp::ObstaclesSoft": False})
+    ego = [0.0, 0.0, 0.0, 5.0, 0.0]
+    other = [18.0, 0.5, 0.0, 2.0, 0.0]
+    dt = 0.25
+    min_gap = 1e9
+    for k in range(8):
+        tr = a.Plan(dt, _world(k * dt, ego, others=[other]))
+        assert a.last_planning_success and a.behavior_status == miqp.BehaviorStatus.VALID
+        assert tr.shape[1] == 5 and tr.shape[0] >= 2 and tr[0, 0] == pytest.approx(k * dt)
+        assert tr[0, 1] == pytest.approx(ego[0], abs=1e-3) and tr[0, 2] == pytest.approx(ego[1], abs=1e-3)
+        acc, delta = a.last_action
+        assert np.isfinite(acc) and np.isfinite(delta) and abs(delta) < 0.6
+        assert a.last_solution_time > 0 and a.obstacle_ids == {10: 0}
+        # predicted separation along the plan: rear-axle point stays out of the inflated box (collision radius 1 m)
+        for i in range(tr.shape[0]):
+            ox = other[0] + other[3] * dt * i
+            inside = abs(tr[i, 1] - ox) < 2.0 and abs(tr[i, 2] - other[1]) < 1.0
+            assert not inside
+            min_gap = min(min_gap, np.hypot(tr[i, 1] - ox, tr[i, 2] - other[1]))
+        accel = (tr[1, 4] - ego[3]) / dt
+        ego = [tr[1, 1], tr[1, 2], tr[1, 3], tr[1, 4], accel]
+        other = [other[0] + other[3] * dt, other[1], 0.0, other[3], 0.0]
+    assert ego[0] > 5.0 and min_gap > 1.0
+
+
+@pytest.mark.gpu
+def test_behavior_agent_multi_agent_planning(miqp):
+    """Miqp::MultiAgentPlanning: the other agent becomes a second car of the joint plan, re-added every cycle"""
+    a = miqp.BehaviorMiqpAgent({"Miqp::NrSteps": 8, "Miqp::NrRegions": 16, "Miqp::DesiredVelocity": 5.0, "Miqp::MaxSolutionTime": 5.0,
+                                "Miqp::RelativeMIPGapTolerance": 1e-2, "Miqp::MultiAgentPlanning": True})
+    ego = [0.0, -2.5, 0.0, 5.0, 0.0]
+    other = [2.0, 3.0, 0.0, 5.0, 0.0]
+    for k in range(3):
+        w = _world(k * 0.25, ego, others=[other])
+        w["ego"]["lane_center"] = LANE + np.array([0.0, -2.5])
+        tr = a.Plan(0.25, w)
+        assert a.last_planning_success, k
+        assert a.car_idxs == {1: 0, 10: 1} and a.obstacle_ids == {}
+        ego = [tr[1, 1], tr[1, 2], tr[1, 3], tr[1, 4], 0.0]
+        other = [other[0] + 5.0 * 0.25, other[1], 0.0, 5.0, 0.0]
