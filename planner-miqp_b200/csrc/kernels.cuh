@@ -27,6 +27,7 @@ struct BnbState {
   int sel_dive;         // nodes per plan per round while diving for the first incumbent
   int dive_fill;        // >0: while diving, widen to (resident warps / active plans) / dive_fill heads when few plans are active
   int wide_div;         // >0: a plan with an incumbent takes at least (open nodes below the cutoff) / wide_div nodes per round
+  int multi_plunge;                 // multi-car plans with an incumbent: dives of the preferred children every other round (1) or best bound only (0)
   int multi_heur;                   // multi-car plans without incumbent: completion heuristic at every multi_heur-th level of the tree (0: off)
   int dive_patience, dive_growth;   // a plan without incumbent after dive_patience rounds widens its dive by dive_growth heads per round
   int work_cap;

@@ -329,6 +329,8 @@ void setup_bnb(MiqpB200Solver *s) {
   if (const char *e = getenv("MIQP_DIVE_GROWTH")) st.dive_growth = atoi(e);
   st.multi_heur = 1;
   if (const char *e = getenv("MIQP_MULTI_HEUR")) st.multi_heur = atoi(e);
+  st.multi_plunge = 0;   // A/B on 512 config-4 plans, 2 s limit (profiles/r2_knobs_heldout.md): 3 hard plans more within 10 %, 11 fewer proven
+  if (const char *e = getenv("MIQP_MULTI_PLUNGE")) st.multi_plunge = atoi(e);
   int kscap = 64;
   // a few multi-car plans alone on the GPU (config 5: ONE joint plan): let a plan take as many nodes per round as CTAs are resident
   if (s->n_single == 0 && s->n_multi > 0) kscap = std::max(64, std::min(1024, st.nwarps / std::max(count, 1)));

@@ -32,7 +32,12 @@ struct Cmp {
       if (x.depth != y.depth) return x.depth > y.depth;
       return x.uid < y.uid;
     }
-    if (have_inc && policy >= 2) {   // best bound with plunging: the children of the last round first (least violated alternative first)
+    if (have_inc && policy == 3 && (round & 1)) {   // every other round: the preferred children of the last two rounds first (plunging), else best bound
+      const bool nx = (x.birth >= round - 2 && x.rank <= 0), ny = (y.birth >= round - 2 && y.rank <= 0);
+      if (nx != ny) return nx;
+      if (nx) { if (x.depth != y.depth) return x.depth > y.depth; if (x.bound != y.bound) return x.bound < y.bound; return x.uid < y.uid; }
+    }
+    if (have_inc && policy == 2) {   // best bound with plunging: the children of the last round first (least violated alternative first)
       const bool nx = (x.birth == round - 1), ny = (y.birth == round - 1);
       if (nx != ny) return nx;
       if (nx) { if (x.rank != y.rank) return x.rank < y.rank; if (x.bound != y.bound) return x.bound < y.bound; return x.uid < y.uid; }
