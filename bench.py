@@ -32,8 +32,10 @@ sys.path.insert(0, ROOT)
 if int(os.environ.get("WORLD_SIZE", "1")) > 1:
     # communicator lines ("... nranks N ... Init COMPLETE") go to stderr (fd 1 is redirected there, see emit()); NCCL reads the
     # variable once, at the first library call, which torch makes on import: set it before
-    os.environ.setdefault("NCCL_DEBUG", "INFO")
-    os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+    # (forced: the GPU boxes preset NCCL_DEBUG=VERSION, which prints the version line only)
+    if not os.environ.get("MIQP_BENCH_KEEP_NCCL_DEBUG"):
+        os.environ["NCCL_DEBUG"] = "INFO"
+        os.environ["NCCL_DEBUG_SUBSYS"] = "INIT"
 
 import numpy as np  # noqa: E402
 
@@ -255,7 +257,6 @@ def init_dist():
         raise SystemExit("bench.py needs a CUDA device: the MIQP backend has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "INFO")     # communicator lines go to stderr (fd 1 is redirected there, see emit())
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     return rank, local_rank, world
 
@@ -494,7 +495,6 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the MIQP backend has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "INFO")     # communicator lines go to stderr (fd 1 is redirected there, see emit())
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     import planner_miqp_b200 as P

@@ -626,10 +626,27 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? NODE_TEAMS_PER_SM : NW == 2
     sio.resume = nullptr; sio.pool = nullptr; sio.counter = st.susp_cnt; sio.nslots = st.susp_slots; sio.stride = st.susp_stride; sio.budget = st.susp_budget;
     if (st.susp_slot) {
       const int ss = st.susp_slot[pb + slot];
-      if (ss >= 0) sio.resume = st.susp_pool[(round + 1) & 1] + (long)ss * st.susp_stride;   // parked by the previous round
+      if (ss >= 0 && ss != SUSP_REQUEUE) sio.resume = st.susp_pool[(round + 1) & 1] + (long)ss * st.susp_stride;   // parked by the previous round
       sio.pool = st.susp_pool[round & 1];
     }
     QpResult r = solve_node_qp(w, e1, e2, zw, st.warm_mu, sio);
+    // A relaxation that stalls from the parent's optimum (or after it was parked) with a feasible point well above its Lagrangian
+    // bound goes back to the open list and is solved from the cold start in the next round: a stalled leaf otherwise leaves a
+    // slightly suboptimal incumbent behind (scenario seed 4774: 11.8390 instead of 11.8211, reported unproven), and the cold start
+    // converges where the warm one does not.  The slot is protected like a parked one (mark SUSP_REQUEUE); the NaN in its copy of
+    // the parent's optimum makes the next solve a cold one, which is final.
+    if (st.susp_slot && zw != nullptr &&
+        ((r.status == 4) || (r.status == 0 && !r.converged && !(r.obj - r.lb <= 0.25 * p.gap_tol * fabs(r.obj))))) {
+      if (threadIdx.x == 0) {
+        st.zpool[(pb + slot) * (long)st.zp_stride] = __longlong_as_double(0x7ff8000000000000LL);
+        st.susp_slot[pb + slot] = SUSP_REQUEUE;
+        const int opos = atomicAdd(&st.open_cnt[s], 1);
+        st.open_idx[pb + opos] = slot;
+        atomicAdd(&st.stat_iters[s], (unsigned long long)r.iters);
+        atomicAdd(&st.stat_rows[s], (unsigned long long)r.rows);
+      }
+      continue;
+    }
     if (r.status == 3) {
       // parked: the node stays open (its bound still counts) and continues in the next round
       if (threadIdx.x == 0) {

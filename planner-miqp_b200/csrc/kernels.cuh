@@ -72,6 +72,7 @@ struct BnbState {
 void launch_bnb_init(const BnbState &st, const DevProb *probs, const unsigned char *warm_dec /* [count][ndec_stride] or null */,
                      const int *has_warm, cudaStream_t s);
 void launch_bnb_select(const BnbState &st, const DevProb *probs, int round, double elapsed_s, cudaStream_t s);
+constexpr int SUSP_REQUEUE = 1 << 30;      // susp_slot mark of a node that is solved again from the cold start (keeps its slot like a parked one)
 constexpr int NODE_TEAM_WARPS = 4;        // warps that share one node relaxation (bnb_nodes_kernel), 2 teams per SM
 #ifndef MQ_TEAMS_PER_SM
 #define MQ_TEAMS_PER_SM 2

@@ -125,3 +125,19 @@ def test_time_limit_and_solve_time_are_per_plan():
     assert not h.proven and 0.4 <= h.seconds < 2.0
     assert h.status in (0, 3)                                     # incumbent found, or FAILED_TIMEOUT without one
     assert len({round(i.seconds, 6) for i in infos}) > 1          # not one number for the whole batch
+
+
+def test_stalled_leaf_is_resolved_from_the_cold_start():
+    """scenario seed 4774 (bench shard 2): the interior-point solve of the optimal leaf stalls when it starts from the parent's
+    optimum; it is re-queued and solved from the cold start, so the plan ends at the optimum the oracle proves instead of an
+    incumbent 1.5e-3 above it that cannot be proven"""
+    p = obstacle_scenario(4774).build()
+    s = P.Solver()
+    x, info = s.solve(p, gap_tol=1e-4, time_limit=60)
+    s.close()
+    xo, io = O.solve(p, gap_tol=1e-4, time_limit=60)
+    assert io.status == 0 and io.proven
+    assert info.status == 0 and info.proven and info.uncertified == 0
+    assert info.objective == pytest.approx(io.objective, rel=1e-6)
+    viol, _ = O.max_violation(p, x)
+    assert viol <= 1e-6
