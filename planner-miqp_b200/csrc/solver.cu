@@ -53,6 +53,10 @@ struct DevBuf {
     n = count;
   }
   void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  ~DevBuf() { release(); }   // (every buffer of a solver goes with it, also those miqp_b200_destroy does not list)
 };
 
 }  // namespace
