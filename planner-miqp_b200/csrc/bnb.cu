@@ -538,7 +538,7 @@ struct NodeSmem { int off_rows, off_int, off_dec, total; };
 // np: bound of the padded stage stride of the (s, lambda) records (team_row_stride; maxN + 7 covers every team size)
 __host__ __device__ inline NodeSmem node_smem_layout(int maxN, int kmax, int ndec_stride, int np) {
   NodeSmem L;
-  int b = (maxN * (S_STRIDE + V_STRIDE + 1) + T_SIZE) * 8;
+  int b = (maxN * (S_STRIDE + V_STRIDE + 1 + 12) + T_SIZE) * 8;   // S, V, auxd, bnd (12 bound rows per stage), T
   b = (b + 15) & ~15;
   L.off_rows = b;   // (s, lambda) records: see RowIO (node_qp.cuh)
   b += (kmax + 1) * np * 16;
@@ -580,6 +580,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? NODE_TEAMS_PER_SM : NW == 2
   w.V = w.S + maxN * S_STRIDE;
   w.T = w.V + maxN * V_STRIDE;
   w.auxd = w.T + T_SIZE;
+  w.bnd = w.auxd + maxN; w.NB = maxN;
   w.rows = reinterpret_cast<double2 *>(base + L.off_rows);
   w.jeff = reinterpret_cast<int *>(base + L.off_int);
   w.aux = w.jeff + maxN;
@@ -612,6 +613,8 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? NODE_TEAMS_PER_SM : NW == 2
       nsoft = warp_sum_i(nsoft);
       pen = nsoft * p.w_slack_obs;
     }
+    __syncthreads();
+    fill_stage_bounds(w);
     __syncthreads();
 
     PhiEntry e1, e2;

@@ -74,6 +74,8 @@ struct WarpCtx {
   int *jeff;            // effective region per stage (-1 unknown)
   int *aux;             // [3N] scan tables: best alt, region_decided, blame
   double *auxd;         // [N] scan: best non-frozen violation
+  double *bnd;          // [12][NB] bound rows of the node: hi / lo of vx, ax, vy, ay, ux, uy per stage (+-INF: no row); filled once per node
+  int NB;               // stage stride of bnd
   double *T;            // [T_SIZE] Riccati scratch (value function of the next stage)
   double2 *rows;        // [kmax+1][NP] (s, lambda) per inequality row
   double *red;          // [8][4] team reduction scratch
@@ -182,6 +184,26 @@ __device__ __forceinline__ void stage_bounds(const WarpCtx &w, int i, int je, bo
   }
 }
 
+// bound rows of every stage of the node in slot order (hi, lo of vx, ax, vy, ay, ux, uy); a row that does not exist (no state
+// rows at stage 0, no input rows at the last stage, an infinite bound) is stored as +-INF.  Called by the whole team once per node.
+__device__ __forceinline__ void fill_stage_bounds(const WarpCtx &w) {
+  const DevProb &p = *w.p;
+  const int N = w.N;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const unsigned char m = (i > 0) ? w.dec[p.off_mode + i] : (unsigned char)0;
+    double lo[8], hi[8];
+    stage_bounds(w, i, w.jeff[i], i > 0 && m == MODE_FROZEN, lo, hi);
+    const bool st = (i > 0), ut = (i < N - 1);
+    const int T[6] = {Y_VX, Y_AX, Y_VY, Y_AY, Y_UX, Y_UY};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const bool act = (k < 4) ? st : ut;
+      w.bnd[(2 * k) * w.NB + i] = act ? hi[T[k]] : MQ_INF;
+      w.bnd[(2 * k + 1) * w.NB + i] = act ? lo[T[k]] : -MQ_INF;
+    }
+  }
+}
+
 // row of one polygon edge for point pt of the car in region j:
 // sign=+1: cross(P)/len <= 0 (obstacle, chosen edge); sign=-1: cross(P)/len >= 0 (environment)
 // points: 0 rear, 1 (xU,yU), 2 (xL,yU), 3 (xU,yL), 4 (xL,yL)
@@ -223,18 +245,17 @@ __device__ __forceinline__ void visit_rows(const WarpCtx &w, int i, Vis &v) {
   const int N = w.N;
   const unsigned char m = (i > 0) ? w.dec[p.off_mode + i] : (unsigned char)0;
   const int je = w.jeff[i];
-  double lo[8], hi[8];
-  stage_bounds(w, i, je, i > 0 && m == MODE_FROZEN, lo, hi);
-  const bool st = (i > 0), ut = (i < N - 1);
+  // bound rows: their right-hand sides are constants of the node (fill_stage_bounds), read from shared memory instead of being
+  // rebuilt from the per-plan tables in every pass of every iteration
   int slot = 0;
-#define MQ_BND(T, act)                                                        \
-  {                                                                           \
-    if ((act) && hi[T] < MQ_INF && w.mine(slot)) v.template bound<T>(slot, 1.0, hi[T]);       \
-    ++slot;                                                                   \
-    if ((act) && lo[T] > -MQ_INF && w.mine(slot)) v.template bound<T>(slot, -1.0, -lo[T]);    \
-    ++slot;                                                                   \
+#define MQ_BND(T)                                                                                  \
+  {                                                                                                \
+    if (w.mine(slot)) { const double h_ = w.bnd[slot * w.NB + i]; if (h_ < MQ_INF) v.template bound<T>(slot, 1.0, h_); }            \
+    ++slot;                                                                                        \
+    if (w.mine(slot)) { const double l_ = w.bnd[slot * w.NB + i]; if (l_ > -MQ_INF) v.template bound<T>(slot, -1.0, -l_); }         \
+    ++slot;                                                                                        \
   }
-  MQ_BND(Y_VX, st) MQ_BND(Y_AX, st) MQ_BND(Y_VY, st) MQ_BND(Y_AY, st) MQ_BND(Y_UX, ut) MQ_BND(Y_UY, ut)
+  MQ_BND(Y_VX) MQ_BND(Y_AX) MQ_BND(Y_VY) MQ_BND(Y_AY) MQ_BND(Y_UX) MQ_BND(Y_UY)
 #undef MQ_BND
   if (i == 0) return;
   // General rows: the sub-lanes of a stage walk every family in lockstep (item = k * sg + g), so that all
@@ -251,15 +272,25 @@ __device__ __forceinline__ void visit_rows(const WarpCtx &w, int i, Vis &v) {
   const double *ft = w.D + p.o_fronttab + 12 * (je >= 0 ? je : 0);
   if (p.E > 0) {
     const int ME = p.maxEnvEdges;
+    // item = pt * ME + ed, tracked incrementally (no division by the run-time ME); with one environment polygon -- the common
+    // case -- its edge range is read once per visit instead of once per row (two dependent table loads less in front of every row)
+    const bool single = (p.E == 1);
+    int e0s = 0, nes = 0;
+    if (single) { e0s = w.I[p.o_env_off]; nes = w.I[p.o_env_off + 1] - e0s; }
+    int pt = 0, ed = g;
+    while (ed >= ME) { ed -= ME; ++pt; }
 #pragma unroll 1
     for (int item = g; item < 5 * ME; item += sg) {
-      const int pt = item / ME, ed = item - pt * ME;
-      const int e = (p.E == 1) ? 0 : w.dec[p.off_env + i * 5 + pt];
-      const bool act = (e != UNDEC) && (pt == 0 || je >= 0);
-      if (!act) continue;
-      const int e0 = w.I[p.o_env_off + e];
-      const int ne = w.I[p.o_env_off + e + 1] - e0;
-      if (ed < ne) { edge_row(w.D + p.o_envtab + 3 * (e0 + ed), ft, pt, -1.0, a, rhs); v.general(slot + item, a, rhs); }
+      int e0 = e0s, ne = nes;
+      bool act = (pt == 0 || je >= 0);
+      if (!single) {
+        const int e = w.dec[p.off_env + i * 5 + pt];
+        act = act && (e != UNDEC);
+        if (act) { e0 = w.I[p.o_env_off + e]; ne = w.I[p.o_env_off + e + 1] - e0; }
+      }
+      if (act && ed < ne) { edge_row(w.D + p.o_envtab + 3 * (e0 + ed), ft, pt, -1.0, a, rhs); v.general(slot + item, a, rhs); }
+      ed += sg;
+      while (ed >= ME) { ed -= ME; ++pt; }
     }
     slot += 5 * ME;
   }
