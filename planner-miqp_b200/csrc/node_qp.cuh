@@ -729,7 +729,9 @@ struct SuspendIO {
 //   if pi_0' x_0 - sum |rho_i| U > h' lambda no such z' exists: returns true, the node is PROVEN infeasible.
 // else (kappa = 1): Lagrangian bound  f(z') >= f(z) - lambda'(h - G z) - sum_i |rho_i| range_i  for every feasible z'
 //   (L(., lambda) is convex, its gradient along the dynamics is rho, |u'_i - u_i| <= range_i), stored in *lb.
-__device__ __forceinline__ bool dual_check(const WarpCtx &w, const StepCtx &sc, bool farkas, double lmax, double *lb) {   // one call site (solve_node_qp)
+// (out of line and with its own copy of the context: it runs once per stalled or infeasible relaxation, and its row pass would
+// otherwise sit in the middle of the iteration loop's instruction stream)
+__device__ __noinline__ bool dual_check(const WarpCtx w, const StepCtx sc, bool farkas, double lmax, double *lb) {
   const DevProb &p = *w.p;
   const double *D = w.D;
   const int N = w.N;
