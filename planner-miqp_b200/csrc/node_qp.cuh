@@ -288,7 +288,7 @@ __device__ __forceinline__ void visit_rows(const WarpCtx &w, int i, Vis &v) {
         act = act && (e != UNDEC);
         if (act) { e0 = w.I[p.o_env_off + e]; ne = w.I[p.o_env_off + e + 1] - e0; }
       }
-      if (act && ed < ne) { edge_row(w.D + p.o_envtab + 3 * (e0 + ed), ft, pt, -1.0, a, rhs); v.general(slot + item, a, rhs); }
+      if (act && ed < ne) { edge_row(w.D + p.o_envtab + 3 * (e0 + ed), ft, pt, -1.0, a, rhs); v.edge(slot + item, a, rhs); }
       ed += sg;
       while (ed >= ME) { ed -= ME; ++pt; }
     }
@@ -300,7 +300,7 @@ __device__ __forceinline__ void visit_rows(const WarpCtx &w, int i, Vis &v) {
     const unsigned char d = w.dec[p.off_obs + (o * N + i) * 5 + pt];
     if (d != UNDEC && d != OBS_SOFT && (pt == 0 || je >= 0)) {
       edge_row(w.D + p.o_obstab + 3 * ((o * N + i) * p.L + d), ft, pt, 1.0, a, rhs);
-      v.general(slot + item, a, rhs);
+      v.edge(slot + item, a, rhs);
     }
   }
 }
@@ -331,6 +331,13 @@ __device__ __forceinline__ double dot6(const double a[6], const double y[8]) {
   return v;
 }
 
+// polygon-edge rows have no acceleration terms (edge_row: a[Y_AX] = a[Y_AY] = 0): four-term products, ten Hessian entries
+__device__ __forceinline__ double dot4(const double a[6], const double y[8]) {
+  double v = 0.0;
+  v += a[Y_PX] * y[Y_PX]; v += a[Y_VX] * y[Y_VX]; v += a[Y_PY] * y[Y_PY]; v += a[Y_VY] * y[Y_VY];
+  return v;
+}
+
 struct PassInit {  // cold: s = max(h - g.z, 1), lambda = 1; warm: s = max(h - g.z, smin), lambda = mu0 / s; gl = G' lambda
   RowIO io; double y[8]; double gl[8];
   double mu0, smin;   // mu0 <= 0: cold start
@@ -348,6 +355,7 @@ struct PassInit {  // cold: s = max(h - g.z, 1), lambda = 1; warm: s = max(h - g
 #pragma unroll
     for (int t = 0; t < 6; ++t) gl[t] += a[t] * lam;
   }
+  __device__ __forceinline__ void edge(int slot, const double a[6], double rhs) { general(slot, a, rhs); }
 };
 
 struct PassA {  // apply the pending step, residuals, Hessian and predictor gradient
@@ -392,6 +400,17 @@ struct PassA {  // apply the pending step, residuals, Hessian and predictor grad
 #pragma unroll
     for (int t = 0; t < 6; ++t) gx[t] += a[t] * wr;
   }
+  __device__ __forceinline__ void edge(int slot, const double a[6], double rhs) {
+    double wgt, wr;
+    core(slot, dot4(a, y), dot4(a, d), dot4(a, da), rhs, wgt, wr);
+    const double wpx = wgt * a[Y_PX], wvx = wgt * a[Y_VX], wpy = wgt * a[Y_PY], wvy = wgt * a[Y_VY];
+    // packed lower triangle, index r (r + 1) / 2 + c with (PX, VX, PY, VY) = (0, 1, 3, 4)
+    H[0] += wpx * a[Y_PX];
+    H[1] += wvx * a[Y_PX]; H[2] += wvx * a[Y_VX];
+    H[6] += wpy * a[Y_PX]; H[7] += wpy * a[Y_VX]; H[9] += wpy * a[Y_PY];
+    H[10] += wvy * a[Y_PX]; H[11] += wvy * a[Y_VX]; H[13] += wvy * a[Y_PY]; H[14] += wvy * a[Y_VY];
+    gx[Y_PX] += a[Y_PX] * wr; gx[Y_VX] += a[Y_VX] * wr; gx[Y_PY] += a[Y_PY] * wr; gx[Y_VY] += a[Y_VY] * wr;
+  }
 };
 
 struct PassD {  // affine step: ratios and the three sums that give mu_aff for any step length
@@ -410,6 +429,7 @@ struct PassD {  // affine step: ratios and the three sums that give mu_aff for a
   }
   template <int T> __device__ __forceinline__ void bound(int slot, double sgn, double rhs) { row(slot, sgn * y[T], sgn * da[T], rhs); }
   __device__ __forceinline__ void general(int slot, const double a[6], double rhs) { row(slot, dot6(a, y), dot6(a, da), rhs); }
+  __device__ __forceinline__ void edge(int slot, const double a[6], double rhs) { row(slot, dot4(a, y), dot4(a, da), rhs); }
 };
 
 struct PassE {  // corrector gradient
@@ -428,6 +448,10 @@ struct PassE {  // corrector gradient
     const double cf = coef(slot, dot6(a, y), dot6(a, da), rhs);
 #pragma unroll
     for (int t = 0; t < 6; ++t) gx[t] += a[t] * cf;
+  }
+  __device__ __forceinline__ void edge(int slot, const double a[6], double rhs) {
+    const double cf = coef(slot, dot4(a, y), dot4(a, da), rhs);
+    gx[Y_PX] += a[Y_PX] * cf; gx[Y_VX] += a[Y_VX] * cf; gx[Y_PY] += a[Y_PY] * cf; gx[Y_VY] += a[Y_VY] * cf;
   }
 };
 
@@ -448,12 +472,14 @@ struct PassG {  // step length of the combined step
   }
   template <int T> __device__ __forceinline__ void bound(int slot, double sgn, double rhs) { row(slot, sgn * y[T], sgn * d[T], sgn * da[T], rhs); }
   __device__ __forceinline__ void general(int slot, const double a[6], double rhs) { row(slot, dot6(a, y), dot6(a, d), dot6(a, da), rhs); }
+  __device__ __forceinline__ void edge(int slot, const double a[6], double rhs) { row(slot, dot4(a, y), dot4(a, d), dot4(a, da), rhs); }
 };
 
 struct PassViol {  // worst primal violation of the current point, largest multiplier
   RowIO io; double y[8]; double worst, lmax;
   template <int T> __device__ __forceinline__ void bound(int slot, double sgn, double rhs) { worst = fmax(worst, sgn * y[T] - rhs); lmax = fmax(lmax, io.ld(slot).y); }
   __device__ __forceinline__ void general(int slot, const double a[6], double rhs) { worst = fmax(worst, dot6(a, y) - rhs); lmax = fmax(lmax, io.ld(slot).y); }
+  __device__ __forceinline__ void edge(int slot, const double a[6], double rhs) { general(slot, a, rhs); }
 };
 
 struct PassDual {  // G' lambda, h' lambda and lambda' G z of a stage (multipliers after the pending step, scaled)
@@ -484,6 +510,7 @@ struct PassDual {  // G' lambda, h' lambda and lambda' G z of a stage (multiplie
 #pragma unroll
     for (int t = 0; t < 6; ++t) gl[t] += a[t] * lam;
   }
+  __device__ __forceinline__ void edge(int slot, const double a[6], double rhs) { general(slot, a, rhs); }
 };
 
 // ---------------------------------------------------------------------------------------
