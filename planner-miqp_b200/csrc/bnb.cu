@@ -601,6 +601,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? NODE_TEAMS_PER_SM : NW == 2
     const long pb = (long)s * st.cap;
     w.p = &p; w.N = p.N;
     w.sg = team_sublanes(p.N, nw); w.spw = 32 / w.sg; w.ls = lane / w.sg; w.g = lane - w.ls * w.sg;
+    { const int even = (p.N + nw - 1) / nw; if (even < w.spw) w.spw = even; }   // stages spread evenly over the warps (two warps, N = 40: 20 + 20, not 32 + 8)
     w.sgmul = 65536 / w.sg + 1; w.NP = team_row_stride(p.N, w.sg); w.kmax = st.kmax;
     double pen = 0.0;
     if (wid == 0) {
