@@ -47,6 +47,10 @@ INSTANCES = [
     ("two_cars_5_steps_close", "parallel_lanes", dict(n_cars=2, nr_steps=5, lane_offset=3.5)),
     ("two_cars_5_steps_slack", "parallel_lanes", dict(n_cars=2, nr_steps=5, lane_offset=4.5)),
     ("two_cars_6_steps_stagger", "parallel_lanes", dict(n_cars=2, nr_steps=6, lane_offset=4.8, stagger=1.0)),
+    ("config2_seed7_n14", "obstacle_scenario", dict(seed=7, nr_regions=32, nr_steps=14)),
+    ("config2_seed11_n12", "obstacle_scenario", dict(seed=11, nr_regions=32, nr_steps=12)),
+    ("three_cars_5_steps", "parallel_lanes", dict(n_cars=3, nr_steps=5, lane_offset=4.5)),
+    ("two_cars_8_steps_stagger", "parallel_lanes", dict(n_cars=2, nr_steps=8, lane_offset=4.8, stagger=1.0)),
 ]
 
 
