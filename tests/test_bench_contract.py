@@ -28,3 +28,29 @@ def test_device_arm_refuses_to_run_without_a_gpu():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0", "--batch", "2"],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_both_arms_share_one_config_object_and_every_workload_refuses_without_gpu():
+    """`config` must be identical in the GPU arm and the reference arm (the driver compares them); what differs per run lives in
+    `run`.  The multi-agent workloads have no CPU fallback either."""
+    import importlib.util
+    import torch
+    spec = importlib.util.spec_from_file_location("_bench_mod", os.path.join(ROOT, "bench.py"))
+    # bench.py redirects fd 1 at import: load it in a child process instead and ask for the config there
+    code = ("import json, os, sys, importlib.util; "
+            f"spec = importlib.util.spec_from_file_location('b', {os.path.join(ROOT, 'bench.py')!r}); "
+            "b = importlib.util.module_from_spec(spec); spec.loader.exec_module(b); "
+            "h = b.gap_histogram([type('I', (), dict(status=0, gap=g))() for g in (0.0, 5e-5, 5e-4, 0.05, 0.5, 3.0)] + "
+            "[type('I', (), dict(status=1, gap=float('nan')))()], 1e-4); "
+            "b.emit({'config': b.bench_config(2048), 'hist': h, 'workloads': sorted(b.WORKLOADS)})")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert set(d["config"]) == {"workload", "plans_per_gpu_per_step", "gap", "seeds", "cache"} and d["config"]["plans_per_gpu_per_step"] == 2048
+    assert d["hist"] == {"<=0.0001": 2, "<=1e-3": 1, "<=1e-2": 0, "<=1e-1": 1, "<=1": 1, ">1": 1, "no incumbent": 1}
+    assert d["workloads"] == ["config3", "config4", "config5"]
+    if not torch.cuda.is_available():
+        for wl in ("config3", "config4", "config5"):
+            rr = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", wl, "--steps", "1", "--warmup", "0"],
+                                capture_output=True, text=True, timeout=600)
+            assert rr.returncode != 0 and "no CPU fallback" in (rr.stderr + rr.stdout), wl
