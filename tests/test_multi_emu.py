@@ -40,3 +40,26 @@ def test_collision_rows_and_slacks(cars, steps, offset, stagger):
     assert r["status"] == 0
     assert r["objective"] == pytest.approx(io.objective, rel=1e-6, abs=1e-7)
     assert abs(r["bound"] - r["objective"]) <= 1e-4 * abs(r["objective"]) + 1e-9
+
+
+def test_completion_heuristic_keeps_results_and_finds_incumbents_early(monkeypatch):
+    """multi-car plans without incumbent also try the completion of a node by the least violated alternatives (bnb_multi.cu;
+    here the emulation's EMU_HEUR): a redundant, fully decided node -- optima and bounds are unchanged, and a joint plan with
+    dozens of violated collision disjunctions gets its first incumbent within a node budget that a plain dive exhausts"""
+    from planner_miqp_b200.scenarios import intersection
+    for args in ((2, 5, 3.5, 0.0), (2, 6, 4.8, 1.0)):
+        p = parallel_lanes(args[0], args[1], args[2], stagger=args[3]).build()
+        monkeypatch.setenv("EMU_HEUR", "0")
+        r0 = emu.solve(p, 1e-4, 60.0)
+        monkeypatch.setenv("EMU_HEUR", "1")
+        r1 = emu.solve(p, 1e-4, 60.0)
+        assert r0["status"] == r1["status"] == 0
+        assert r1["objective"] == pytest.approx(r0["objective"], rel=1e-9)
+        assert abs(r1["bound"] - r1["objective"]) <= 1e-4 * abs(r1["objective"]) + 1e-9
+    p = intersection(0, n_cars=6, nr_steps=10).build()
+    monkeypatch.setenv("EMU_HEUR", "0")
+    plain = emu.solve(p, 1e-4, 120.0, max_nodes=60)
+    monkeypatch.setenv("EMU_HEUR", "1")
+    heur = emu.solve(p, 1e-4, 120.0, max_nodes=60)
+    assert heur["status"] == 0 and heur["objective"] < float("inf")
+    assert plain["status"] != 0 or plain["objective"] >= heur["objective"] - 1e-9 or plain["nodes"] >= heur["nodes"]
