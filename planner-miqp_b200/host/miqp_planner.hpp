@@ -13,10 +13,11 @@
 //
 // Geometry types: BARK / boost.geometry are not part of this build.  Reference lines are
 // poly-lines (PolyLine), polygons are (k, 2) vertex matrices.  The drivable area may be given
-// as a convex polygon (shrunk by the collision radius, one cell) or as a ready convex
-// decomposition (SetConvexEnvironmentCells); decomposing a NON-convex road polygon
-// (common/map/convexified_map.cpp, Voronoi + merging) is outside the hot path and not rebuilt:
-// UpdateConvexifiedMap returns false for such input.
+// as a road polygon -- convex (shrunk by the collision radius, one cell) or non-convex
+// (decomposed by host/convexified_map.hpp: ear clipping + Hertel-Mehlhorn merging, boundary
+// edges moved inwards; the reference: common/map/convexified_map.cpp) -- or as a ready convex
+// decomposition (SetConvexEnvironmentCells).  A polygon that cannot be decomposed makes
+// UpdateConvexifiedMap return false and Plan() refuse to run (fail closed).
 #pragma once
 #include <array>
 #include <cmath>
@@ -64,7 +65,7 @@ class MiqpPlanner {
   void RemoveObstacle(int id);        // throws NotImplementedException, like the reference
   void RemoveAllObstacles();
 
-  bool UpdateConvexifiedMap(const MatrixXd &mapPolygon);                 // convex polygons only (see above)
+  bool UpdateConvexifiedMap(const MatrixXd &mapPolygon);                 // convex or non-convex road polygon (see above)
   void SetConvexEnvironmentCells(const std::vector<MatrixXd> &cells);   // already shrunk, convex, any orientation
 
   bool Plan(double timestamp = 0.0);
