@@ -569,27 +569,44 @@ def main():
     # ---- two batches in flight (two solver instances, two streams) ---------------------------
     # the tail rounds of one batch (a few hard plans, a near-empty GPU) overlap with the head rounds of the next one;
     # device time from the first launch to the last completion on either stream (CUDA events on the solvers' streams)
+    def agree(flag: bool) -> bool:
+        """True only if `flag` holds on every rank (keeps the collectives below in step when one rank fails a leg)"""
+        if world == 1:
+            return bool(flag)
+        t = torch.tensor([1.0 if flag else 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return float(t.item()) > 0.5
+
     pipe = None
     pipe_ms = None
     if args.in_flight > 1 and S > 1 and args.steps > 1:
+        ok = True
+        stagger = 0.5e-3 * seq_ms_per_step * (args.in_flight / 2.0)
         try:
             pipe = P.PipelinedSolver(device=local_rank, depth=args.in_flight, nodes_per_round=args.nodes_per_round)
             pipe.upload_resident([prepared[shard_ids[k % S]] for k in range(args.in_flight)])
-            stagger = 0.5e-3 * seq_ms_per_step * (args.in_flight / 2.0)
             pipe.run_resident(max(args.warmup, args.in_flight), stagger)
-            barrier()
-            pipe_ms, pipe_runs = pipe.timed_resident(args.steps, stagger)
-            barrier()
-            launches_pipe = int(sum(s_.run_stats()["launches"] for s_ in pipe.solvers) / len(pipe.solvers) * args.steps)
         except Exception as ex:     # (e.g. not enough memory for a second node pool): the sequential figures stand
             sys.stderr.write(f"[bench] pipelined leg failed: {ex}\n")
-            pipe, pipe_ms = None, None
-    if world > 1:
-        t = torch.tensor([pipe_ms if pipe_ms is not None else -1.0], dtype=torch.float64, device="cuda")
-        tmin = t.clone()
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
-        pipe_ms = float(t.item()) if float(tmin.item()) > 0 else None
+            ok = False
+        if agree(ok):
+            barrier()
+            try:
+                pipe_ms, pipe_runs = pipe.timed_resident(args.steps, stagger)
+                launches_pipe = int(sum(s_.run_stats()["launches"] for s_ in pipe.solvers) / len(pipe.solvers) * args.steps)
+            except Exception as ex:
+                sys.stderr.write(f"[bench] pipelined leg failed: {ex}\n")
+                pipe_ms = None
+            barrier()
+        if world > 1:
+            t = torch.tensor([pipe_ms if pipe_ms is not None else -1.0], dtype=torch.float64, device="cuda")
+            tmin = t.clone()
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+            pipe_ms = float(t.item()) if float(tmin.item()) > 0 else None
+        if pipe_ms is None and pipe is not None:      # (on every rank alike)
+            pipe.close()
+            pipe = None
     value_pipe = world * B * args.steps / (pipe_ms * 1e-3) if pipe_ms else None
     use_pipe = value_pipe is not None and value_pipe > value_seq
     value = value_pipe if use_pipe else value_seq
@@ -638,26 +655,30 @@ def main():
     e2e_seq_ms = 1e3 * e2e_s / args.steps
     # the same calls with two batches in flight: pack + H2D of one batch and D2H + scatter of the other overlap with the search
     e2e_pipe = None
-    if pipe is not None:
+    if pipe is not None:          # (the same on every rank, see above)
+        jobs = [prepared[shard_ids[k % S]] for k in range(args.steps)]
+        ok = True
         try:
-            jobs = [prepared[shard_ids[k % S]] for k in range(args.steps)]
             pipe.solve_stream_compact(jobs[:args.in_flight], 0.5e-3 * e2e_seq_ms)
-            barrier()
-            t0 = time.perf_counter()
-            pipe.solve_stream_compact(jobs, 0.5e-3 * e2e_seq_ms)
-            e2e_pipe_s = time.perf_counter() - t0
-            barrier()
-            if world > 1:
-                t = torch.tensor([e2e_pipe_s], dtype=torch.float64, device="cuda")
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                e2e_pipe_s = float(t.item())
-            e2e_pipe = world * B * args.steps / e2e_pipe_s
         except Exception as ex:
             sys.stderr.write(f"[bench] pipelined end-to-end leg failed: {ex}\n")
-        if world > 1:
-            t = torch.tensor([e2e_pipe if e2e_pipe is not None else -1.0], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MIN)
-            e2e_pipe = e2e_pipe if float(t.item()) > 0 else None
+            ok = False
+        if agree(ok):
+            barrier()
+            t0 = time.perf_counter()
+            try:
+                pipe.solve_stream_compact(jobs, 0.5e-3 * e2e_seq_ms)
+            except Exception as ex:
+                sys.stderr.write(f"[bench] pipelined end-to-end leg failed: {ex}\n")
+                ok = False
+            e2e_pipe_s = time.perf_counter() - t0
+            barrier()
+            if agree(ok):
+                if world > 1:
+                    t = torch.tensor([e2e_pipe_s], dtype=torch.float64, device="cuda")
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    e2e_pipe_s = float(t.item())
+                e2e_pipe = world * B * args.steps / e2e_pipe_s
     if e2e_pipe is not None and e2e_pipe > e2e_seq:
         e2e_value, e2e_s = e2e_pipe, e2e_pipe_s
     else:
