@@ -498,6 +498,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     import planner_miqp_b200 as P
+    if world > 1:
+        # one process per GPU and several batches in flight per process share the host cores: keep the packing threads of all of
+        # them within the core count (8 ranks x 3 batches x 8 threads on 16 cores otherwise)
+        os.environ.setdefault("MIQP_PACK_THREADS", str(max(1, min(8, (os.cpu_count() or 8) // (world * max(args.in_flight, 1))))))
     B = args.batch
     S = max(1, min(args.shards, args.steps))
     shard_ids = [args.first_shard + rank + k * world for k in range(S)]          # rank r: shards r, r + world, ...

@@ -145,7 +145,9 @@ void pack_batch(MiqpB200Solver *s, const MiqpB200Problem *problems, int count) {
   s->time_limits.clear();
   for (int k = 0; k < count; ++k) s->time_limits.push_back(problems[k].time_limit);
   const int hw = (int)std::thread::hardware_concurrency();
-  const int nthr = std::max(1, std::min(std::min(8, hw > 0 ? hw : 1), count / 128));
+  int cap = 8;   // packing threads; MIQP_PACK_THREADS lowers it when several processes / solver instances share the host cores
+  if (const char *e = std::getenv("MIQP_PACK_THREADS")) cap = std::max(1, std::min(8, atoi(e)));
+  const int nthr = std::max(1, std::min(std::min(cap, hw > 0 ? hw : 1), count / 128));
   if (nthr == 1) {
     for (int k = 0; k < count; ++k) {
       std::string v = validate(problems[k]);
