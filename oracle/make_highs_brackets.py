@@ -51,6 +51,8 @@ INSTANCES = [
     ("config2_seed11_n12", "obstacle_scenario", dict(seed=11, nr_regions=32, nr_steps=12)),
     ("three_cars_5_steps", "parallel_lanes", dict(n_cars=3, nr_steps=5, lane_offset=4.5)),
     ("two_cars_8_steps_stagger", "parallel_lanes", dict(n_cars=2, nr_steps=8, lane_offset=4.8, stagger=1.0)),
+    ("config2_seed3_n16", "obstacle_scenario", dict(seed=3, nr_regions=32, nr_steps=16)),
+    ("config2_seed0_n20", "obstacle_scenario", dict(seed=0, nr_regions=32, nr_steps=20)),
 ]
 
 
@@ -86,7 +88,7 @@ def separable_objective(p):
     return q, c, f0
 
 
-def bracket(p, rel=2e-3, max_iter=40, time_limit=300.0, verbose=False):
+def bracket(p, rel=2e-3, max_iter=40, time_limit=900.0, verbose=False):
     rowptr, cols, vals, lo, hi = O.build_rows(p)
     nrows, n = len(lo), O.layout(p).ncols
     A = sp.csr_matrix((vals, cols, rowptr), shape=(nrows, n))
