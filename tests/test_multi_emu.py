@@ -63,3 +63,19 @@ def test_completion_heuristic_keeps_results_and_finds_incumbents_early(monkeypat
     heur = emu.solve(p, 1e-4, 120.0, max_nodes=60)
     assert heur["status"] == 0 and heur["objective"] < float("inf")
     assert plain["status"] != 0 or plain["objective"] >= heur["objective"] - 1e-9 or plain["nodes"] >= heur["nodes"]
+
+
+def test_bounds_of_two_independent_searches_bracket_each_other_on_hard_multi_car_plans():
+    """plans that neither search proves within its budget (active collision rows, slack-paying merges): if both keep sound books,
+    the best bound of one can never exceed the incumbent of the other (the multi-car kernel used to score stalled
+    relaxations with an upper bound)"""
+    from planner_miqp_b200.scenarios import two_agent_merge, random_scenario
+    cases = [two_agent_merge(0, nr_steps=8).build(), two_agent_merge(1, nr_steps=10).build(), random_scenario(23, nr_steps=12).build()]
+    for p in cases:
+        r = emu.solve(p, 1e-4, 30.0, max_nodes=1200)
+        xo, io = O.solve(p, gap_tol=1e-4, time_limit=8.0)
+        assert r["status"] == 0 and io.status == 0
+        tol = 1e-7 * max(1.0, abs(io.objective))
+        assert r["bound"] <= io.objective + tol, (r["bound"], io.objective)
+        assert io.best_bound <= r["objective"] + tol, (io.best_bound, r["objective"])
+        assert r["bound"] <= r["objective"] + tol and io.best_bound <= io.objective + tol
