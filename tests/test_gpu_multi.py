@@ -104,3 +104,19 @@ def test_random_scenarios_of_config4(solver):
             xo, io = O.solve(p, gap_tol=1e-4, time_limit=60)
             if io.proven:
                 assert info.objective == pytest.approx(io.objective, rel=1e-6, abs=1e-7)
+
+
+def test_device_and_oracle_bounds_bracket_each_other_on_unproven_plans(solver):
+    """hard multi-car plans stop at the time limit in both searches; sound books mean: nobody's best bound exceeds the other's
+    incumbent, and the device's incumbent is feasible for the big-M model"""
+    ps = [two_agent_merge(0, nr_steps=8).build(), two_agent_merge(1, nr_steps=10).build(), random_scenario(23, nr_steps=12).build()]
+    xs, infos = solver.solve_batch(ps, gap_tol=1e-4, time_limit=2.0)
+    for p, x, i in zip(ps, xs, infos):
+        xo, io = O.solve(p, gap_tol=1e-4, time_limit=8.0)
+        assert i.status == 0 and io.status == 0
+        tol = 1e-7 * max(1.0, abs(io.objective))
+        assert i.best_bound <= io.objective + tol, (i.best_bound, io.objective)
+        assert io.best_bound <= i.objective + tol, (io.best_bound, i.objective)
+        viol, worst = O.max_violation(p, x)
+        assert viol <= 1e-6, (viol, worst)
+        assert O.objective(p, x) == pytest.approx(i.objective, rel=1e-9, abs=1e-9)
